@@ -1,0 +1,258 @@
+#!/usr/bin/env python
+"""bench.py -- encode+decode throughput of the lossless LiDAR geometry codec hot path on B200.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line on
+rank 0.  A "step" = compress + decompress of `--frames` synthetic KITTI-shaped scans (S2 "lidar-120k",
+SURVEY.md 8d) per GPU through models/convolutional/lossl_coord_int's B200-native twin
+(fastpcc_b200.lossl_coord_int.Model, default 256-channel config).  Frames are independent, so ranks share
+nothing: weak scaling, no data-path collective; the only collectives are the barrier and the max-over-ranks
+of the timed region.
+
+  value     Mpts/s with the voxelised frames already resident in HBM (CUDA events, max over ranks)
+  e2e       same metric through the public API from HOST buffers: H2D of the coordinates, D2H of the
+            bitstream, H2D of the bitstream, D2H of the decoded coordinates, all inside the timed region
+  roofline  the tcgen05 sparse-conv kernel: algorithmic int8 OPs (2*pairs*Cin*Cout) / its CUDA-event time
+  cpu_baseline  the CPU oracle (numpy port of the reference path) on a bounded sample of the same workload
+
+`--impl reference` times the reference's CPU implementation of the path (the oracle port; the reference's
+own GPU path needs MinkowskiEngine/torchsparse/CUTLASS-fork, none installable offline) on the host cores.
+"""
+import argparse
+import json
+import os
+import os.path as osp
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = osp.dirname(osp.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(channels=256, max_stride_wo_recurrent=2048, max_stride=8192, fea_stride=16)
+WORKLOAD = 'lossl_coord_int LiDAR lossless (KITTI-shaped synthetic scans ~120k pts/frame, 16-bit grid, C=256)'
+
+
+def load_peaks():
+    p = osp.join(ROOT, 'MEASURED_PEAKS.json')
+    if osp.isfile(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, 'measured'
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback'
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons of one GPU during the timed region."""
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([v.strip() for v in out.split(',')])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith('active') for s in self.samples)]
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.samples[0][1]), 'reasons': reasons,
+                'samples': len(sm), 'power_w_max': max(float(s[2]) for s in self.samples)}
+
+
+def make_frames(n, rank):
+    from fastpcc_b200 import synth
+    return [synth.with_batch(synth.lidar_frame(1000 + rank * 1000 + i)) for i in range(n)]
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU restatement of the reference path, all host threads, bounded sample."""
+    if rank != 0:
+        return
+    from fastpcc_b200 import synth
+    from oracle.lossl_coord_int import Model as OracleModel
+    cores = os.cpu_count()
+    sd = synth.make_lossl_int_state_dict(seed=7, **CFG)
+    model = OracleModel(sd, **CFG)
+    frame = make_frames(1, 0)[0]
+    sample = frame[:: args.cpu_stride]
+    times = []
+    for i in range(args.warmup + args.steps):
+        t = time.perf_counter()
+        data = model.compress(sample)
+        rec = model.decompress(data)
+        dt = time.perf_counter() - t
+        assert rec.shape[0] == sample.shape[0]
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    v = sample.shape[0] / (ms * 1e-3) / 1e6
+    desc = f'1 frame of the workload subsampled 1:{args.cpu_stride} ({sample.shape[0]} pts), compress+decompress, numpy/BLAS on {cores} threads'
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'encode+decode Mpts/s', 'value': v, 'unit': 'Mpts/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'int8', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'frames_per_step': 1, 'sample': desc},
+        'cpu_baseline': {'value': v, 'unit': 'Mpts/s', 'cores': cores, 'kind': 'port', 'sample': desc},
+        'e2e': {'value': v, 'unit': 'Mpts/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--frames', type=int, default=2, help='frames per step per GPU')
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--cpu-stride', type=int, default=8, help='subsampling of the CPU baseline sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+
+    rank = int(os.environ.get('RANK', 0))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from fastpcc_b200 import _lib, ops, synth
+    from fastpcc_b200.lossl_coord_int import Config, Model
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback exists)'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    _lib.load(build_if_missing=False)
+
+    sd = synth.make_lossl_int_state_dict(seed=7, **CFG)
+    model = Model(Config(**CFG), device=dev).load_numpy_state_dict(sd).to(dev)
+    frames_host = make_frames(args.frames, rank)
+    pinned = [torch.from_numpy(f).pin_memory() for f in frames_host]
+    frames_dev = [p.to(dev) for p in pinned]
+    n_pts = sum(f.shape[0] for f in frames_host)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step_device():
+        for x in frames_dev:
+            data = model.compress(x)
+            rec = model.decompress(data)
+        return rec
+
+    h2d = d2h = 0
+
+    def step_e2e():
+        nonlocal h2d, d2h
+        h2d = d2h = 0
+        for p in pinned:
+            x = p.to(dev, non_blocking=True)
+            data = model.compress(x)          # bytes on the host: D2H of the bitstream inside
+            rec = model.decompress(data)      # H2D of the bitstream inside
+            rec_h = rec.cpu()                 # D2H of the decoded coordinates
+            h2d += p.numel() * 4 + len(data)
+            d2h += len(data) + rec_h.numel() * 4
+        return rec_h
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, sample_clocks=False):
+        for _ in range(warmup):
+            fn()
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        barrier()
+        total_ms = 0.0
+        for _ in range(steps):
+            flush.fill_(1)  # evict L2 between timed iterations
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            total_ms += e0.elapsed_time(e1)
+        barrier()
+        clocks = sampler.summary() if sampler else None
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps, clocks
+
+    ms_dev, clocks = timed(step_device, args.steps, args.warmup, sample_clocks=True)
+    ms_e2e, _ = timed(step_e2e, args.steps, 1)
+    pts_all = torch.tensor([n_pts], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(pts_all)
+    pts_all = float(pts_all.item())
+
+    # ---- instrumented pass: CUDA-event time and algorithmic work of every GEMM-class launch -------------
+    prof = ops.enable_profile(True)
+    step_device()
+    torch.cuda.synchronize()
+    ops.enable_profile(False)
+    stats = ops.profile_summary(prof)
+    peaks, peak_kind = load_peaks()
+    int8_peak = 2.0 * peaks['bf16_tflops']  # kind::i8 runs at twice the bf16 rate; measured bf16 burst x 2
+    conv = stats.get('spconv_tc', {'ms': 0.0, 'ops': 0.0, 'launches': 0, 'mma_ops': 0.0})
+    roof = {'bound': 'tensor', 'kernel': 'igemm_tc_kernel<conv> (tcgen05.mma.kind::i8)',
+            'achieved': (conv['ops'] / (conv['ms'] * 1e-3) / 1e12) if conv['ms'] else 0.0,
+            'peak': int8_peak, 'unit': 'TOP/s', 'traffic': None,
+            'peak_source': f'2 x bf16_tflops of MEASURED_PEAKS.json ({peak_kind})',
+            'launches': conv['launches'], 'ms_per_step': conv['ms'],
+            'executed_mma_tops': (conv['mma_ops'] / (conv['ms'] * 1e-3) / 1e12) if conv['ms'] else 0.0,
+            'share_of_step': conv['ms'] / ms_dev if ms_dev else 0.0}
+    roof['frac'] = roof['achieved'] / roof['peak'] if roof['peak'] else 0.0
+    launches = sum(v['launches'] for v in stats.values())
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle.lossl_coord_int import Model as OracleModel
+        om = OracleModel(sd, **CFG)
+        sample = frames_host[0][:: args.cpu_stride]
+        t = time.perf_counter()
+        rec = om.decompress(om.compress(sample))
+        dt = time.perf_counter() - t
+        assert rec.shape[0] == sample.shape[0]
+        cpu = {'value': sample.shape[0] / dt / 1e6, 'unit': 'Mpts/s', 'cores': os.cpu_count(), 'kind': 'port',
+               'sample': f'frame 0 subsampled 1:{args.cpu_stride} ({sample.shape[0]} pts), compress+decompress once, numpy/BLAS oracle'}
+
+    if rank == 0:
+        print(json.dumps({
+            'metric': 'encode+decode Mpts/s', 'value': pts_all / (ms_dev * 1e-3) / 1e6, 'unit': 'Mpts/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_dev,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int8', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'frames_per_step_per_gpu': args.frames, 'points_per_step': pts_all,
+                       'l2': 'flushed between timed iterations (256 MB write)', 'weights': 'seeded random int8 (seed 7)'},
+            'clocks': clocks,
+            'e2e': {'value': pts_all / (ms_e2e * 1e-3) / 1e6, 'unit': 'Mpts/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'ms_per_step': ms_e2e},
+            'gpu_launches': launches * args.steps,
+            'roofline': roof, 'cpu_baseline': cpu,
+            'kernels': {k: {'ms': round(v['ms'], 3), 'launches': v['launches']} for k, v in stats.items()},
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

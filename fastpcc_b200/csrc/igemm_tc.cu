@@ -1,0 +1,464 @@
+// tcgen05 (5th-gen tensor core) int8 implicit GEMM for sm_100a: the hot kernel of the codec.
+//
+//   D[128 x N] (int32, TMEM)  +=  A[128 x 128B] (smem, gathered rows)  x  W[N x 128B]^T (smem, TMA)
+//
+// One CTA owns a tile of 128 output rows and up to 256 output channels; the accumulator lives in
+// tensor memory for the whole tile, so a sparse convolution is OUTPUT-STATIONARY: all kernel offsets
+// that have at least one neighbour in the tile are accumulated by `tcgen05.mma.kind::i8` before a
+// single fused epilogue (bias + Q6.25 PReLU + requant [+ residual + PReLU]) writes int8 / Q8.23 once.
+// No atomics, no int32 round trip through HBM, deterministic.
+//
+// Warp roles (192 threads):
+//   warps 0-3  gather producers: one output row each; 16-byte cp.async with zero-fill for missing
+//              neighbours, written straight into the 128B-swizzled K-major layout the MMA expects;
+//              afterwards the same four warps run the epilogue (TMEM lane quarter = warp id).
+//   warp 4     weight producer: one TMA box (N x 128 B, SWIZZLE_128B) per pipeline stage.
+//   warp 5     TMEM allocation + the single MMA-issuing thread.
+// smem stages hand over through mbarriers (full: 128 gather arrivals + TMA transaction bytes; empty:
+// tcgen05.commit); the accumulator hands over to the epilogue through one more mbarrier.
+//
+// Two front-ends share the kernel: MODE_CONV reads the k-major neighbour table of coords.cu, MODE_PAIRS
+// reads (in,out) pair lists grouped by weight block (dense linear, occupied-children linear).
+//
+// Replaces lib/int_sparse_conv/src/gather_gemm_scatter.cu:11-144 / gemm.cu:11-127 (CUTLASS 2.x
+// mma.sync m16n8k32, one launch per kernel offset, read-modify-write of D per offset) plus the separate
+// element-wise epilogue kernels of src/element_wise/*.cu.
+#include <cuda.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "common.cuh"
+
+namespace fpcc {
+
+constexpr int TC_M = 128;         // rows per tile (UMMA M)
+constexpr int TC_KB = 128;        // K bytes per stage (one 128B swizzle atom)
+constexpr int TC_MAX_KVOL = 32;   // offsets tracked by the per-tile activity mask
+constexpr int TC_THREADS = 192;
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra.uni WAIT_DONE;\n\t"
+        "bra.uni WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+
+// SM100 shared-memory matrix descriptor, K-major, SWIZZLE_128B: 8-row groups are 1024 B apart (SBO),
+// the leading-dimension offset is unused for a single 128 B atom along K.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);  // start address, bits [0,14)
+    d |= (uint64_t)(1024u >> 4) << 32;             // stride byte offset, bits [32,46)
+    d |= (uint64_t)1 << 46;                        // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                        // layout type: SWIZZLE_128B
+    return d;
+}
+// kind::i8 instruction descriptor: D = s32, A = B = s8, both K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t umma_idesc_i8(int n) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------
+struct TcArgs {
+    // common
+    const int8_t *A;   // activations [*, K]
+    int K;             // contraction bytes (C_in), multiple of 16
+    int N;             // output channels of one weight block (C_out)
+    int n_tile;        // channels per CTA: multiple of 16, <= 256
+    int tmem_cols;     // power of two >= n_tile, >= 32
+    // MODE_CONV
+    const int32_t *nbr;
+    int64_t ld;
+    int n_out, kvol;
+    // MODE_PAIRS
+    const int32_t *in_idx, *out_idx, *offsets;
+    int n_groups, n_pairs, bias_per_group;
+};
+
+template <int STAGES>
+struct TcSmem {
+    static constexpr int a_bytes = TC_M * TC_KB;
+    static size_t bytes(int n_tile, int kvol_rows) {
+        return 1024 + (size_t)STAGES * (a_bytes + (size_t)n_tile * TC_KB) + (size_t)kvol_rows * TC_M * 4 + 256;
+    }
+};
+
+template <int MODE, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1) igemm_tc_kernel(TcArgs a, const __grid_constant__ CUtensorMap tmap_w,
+                                                                 EpiParams ep, void *__restrict__ out) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int b_bytes = a.n_tile * TC_KB;
+    uint8_t *sA = smem;
+    uint8_t *sB = smem + STAGES * TcSmem<STAGES>::a_bytes;
+    int32_t *rows_s = (int32_t *)(sB + (size_t)STAGES * b_bytes);  // CONV: [kvol][128] source rows; PAIRS: [2][128] src,dst
+    const int rows_k = MODE == 0 ? a.kvol : 2;
+    uint64_t *bars = (uint64_t *)(rows_s + rows_k * TC_M);
+    uint64_t *full = bars, *empty = bars + STAGES, *tmem_full = bars + 2 * STAGES;
+    uint32_t *tmem_ptr = (uint32_t *)(bars + 2 * STAGES + 1);
+    uint32_t *kmask = tmem_ptr + 1;
+    int32_t *tile_info = (int32_t *)(kmask + 1);  // PAIRS: group, begin, end
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.x * TC_M, n0 = blockIdx.y * a.n_tile;
+
+    if (tid == 0) {
+        *kmask = 0;
+        if (MODE == 1) {
+            int g = 0, begin = blockIdx.x * TC_M, end = a.n_pairs;
+            if (a.offsets) {
+                int t = blockIdx.x;
+                begin = end = -1;
+                for (g = 0; g < a.n_groups; ++g) {
+                    int lo = a.offsets[g], hi = a.offsets[g + 1];
+                    int nt = (hi - lo + TC_M - 1) / TC_M;
+                    if (t < nt) { begin = lo + t * TC_M; end = hi; break; }
+                    t -= nt;
+                }
+            }
+            tile_info[0] = g; tile_info[1] = begin; tile_info[2] = end;
+        }
+    }
+    if (warp == 5 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], TC_M + 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+    __syncthreads();
+    if (MODE == 1 && (tile_info[1] < 0 || tile_info[1] >= tile_info[2])) return;  // block beyond the last tile
+
+    if (warp == 5) {  // TMEM allocation (whole warp), address lands in smem
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"((uint32_t)a.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // source rows of this tile -> smem, plus the mask of kernel offsets that have any neighbour
+    if (tid < TC_M) {
+        if (MODE == 0) {
+            int m = m0 + tid;
+            uint32_t mine = 0;
+            for (int k = 0; k < a.kvol; ++k) {
+                int32_t v = m < a.n_out ? __ldg(&a.nbr[(int64_t)k * a.ld + m]) : 0;
+                rows_s[k * TC_M + tid] = v - 1;
+                mine |= (v != 0) << k;
+            }
+            mine = __reduce_or_sync(0xffffffffu, mine);
+            if (lane == 0 && mine) atomicOr(kmask, mine);
+        } else {
+            int p = tile_info[1] + tid;
+            bool ok = p < tile_info[2];
+            rows_s[tid] = ok ? (a.in_idx ? __ldg(&a.in_idx[p]) : p) : -1;
+            rows_s[TC_M + tid] = ok ? (a.out_idx ? __ldg(&a.out_idx[p]) : p) : -1;
+            if (tid == 0) *kmask = 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t active = *kmask;
+    const int nk = __popc(active);
+    const int n_chunks = (a.K + TC_KB - 1) / TC_KB;
+    const int total = nk * n_chunks;
+    const int group = MODE == 1 ? tile_info[0] : 0;
+
+    if (warp < 4) {
+        // ================= gather producers =================
+        const int r = tid;
+        const uint32_t row_smem = r * TC_KB;
+        const uint32_t sw = r & 7;
+        uint32_t rem = active;
+        int k = -1;
+        for (int i = 0; i < total; ++i) {
+            const int kc = i % n_chunks;
+            if (kc == 0) { k = __ffs(rem) - 1; rem &= rem - 1; }
+            const int stage = i % STAGES;
+            mbar_wait(&empty[stage], ((i / STAGES) & 1) ^ 1);
+            const int32_t src = rows_s[(MODE == 0 ? k : 0) * TC_M + r];
+            const int8_t *gsrc = a.A + (src >= 0 ? (int64_t)src * a.K : 0) + kc * TC_KB;
+            const uint32_t dst = smem_u32(sA + stage * TcSmem<STAGES>::a_bytes) + row_smem;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const bool ok = src >= 0 && kc * TC_KB + c * 16 < a.K;
+                cp_async16(dst + ((c ^ sw) << 4), ok ? (const void *)(gsrc + c * 16) : (const void *)a.A, ok ? 16u : 0u);
+            }
+            cp_async_commit();
+            if (i >= STAGES - 1) {
+                cp_async_wait<STAGES - 1>();
+                fence_proxy_async();
+                mbar_arrive(&full[(i - (STAGES - 1)) % STAGES]);
+            }
+        }
+        cp_async_wait<0>();
+        fence_proxy_async();
+        for (int i = max(total - (STAGES - 1), 0); i < total; ++i) mbar_arrive(&full[i % STAGES]);
+
+        // ================= epilogue =================
+        if (total > 0) {
+            mbar_wait(tmem_full, 0);
+            tc_fence_after();
+        }
+        const int64_t m = MODE == 0 ? (int64_t)(m0 + r) : (int64_t)rows_s[TC_M + r];
+        const bool row_ok = MODE == 0 ? (m < a.n_out) : (m >= 0);
+        const bool has_slope = ep.slope != nullptr, has_post = ep.post_slope != nullptr;
+        const int32_t slope = has_slope ? ep.slope[0] : 0, post = has_post ? ep.post_slope[0] : 0;
+        const int64_t zp = ep.zp[0];
+        const int pbase = (MODE == 1 && a.bias_per_group) ? group * a.N : 0;
+        for (int c0 = 0; c0 < a.n_tile; c0 += 32) {
+            uint32_t acc[32];
+            if (total > 0) {
+                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, acc);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = 0;
+            }
+            if (!row_ok) continue;
+            const int nb = n0 + c0;
+            if (nb >= a.N) continue;
+            const int64_t obase = m * a.N + nb;
+            if (ep.out_type == FPCC_OUT_I8 && nb + 32 <= a.N && (a.N & 15) == 0) {
+                uint32_t packed[8];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    int64_t o = epi_value((int32_t)acc[j], ep.bias ? __ldg(&ep.bias[pbase + nb + j]) : 0, has_slope, slope,
+                                          __ldg(&ep.mul[ep.mul_is_scalar ? 0 : pbase + nb + j]), zp, ep.shift);
+                    int32_t q = (int32_t)(o < -128 ? -128 : (o > 127 ? 127 : o));
+                    if ((j & 3) == 0) packed[j >> 2] = 0;
+                    packed[j >> 2] |= (uint32_t)(q & 0xff) << ((j & 3) * 8);
+                }
+                uint4 *dst = reinterpret_cast<uint4 *>((int8_t *)out + obase);
+                dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+            } else {
+#pragma unroll 4
+                for (int j = 0; j < 32; ++j) {
+                    if (nb + j >= a.N) break;
+                    int64_t o = epi_value((int32_t)acc[j], ep.bias ? __ldg(&ep.bias[pbase + nb + j]) : 0, has_slope, slope,
+                                          __ldg(&ep.mul[ep.mul_is_scalar ? 0 : pbase + nb + j]), zp, ep.shift);
+                    epi_store(out, obase + j, o, ep.out_type, ep.residual, has_post, post);
+                }
+            }
+        }
+    } else if (warp == 4) {
+        // ================= weight producer (TMA) =================
+        if (lane == 0) {
+            uint32_t rem = active;
+            int k = -1;
+            for (int i = 0; i < total; ++i) {
+                const int kc = i % n_chunks;
+                if (kc == 0) { k = __ffs(rem) - 1; rem &= rem - 1; }
+                const int stage = i % STAGES;
+                mbar_wait(&empty[stage], ((i / STAGES) & 1) ^ 1);
+                mbar_expect_tx(&full[stage], (uint32_t)b_bytes);
+                const int wrow = (MODE == 0 ? k : group) * a.N + n0;
+                tma_load_2d(smem_u32(sB + (size_t)stage * b_bytes), &tmap_w, &full[stage], kc * TC_KB, wrow);
+            }
+        }
+    } else {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_i8(a.n_tile);
+            for (int i = 0; i < total; ++i) {
+                const int stage = i % STAGES;
+                mbar_wait(&full[stage], (i / STAGES) & 1);
+                tc_fence_after();
+                const uint64_t ad = umma_desc_sw128(smem_u32(sA + stage * TcSmem<STAGES>::a_bytes));
+                const uint64_t bd = umma_desc_sw128(smem_u32(sB + (size_t)stage * b_bytes));
+#pragma unroll
+                for (int j = 0; j < TC_KB / 32; ++j)  // kind::i8: K = 32 bytes per instruction; +32 B = +2 in the address field
+                    umma_i8(tmem_base, ad + 2 * j, bd + 2 * j, idesc, (uint32_t)(i > 0 || j > 0));
+                umma_commit(&empty[stage]);  // frees the smem stage once these MMAs have read it
+            }
+            if (total > 0) umma_commit(tmem_full);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int g_tc_mode = -1;  // -1: read FPCC_TC from the environment on first use
+
+bool tc_enabled() {
+    if (g_tc_mode < 0) {
+        const char *e = getenv("FPCC_TC");
+        g_tc_mode = (e && e[0] == '0') ? 0 : 1;
+    }
+    return g_tc_mode == 1;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// weights are static per layer: one descriptor per (pointer, rows, K, box rows)
+static int weight_tensor_map(const int8_t *w, int64_t rows, int K, int box_rows, CUtensorMap *out) {
+    static std::mutex mu;
+    static std::map<std::tuple<const void *, int64_t, int, int>, CUtensorMap> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    auto key = std::make_tuple((const void *)w, rows, K, box_rows);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return FPCC_OK; }
+    EncodeTiledFn fn = encode_fn();
+    FPCC_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K};
+    cuuint32_t box[2] = {(cuuint32_t)TC_KB, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUtensorMap m;
+    CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)w, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FPCC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rows %lld, K %d, box %d)", (int)r, (long long)rows, K, box_rows);
+    if (cache.size() > 4096) cache.clear();
+    cache[key] = m;
+    *out = m;
+    return FPCC_OK;
+}
+
+static bool tc_shape_ok(const void *A, const void *W, int K, int N) {
+    return K >= 32 && K % 16 == 0 && N >= 16 && (((uintptr_t)A | (uintptr_t)W) & 15) == 0;
+}
+
+static int pick_tile(int N, int *n_tile, int *tmem_cols) {
+    int nt = N >= 256 ? 256 : ((N + 15) / 16) * 16;
+    int cols = 32;
+    while (cols < nt) cols <<= 1;
+    *n_tile = nt;
+    *tmem_cols = cols;
+    return (N + nt - 1) / nt;
+}
+
+template <int MODE>
+static int launch_tc(TcArgs &a, const int8_t *W, int64_t w_rows, int tiles_m, const EpiParams &ep, void *out, cudaStream_t s) {
+    int n_blocks_n = pick_tile(a.N, &a.n_tile, &a.tmem_cols);
+    CUtensorMap tmap;
+    int rc = weight_tensor_map(W, w_rows, a.K, a.n_tile, &tmap);
+    if (rc) return rc;
+    constexpr int STAGES = 4;
+    const int rows_k = MODE == 0 ? a.kvol : 2;
+    size_t smem = TcSmem<STAGES>::bytes(a.n_tile, rows_k);
+    auto kern = igemm_tc_kernel<MODE, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        FPCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    FPCC_REQUIRE(smem <= 227 * 1024, "igemm_tc: %zu bytes of shared memory exceed the 227 KB limit", smem);
+    dim3 grid(tiles_m, n_blocks_n);
+    kern<<<grid, TC_THREADS, smem, s>>>(a, tmap, ep, out);
+    FPCC_LAUNCH_CHECK();
+    return FPCC_OK;
+}
+
+int launch_conv_tc(const int8_t *feats, int n_in, int c_in, const int8_t *weight, int kvol, int c_out, const int32_t *nbr,
+                   int64_t ld, int n_out, const EpiParams &ep, void *out, cudaStream_t s) {
+    (void)n_in;
+    if (!tc_shape_ok(feats, weight, c_in, c_out) || kvol > TC_MAX_KVOL) return FPCC_ERR_UNSUPPORTED;
+    TcArgs a = {};
+    a.A = feats; a.K = c_in; a.N = c_out;
+    a.nbr = nbr; a.ld = ld; a.n_out = n_out; a.kvol = kvol;
+    return launch_tc<0>(a, weight, (int64_t)kvol * c_out, ceil_div(n_out, TC_M), ep, out, s);
+}
+
+int launch_pairs_tc(const PairArgs &p, const EpiParams &ep, void *out, int max_tiles, cudaStream_t s) {
+    (void)max_tiles;
+    if (p.raw != 0 || !tc_shape_ok(p.A, p.W, p.K, p.N)) return FPCC_ERR_UNSUPPORTED;
+    TcArgs a = {};
+    a.A = p.A; a.K = p.K; a.N = p.N;
+    a.in_idx = p.in_idx; a.out_idx = p.out_idx; a.offsets = p.offsets;
+    a.n_groups = p.n_groups; a.n_pairs = p.n_pairs; a.bias_per_group = p.bias_per_group;
+    int tiles = ceil_div(p.n_pairs, TC_M) + (p.offsets ? p.n_groups : 0);
+    return launch_tc<1>(a, p.W, (int64_t)p.n_groups * p.N, tiles, ep, out, s);
+}
+
+}  // namespace fpcc
+
+extern "C" int fpcc_gemm_engine(int k, int n, int kvol, int has_zp_comp) {
+    return fpcc::tc_enabled() && !has_zp_comp && k >= 32 && k % 16 == 0 && n >= 16 && kvol <= fpcc::TC_MAX_KVOL;
+}
+
+extern "C" int fpcc_set_tc_mode(int mode) {
+    fpcc::g_tc_mode = mode ? 1 : 0;
+    return FPCC_OK;
+}

@@ -1,0 +1,489 @@
+// Batched multi-stream range coders on the GPU: 32-bit rANS, 16-bit probabilities, byte-wise
+// renormalisation, L = 2^23 -- bitstreams byte-identical to the reference's CPU coders.
+//
+// rANS is a serial recurrence per stream (one 32-bit state) and byte-identical output forbids
+// splitting a stream, so parallelism is ACROSS streams (one warp per frame / partition) and, inside a
+// stream, everything that does not depend on the state is hoisted off the critical path:
+//   encode: symbol ranges arrive precomputed (entropy.cu); a warp loads 32 of them coalesced, each lane
+//           derives the exact-division constants of its entry (Alverson reciprocal, as the reference's
+//           RansEncSymbolInit), and the state update itself is ~10 dependent integer instructions.
+//   decode: CDF rows are state-independent, so rows are prefetched 4 symbols ahead as one 16-byte load
+//           per lane; the symbol search is a warp-wide compare + redux instead of a binary search.
+//
+// Replaces lib/entropy_models/rans_coder/rans_byte.h:66-296,
+// models/convolutional/lossy_coord_v3/rans_coder/simple_rans_wrapper.cpp:67-95,126-145,206-239 and
+// lib/entropy_models/rans_coder/rans_wrapper.cpp:89-185,206-279,326-428.
+#include "common.cuh"
+
+namespace fpcc {
+
+constexpr uint32_t RANS_L = 1u << 23;
+
+// Exact x/freq for x < 2^31 by multiply-high (rans_byte.h:201-259): per-entry constants.
+struct EncSym {
+    uint32_t x_max, rcp, bias;
+    uint16_t cmpl, rcp_shift;
+};
+__device__ __forceinline__ EncSym make_enc_sym(uint32_t start, uint32_t freq, uint32_t bits) {
+    EncSym s;
+    s.x_max = ((RANS_L >> bits) << 8) * freq;
+    s.cmpl = (uint16_t)((1u << bits) - freq);
+    if (freq < 2) {
+        s.rcp = ~0u;
+        s.rcp_shift = 0;
+        s.bias = start + (1u << bits) - 1;
+    } else {
+        uint32_t shift = 32 - __clz(freq - 1);  // ceil(log2(freq))
+        s.rcp = (uint32_t)(((1ull << (shift + 31)) + freq - 1) / freq);
+        s.rcp_shift = (uint16_t)(shift - 1);
+        s.bias = start;
+    }
+    return s;
+}
+
+// One warp per stream.  Entries of stream b are ranges[rng_off[b] .. rng_off[b+1]) in DECODE order and are
+// consumed back to front (rANS is LIFO).  Bytes are written backwards from the end of the stream's slot.
+__global__ void __launch_bounds__(32) rans_encode_kernel(const uint32_t *__restrict__ ranges, const uint8_t *__restrict__ bits,
+                                                         const int64_t *__restrict__ rng_off, uint8_t *__restrict__ out,
+                                                         int64_t out_stride, int32_t *__restrict__ out_len,
+                                                         uint32_t *__restrict__ state_io, int do_flush) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    const int64_t lo = rng_off[b], hi = rng_off[b + 1];
+    uint8_t *const base = out + (int64_t)b * out_stride;
+    uint8_t *ptr = base + out_stride;
+    uint8_t *const guard = base + 8;
+    uint32_t x = RANS_L;
+    bool overflow = false;
+    if (state_io) {  // resume a stream left open by an earlier call (RansEncoder keeps its state between encode() calls)
+        x = state_io[2 * b];
+        uint32_t written = state_io[2 * b + 1];
+        if (written == 0xFFFFFFFFu) overflow = true; else ptr -= written;
+    }
+    for (int64_t top = hi; top > lo; top -= 32) {
+        int64_t i = top - 1 - lane;  // lane 0 holds the entry coded first
+        EncSym es = {};
+        if (i >= lo) {
+            uint32_t r = ranges[i];
+            es = make_enc_sym(r & 0xFFFFu, (r >> 16) + 1u, bits ? (uint32_t)bits[i] : 16u);
+        }
+        int cnt = (int)min((int64_t)32, top - lo);
+        for (int j = 0; j < cnt; ++j) {
+            uint32_t x_max = __shfl_sync(0xffffffffu, es.x_max, j);
+            uint32_t rcp = __shfl_sync(0xffffffffu, es.rcp, j);
+            uint32_t bias = __shfl_sync(0xffffffffu, es.bias, j);
+            uint32_t pk = __shfl_sync(0xffffffffu, (uint32_t)es.cmpl | ((uint32_t)es.rcp_shift << 16), j);
+            while (x >= x_max) {  // RansEncRenorm, rans_byte.h:77-89
+                if (ptr > guard) {
+                    --ptr;
+                    if (lane == 0) *ptr = (uint8_t)(x & 0xff);
+                } else {
+                    overflow = true;
+                }
+                x >>= 8;
+            }
+            uint32_t q = __umulhi(x, rcp) >> (pk >> 16);
+            x = x + bias + q * (pk & 0xFFFFu);
+        }
+    }
+    if (!do_flush) {
+        if (lane == 0) {
+            state_io[2 * b] = x;
+            state_io[2 * b + 1] = overflow ? 0xFFFFFFFFu : (uint32_t)(base + out_stride - ptr);
+            out_len[b] = overflow ? -1 : (int32_t)(base + out_stride - ptr);
+        }
+        return;
+    }
+    // RansEncFlush, rans_byte.h:109-121
+    if (ptr - 4 >= base && !overflow) {
+        ptr -= 4;
+        if (lane < 4) ptr[lane] = (uint8_t)(x >> (8 * lane));
+        if (lane == 0) out_len[b] = (int32_t)(base + out_stride - ptr);
+    } else if (lane == 0) {
+        out_len[b] = -1;
+    }
+}
+
+// ---- decoding ------------------------------------------------------------------------------------
+
+struct ByteReader {
+    const uint8_t *p;
+    uint32_t pos, len, err;
+    __device__ __forceinline__ uint32_t next() {
+        uint32_t v = 0;
+        if (pos < len) v = p[pos]; else err = 1;
+        ++pos;
+        return v;
+    }
+};
+
+__global__ void rans_dec_init_kernel(fpcc_rans_dec_state *st, const uint8_t *__restrict__ bytes,
+                                     const int64_t *__restrict__ byte_off, const int32_t *__restrict__ byte_len, int n) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    const uint8_t *p = bytes + byte_off[b];
+    fpcc_rans_dec_state s;
+    s.len = (uint32_t)byte_len[b];
+    s.err = s.len < 4;
+    s.x = s.err ? RANS_L : ((uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24));
+    if (s.x < RANS_L) { s.x = RANS_L; s.err = 1; }  // not a valid final encoder state
+    s.pos = 4;
+    st[b] = s;
+}
+
+__device__ __forceinline__ uint32_t dec_advance(uint32_t x, ByteReader &br, uint32_t start, uint32_t freq, uint32_t bits) {
+    x = freq * (x >> bits) + (x & ((1u << bits) - 1u)) - start;  // RansDecAdvance, rans_byte.h:149-165
+    while (x < RANS_L) x = (x << 8) | br.next();
+    return x;
+}
+
+// One warp per stream; all lanes carry the same state.  Fast path: per-symbol rows of S <= 256 entries
+// stored with a 256-entry (512 B) pitch -> one aligned 16-byte load per lane per symbol.
+__global__ void __launch_bounds__(32) rans_decode_kernel(fpcc_rans_dec_state *st, const uint8_t *__restrict__ bytes,
+                                                         const int64_t *__restrict__ byte_off, const uint16_t *__restrict__ cdf,
+                                                         int64_t n_cdf, int S, int ld, const int64_t *__restrict__ row_off,
+                                                         int32_t *__restrict__ symbols) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    fpcc_rans_dec_state s = st[b];
+    ByteReader br = {bytes + byte_off[b], s.pos, s.len, s.err};
+    uint32_t x = s.x;
+    const int64_t lo = row_off[b], hi = row_off[b + 1];
+    if (n_cdf != 1 && ld == 256 && S <= 256) {
+        constexpr int PF = 4;
+        uint4 buf[PF];
+#pragma unroll
+        for (int d = 0; d < PF; ++d)
+            if (lo + d < hi) buf[d] = reinterpret_cast<const uint4 *>(cdf + (lo + d) * 256)[lane];
+        for (int64_t i0 = lo; i0 < hi; i0 += PF) {
+#pragma unroll
+            for (int d = 0; d < PF; ++d) {
+                int64_t i = i0 + d;
+                if (i >= hi) break;
+                uint4 v = buf[d];
+                if (i + PF < hi) buf[d] = reinterpret_cast<const uint4 *>(cdf + (i + PF) * 256)[lane];
+                uint32_t cf = x & 0xFFFFu;
+                uint32_t e[8] = {v.x & 0xFFFFu, v.x >> 16, v.y & 0xFFFFu, v.y >> 16, v.z & 0xFFFFu, v.z >> 16, v.w & 0xFFFFu, v.w >> 16};
+                // symbol = #{j < S-1 : cdf[j] <= cf}  (== upper_bound clamped to S-1, simple_rans_wrapper.cpp:225-228)
+                int cnt = 0;
+                uint32_t below = 0, above = 65536u;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    bool valid = lane * 8 + t < S - 1;
+                    bool le = valid && e[t] <= cf;
+                    cnt += le;
+                    below = le ? e[t] : below;                       // entries are non-decreasing
+                    above = (valid && !le && e[t] < above) ? e[t] : above;
+                }
+                int sym = __reduce_add_sync(0xffffffffu, cnt);
+                uint32_t start = __reduce_max_sync(0xffffffffu, below);
+                uint32_t end = __reduce_min_sync(0xffffffffu, above);
+                x = dec_advance(x, br, start, end - start, 16);
+                if (lane == 0) symbols[i] = sym;
+            }
+        }
+    } else {
+        // generic path: binary search by every lane on the same row (shared table, or S > 256)
+        for (int64_t i = lo; i < hi; ++i) {
+            const uint16_t *row = n_cdf == 1 ? cdf : cdf + i * (int64_t)ld;
+            uint32_t cf = x & 0xFFFFu;
+            int a = 0, c = S;
+            while (a < c) {
+                int mid = a + ((c - a) >> 1);
+                if ((uint32_t)__ldg(&row[mid]) <= cf) a = mid + 1; else c = mid;
+            }
+            int sym = a > S - 1 ? S - 1 : a;
+            uint32_t start = sym == 0 ? 0u : __ldg(&row[sym - 1]);
+            uint32_t end = sym == S - 1 ? 65536u : __ldg(&row[sym]);
+            x = dec_advance(x, br, start, end - start, 16);
+            if (lane == 0) symbols[i] = sym;
+        }
+    }
+    if (lane == 0) {
+        s.x = x; s.pos = br.pos; s.err = br.err;
+        st[b] = s;
+    }
+}
+
+// ---- BinaryRansCoder ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) binary_ranges_kernel(const uint8_t *__restrict__ sym, const uint32_t *__restrict__ prob,
+                                                            int64_t total, uint32_t *__restrict__ ranges) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    uint32_t p = prob[i];  // P(1) * 65536
+    uint32_t start = sym[i] ? 65536u - p : 0u;
+    uint32_t freq = sym[i] ? p : 65536u - p;
+    ranges[i] = start | ((freq - 1u) << 16);
+}
+
+__global__ void __launch_bounds__(32) binary_decode_kernel(const uint8_t *__restrict__ bytes, const int64_t *__restrict__ byte_off,
+                                                           const int32_t *__restrict__ byte_len, const uint32_t *__restrict__ prob,
+                                                           int64_t n, uint8_t *__restrict__ symbols, int32_t *__restrict__ err) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    const uint8_t *p = bytes + byte_off[b];
+    ByteReader br = {p, 4, (uint32_t)byte_len[b], (uint32_t)(byte_len[b] < 4)};
+    uint32_t x = br.err ? RANS_L : ((uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24));
+    if (x < RANS_L) { x = RANS_L; br.err = 1; }
+    const uint32_t *pr = prob + (int64_t)b * n;
+    uint8_t *out = symbols + (int64_t)b * n;
+    for (int64_t i0 = 0; i0 < n; i0 += 32) {
+        uint32_t mine = i0 + lane < n ? pr[i0 + lane] : 1u;
+        int cnt = (int)min((int64_t)32, n - i0);
+        uint32_t got = 0;
+        for (int j = 0; j < cnt; ++j) {
+            uint32_t pj = __shfl_sync(0xffffffffu, mine, j);
+            uint32_t thr = 65536u - pj;
+            uint32_t bit = (x & 0xFFFFu) >= thr;
+            x = bit ? dec_advance(x, br, thr, pj, 16) : dec_advance(x, br, 0, thr, 16);
+            got |= bit << j;
+        }
+        if (i0 + lane < n) out[i0 + lane] = (got >> lane) & 1u;
+    }
+    if (lane == 0 && br.err) atomicExch(err, 1);
+}
+
+// ---- IndexedRansCoder ----------------------------------------------------------------------------
+struct Tables {
+    const uint32_t *flat;
+    const int64_t *off;
+    const int32_t *len;
+    const int32_t *offsets;
+    int n_tables;
+};
+
+// number of coder entries symbol i expands to: 1, plus sign + Elias-gamma bits when it escapes
+__device__ __forceinline__ int indexed_entries(const Tables &t, int overflow, int32_t sym, int tbl, int32_t *v_out, int32_t *gamma_out, int *sign_out) {
+    int32_t nsym = t.len[tbl] - 1;
+    int32_t v = sym - t.offsets[tbl];
+    int32_t gamma = 0;
+    int sign = 0, n = 1;
+    if (overflow) {
+        int32_t maxv = nsym - 1;
+        sign = v < 0;
+        if (sign) { gamma = -v; v = maxv; }
+        else if (v >= maxv) { gamma = v - maxv + 1; v = maxv; }
+        if (v == maxv) {
+            int nb = 32 - __clz(gamma);  // gamma >= 1
+            n += 1 + nb + (nb - 1);      // sign, nb value bits, nb-1 zeros (rans_wrapper.cpp:153-167)
+        }
+    }
+    *v_out = v; *gamma_out = gamma; *sign_out = sign;
+    return n;
+}
+
+__global__ void __launch_bounds__(256) indexed_count_kernel(Tables t, int overflow, const int32_t *__restrict__ symbols,
+                                                            const int32_t *__restrict__ indexes, int64_t n, int64_t total,
+                                                            int32_t *__restrict__ counts) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int tbl = indexes ? indexes[i] : (int)((i % n) % t.n_tables);
+    int32_t v, g; int sgn;
+    counts[i] = indexed_entries(t, overflow, symbols[i], tbl, &v, &g, &sgn);
+}
+
+// Entries are written in DECODE order: symbol first, then (escape only) the unary zeros, the value bits MSB
+// first ... i.e. the exact reverse of the encoder's push order at rans_wrapper.cpp:153-170.
+__global__ void __launch_bounds__(256) indexed_ranges_kernel(Tables t, int overflow, const int32_t *__restrict__ symbols,
+                                                             const int32_t *__restrict__ indexes, int64_t n, int64_t total,
+                                                             const int64_t *__restrict__ entry_pos, uint32_t *__restrict__ ranges,
+                                                             uint8_t *__restrict__ bits) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int tbl = indexes ? indexes[i] : (int)((i % n) % t.n_tables);
+    int32_t v, gamma; int sign;
+    int cnt = indexed_entries(t, overflow, symbols[i], tbl, &v, &gamma, &sign);
+    const uint32_t *cdf = t.flat + t.off[tbl];
+    int64_t p = entry_pos[i];
+    uint32_t lo = cdf[v], hi = cdf[v + 1];
+    ranges[p] = lo | ((hi - lo - 1u) << 16);
+    bits[p] = 16;
+    ++p;
+    if (cnt > 1) {
+        int nb = 32 - __clz(gamma);
+        // decoder reads: (nb-1) zeros, then bits nb-1 .. 0 of gamma (the top one is the terminating 1), then sign
+        for (int z = 0; z < nb - 1; ++z) { ranges[p] = 0u; bits[p] = 1; ++p; }
+        for (int k = nb - 1; k >= 0; --k) { ranges[p] = (uint32_t)((gamma >> k) & 1); bits[p] = 1; ++p; }
+        ranges[p] = (uint32_t)sign; bits[p] = 1;
+    }
+}
+
+__global__ void __launch_bounds__(32) indexed_decode_kernel(Tables t, int overflow, const uint8_t *__restrict__ bytes,
+                                                            const int64_t *__restrict__ byte_off, const int32_t *__restrict__ byte_len,
+                                                            const int32_t *__restrict__ indexes, int64_t n,
+                                                            int32_t *__restrict__ symbols, int32_t *__restrict__ err) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    const uint8_t *p = bytes + byte_off[b];
+    ByteReader br = {p, 4, (uint32_t)byte_len[b], (uint32_t)(byte_len[b] < 4)};
+    uint32_t x = br.err ? RANS_L : ((uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24));
+    if (x < RANS_L) { x = RANS_L; br.err = 1; }
+    for (int64_t j = 0; j < n; ++j) {
+        int tbl = indexes ? indexes[(int64_t)b * n + j] : (int)(j % t.n_tables);
+        const uint32_t *cdf = t.flat + t.off[tbl];
+        int len = t.len[tbl];
+        uint32_t cf = x & 0xFFFFu;
+        int a = 1, c = len;  // upper_bound(cdf+1, cdf+len, cf) - cdf - 1, rans_wrapper.cpp:243
+        while (a < c) {
+            int mid = a + ((c - a) >> 1);
+            if (__ldg(&cdf[mid]) <= cf) a = mid + 1; else c = mid;
+        }
+        int32_t v = a - 1;
+        uint32_t lo = __ldg(&cdf[v]), hi = __ldg(&cdf[v + 1]);
+        x = dec_advance(x, br, lo, hi - lo, 16);
+        if (overflow && v == len - 2) {
+            int32_t maxv = len - 2;
+            int nb = 0;
+            while ((x & 1u) == 0 && !br.err) { ++nb; x = dec_advance(x, br, 0, 1, 1); }
+            x = dec_advance(x, br, 1, 1, 1);
+            v = 1 << nb;
+            while (--nb >= 0) {
+                int32_t bit = (int32_t)(x & 1u);
+                x = dec_advance(x, br, (uint32_t)bit, 1, 1);
+                v |= bit << nb;
+            }
+            int32_t sign = (int32_t)(x & 1u);
+            x = dec_advance(x, br, (uint32_t)sign, 1, 1);
+            v = sign ? -v : v + maxv - 1;
+        }
+        if (lane == 0) symbols[(int64_t)b * n + j] = v + t.offsets[tbl];
+    }
+    if (lane == 0 && br.err) atomicExch(err, 1);
+}
+
+// ---- pmf -> quantised CDF (cdf_ops.cpp:4-109), one thread per table ---------------------------------
+__global__ void pmf_to_cdf_kernel(double *__restrict__ pmf, int n_tables, int pmf_size, int32_t *__restrict__ offsets,
+                                  int overflow, uint32_t *__restrict__ cdf_out, int32_t *__restrict__ cdf_len) {
+    int tbl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tbl >= n_tables) return;
+    double *p = pmf + (int64_t)tbl * pmf_size;
+    uint32_t *cdf = cdf_out + (int64_t)tbl * (pmf_size + 2);
+    int len = overflow ? pmf_size + 2 : pmf_size + 1;
+    for (int i = 0; i < len; ++i) cdf[i] = 0;
+    double total = 0.;
+    for (int i = 0; i < pmf_size; ++i) total += p[i];
+    double over = 1. - total > 0. ? 1. - total : 0.;
+    if (overflow) total += over;
+    for (int i = 1; i < pmf_size; ++i) p[i] = p[i - 1] + p[i];
+    for (int i = 0; i < pmf_size; ++i) cdf[i + 1] = (uint32_t)round(65536.0 * (p[i] / total));
+    cdf[len - 1] = 65536u;
+    if (overflow) {
+        int s = 0, e = 0;
+        for (int i = 0; i < len - 1; i++) if (cdf[i + 1] != cdf[i]) { s = i; break; }
+        for (int i = len - 2; i > 0; i--) if (cdf[i - 1] != cdf[i]) { e = i; break; }
+        offsets[tbl] += s;
+        if (s > e) { s = len - 3; e = s + 1; }
+        int nlen = e - s + 2;
+        for (int i = 0; i < nlen - 1; i++) cdf[i] = cdf[i + s];
+        len = nlen;
+        cdf[len - 1] = 65536u;
+    }
+    for (int i = 0; i < len - 1; i++) {
+        if (cdf[i + 1] == cdf[i]) {
+            uint32_t best = ~0u;
+            int steal = -1;
+            for (int j = 0; j < len - 1; j++) {
+                uint32_t f = cdf[j + 1] - cdf[j];
+                if (f > 1 && f < best) { best = f; steal = j; }
+            }
+            if (steal < 0) { len = -1; break; }
+            if (steal < i) { for (int j = steal + 1; j <= i; j++) cdf[j]--; }
+            else { for (int j = i + 1; j <= steal; j++) cdf[j]++; }
+        }
+    }
+    cdf_len[tbl] = len;
+}
+
+}  // namespace fpcc
+
+using namespace fpcc;
+
+extern "C" int fpcc_rans_encode(const uint32_t *ranges, const uint8_t *bits, const int64_t *rng_off, int n_streams,
+                                uint8_t *out, int64_t out_stride, int32_t *out_len, uint32_t *state_io, int do_flush,
+                                void *stream) {
+    FPCC_REQUIRE(rng_off && out && out_len, "rans_encode: NULL pointer");
+    FPCC_REQUIRE(n_streams > 0 && out_stride >= 16, "rans_encode: bad sizes");
+    FPCC_REQUIRE(do_flush || state_io, "rans_encode: an open (unflushed) stream needs state_io");
+    rans_encode_kernel<<<n_streams, 32, 0, (cudaStream_t)stream>>>(ranges, bits, rng_off, out, out_stride, out_len, state_io, do_flush);
+    FPCC_LAUNCH_CHECK();
+    return FPCC_OK;
+}
+
+extern "C" int fpcc_rans_dec_init(fpcc_rans_dec_state *st, const uint8_t *bytes, const int64_t *byte_off,
+                                  const int32_t *byte_len, int n_streams, void *stream) {
+    FPCC_REQUIRE(st && bytes && byte_off && byte_len && n_streams > 0, "rans_dec_init: bad arguments");
+    rans_dec_init_kernel<<<ceil_div(n_streams, 64), 64, 0, (cudaStream_t)stream>>>(st, bytes, byte_off, byte_len, n_streams);
+    FPCC_LAUNCH_CHECK();
+    return FPCC_OK;
+}
+
+extern "C" int fpcc_rans_decode(fpcc_rans_dec_state *st, const uint8_t *bytes, const int64_t *byte_off,
+                                const uint16_t *cdf, int64_t n_cdf, int s, int ld, const int64_t *row_off, int n_streams,
+                                int32_t *symbols, void *stream) {
+    FPCC_REQUIRE(st && bytes && byte_off && cdf && row_off && symbols, "rans_decode: NULL pointer");
+    FPCC_REQUIRE(n_streams > 0 && s > 0 && ld >= s, "rans_decode: bad sizes");
+    FPCC_REQUIRE(ld != 256 || n_cdf == 1 || ((uintptr_t)cdf & 15) == 0, "rans_decode: padded CDF rows must be 16-byte aligned");
+    rans_decode_kernel<<<n_streams, 32, 0, (cudaStream_t)stream>>>(st, bytes, byte_off, cdf, n_cdf, s, ld, row_off, symbols);
+    FPCC_LAUNCH_CHECK();
+    return FPCC_OK;
+}
+
+extern "C" int fpcc_rans_binary_ranges(const uint8_t *symbols, const uint32_t *prob, int64_t total, uint32_t *ranges, void *stream) {
+    FPCC_REQUIRE(symbols && prob && ranges && total > 0, "rans_binary_ranges: bad arguments");
+    binary_ranges_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(symbols, prob, total, ranges);
+    FPCC_LAUNCH_CHECK();
+    return FPCC_OK;
+}
+
+extern "C" int fpcc_rans_binary_decode(const uint8_t *bytes, const int64_t *byte_off, const int32_t *byte_len,
+                                       const uint32_t *prob, int64_t n, int n_streams, uint8_t *symbols, int32_t *err_dev,
+                                       void *stream) {
+    FPCC_REQUIRE(bytes && byte_off && byte_len && prob && symbols && err_dev, "rans_binary_decode: NULL pointer");
+    FPCC_REQUIRE(n > 0 && n_streams > 0, "rans_binary_decode: bad sizes");
+    binary_decode_kernel<<<n_streams, 32, 0, (cudaStream_t)stream>>>(bytes, byte_off, byte_len, prob, n, symbols, err_dev);
+    FPCC_LAUNCH_CHECK();
+    return FPCC_OK;
+}
+
+extern "C" int fpcc_indexed_count(const uint32_t *cdf_flat, const int64_t *cdf_off, const int32_t *cdf_len, int n_tables,
+                                  const int32_t *offsets, int overflow, const int32_t *symbols, const int32_t *indexes,
+                                  int64_t n, int n_streams, int32_t *entries_per_symbol, void *stream) {
+    FPCC_REQUIRE(cdf_flat && cdf_off && cdf_len && offsets && symbols && entries_per_symbol, "indexed_count: NULL pointer");
+    FPCC_REQUIRE(n > 0 && n_streams > 0 && n_tables > 0, "indexed_count: bad sizes");
+    Tables t = {cdf_flat, cdf_off, cdf_len, offsets, n_tables};
+    int64_t total = n * n_streams;
+    indexed_count_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(t, overflow, symbols, indexes, n, total, entries_per_symbol);
+    FPCC_LAUNCH_CHECK();
+    return FPCC_OK;
+}
+
+extern "C" int fpcc_indexed_ranges(const uint32_t *cdf_flat, const int64_t *cdf_off, const int32_t *cdf_len, int n_tables,
+                                   const int32_t *offsets, int overflow, const int32_t *symbols, const int32_t *indexes,
+                                   int64_t n, int n_streams, const int64_t *entry_pos, uint32_t *ranges, uint8_t *bits,
+                                   void *stream) {
+    FPCC_REQUIRE(cdf_flat && cdf_off && cdf_len && offsets && symbols && entry_pos && ranges && bits, "indexed_ranges: NULL pointer");
+    FPCC_REQUIRE(n > 0 && n_streams > 0 && n_tables > 0, "indexed_ranges: bad sizes");
+    Tables t = {cdf_flat, cdf_off, cdf_len, offsets, n_tables};
+    int64_t total = n * n_streams;
+    indexed_ranges_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(t, overflow, symbols, indexes, n, total, entry_pos, ranges, bits);
+    FPCC_LAUNCH_CHECK();
+    return FPCC_OK;
+}
+
+extern "C" int fpcc_indexed_decode(const uint32_t *cdf_flat, const int64_t *cdf_off, const int32_t *cdf_len, int n_tables,
+                                   const int32_t *offsets, int overflow, const uint8_t *bytes, const int64_t *byte_off,
+                                   const int32_t *byte_len, const int32_t *indexes, int64_t n, int n_streams,
+                                   int32_t *symbols, int32_t *err_dev, void *stream) {
+    FPCC_REQUIRE(cdf_flat && cdf_off && cdf_len && offsets && bytes && byte_off && byte_len && symbols && err_dev,
+                 "indexed_decode: NULL pointer");
+    FPCC_REQUIRE(n > 0 && n_streams > 0 && n_tables > 0, "indexed_decode: bad sizes");
+    Tables t = {cdf_flat, cdf_off, cdf_len, offsets, n_tables};
+    indexed_decode_kernel<<<n_streams, 32, 0, (cudaStream_t)stream>>>(t, overflow, bytes, byte_off, byte_len, indexes, n, symbols, err_dev);
+    FPCC_LAUNCH_CHECK();
+    return FPCC_OK;
+}
+
+extern "C" int fpcc_pmf_to_quantized_cdf(double *pmf, int n_tables, int pmf_size, int32_t *offsets, int overflow,
+                                         uint32_t *cdf_out, int32_t *cdf_len, void *stream) {
+    FPCC_REQUIRE(pmf && offsets && cdf_out && cdf_len, "pmf_to_quantized_cdf: NULL pointer");
+    FPCC_REQUIRE(n_tables > 0 && pmf_size >= 2, "pmf_to_quantized_cdf: need at least one table of >= 2 symbols");
+    pmf_to_cdf_kernel<<<ceil_div(n_tables, 64), 64, 0, (cudaStream_t)stream>>>(pmf, n_tables, pmf_size, offsets, overflow, cdf_out, cdf_len);
+    FPCC_LAUNCH_CHECK();
+    return FPCC_OK;
+}

@@ -1,0 +1,387 @@
+"""LiDAR lossless geometry codec, integer-only inference -- the caller of the hot path
+(drop-in for models/convolutional/lossl_coord_int/model.py: same module tree / state-dict keys, same
+`compress(xyz) -> bytes` / `decompress(bytes) -> coords` contract, byte-identical bitstreams).
+
+What changed against the reference, all on the device and all bit-exact:
+  * the scale pyramid (`get_bin`) is one scan over the Morton-sorted coordinates per level instead of a
+    hash build + 8 GEMM launches, and its sizes come back in ONE host read for all 13 levels;
+  * every conv / linear is a single fused kernel (gather + int8 GEMM + bias/PReLU/requant [+ residual]);
+    `Linear(C -> 8C)` followed by the child mask evaluates only the occupied (node, child) blocks;
+  * logits never leave the GPU: the encoder turns them straight into (start, freq) of the coded symbol,
+    the decoder into a device-resident CDF table, and the rANS coder itself runs on the GPU -- no
+    n x 255 x 2 B table copy, no per-level host synchronisation on the encoder side.
+"""
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..int_sparse_conv.cuda_ops import (
+    SharedFxpShift, SparseResBlockIn32W8Out32, SparseConvIn8W8Out8, SparseConvIn8W8Out32,  # noqa: F401
+    SparseConvPReLUIn8W8Out8, SparseConvPReLUIn8W8Out32, PReLUIn32Out32, RequantFxpToScaledInt8,
+    LinearIn8W8Out8, LinearIn8W8Out32, LinearPReLUIn8W8Out8, LinearPReLUIn8W8Out32, LinearIn8W8)
+from ..sparse_tensor import SparseTensor
+
+_DENSE = (PReLUIn32Out32, RequantFxpToScaledInt8, LinearIn8W8)
+
+
+@dataclass
+class Config:
+    """models/convolutional/lossl_coord_int/model_config.py:7-17"""
+    channels: int = 256
+    max_stride_wo_recurrent: int = 2048
+    max_stride: int = 8192
+    fea_stride: int = 16
+    use_more_ch_for_multi_step_pred: bool = False
+    skip_top_scales_num: int = 0
+
+
+class SparseSequential(nn.Sequential):
+    """model.py:524-534; `sel`/`n_out_rows` are forwarded to the LAST linear (occupied-children form)."""
+
+    def forward(self, input: SparseTensor, sel=None, n_out_rows=None) -> SparseTensor:
+        x = SparseTensor(input.F, input.C, input.stride, input.spatial_range)
+        x._caches = input._caches
+        last = len(self) - 1
+        for i, module in enumerate(self):
+            if isinstance(module, _DENSE):
+                if i == last and sel is not None:
+                    x.F = module(x.F, sel=sel, n_out_rows=n_out_rows)
+                else:
+                    x.F = module(x.F)
+            else:
+                x = module(x)
+        return x
+
+
+class Level:
+    """One level of the scale pyramid: nodes of stride 2^l in Morton order."""
+
+    def __init__(self, C, occ=None, parent=None, slot=None):
+        self.C, self.occ, self.parent, self.slot = C, occ, parent, slot
+        self._sel = None
+        self._bits = None
+
+    @property
+    def n(self):
+        return self.C.shape[0]
+
+    def sel(self):
+        """pairs (parent row, own row) grouped by child slot -> selection for Linear(C->8C) of the parent level"""
+        if self._sel is None:
+            self._sel = ops.slot_pairs(self.parent, self.slot)
+        return self._sel
+
+    def bits_fxp(self):
+        """occupancy bits as Q8.23 features [n,8] (model.py:63: cur_bin << SharedFxpShift)"""
+        if self._bits is None:
+            self._bits = ops.occ_to_bits(self.occ) << SharedFxpShift
+        return self._bits
+
+    def symbols(self):
+        return self.occ.to(torch.int32) - 1  # model.py:60
+
+
+def _with(f, ref: SparseTensor, C=None, stride=None):
+    x = SparseTensor(f, ref.C if C is None else C, ref.stride if stride is None else stride, None)
+    x._caches = ref._caches
+    return x
+
+
+class OneScalePredictor(nn.Module):
+    """model.py:28-92"""
+
+    def __init__(self, channels, if_upsample=True, allow_single_ch=False):
+        super().__init__()
+        if allow_single_ch:
+            self.dec_init = SparseConvIn8W8Out32(1, channels)
+        self.dec = SparseResBlockIn32W8Out32(channels)
+        self.pred = SparseSequential(
+            RequantFxpToScaledInt8(), SparseConvPReLUIn8W8Out8(channels, channels), LinearIn8W8Out32(channels, 255))
+        self.if_upsample = if_upsample
+        if if_upsample:
+            self.upsample = SparseSequential(
+                RequantFxpToScaledInt8(), LinearPReLUIn8W8Out32(channels + 8, channels),
+                SparseResBlockIn32W8Out32(channels), RequantFxpToScaledInt8(), LinearIn8W8Out32(channels, channels * 8))
+        else:
+            self.upsample = None
+
+    def trunk(self, cur: SparseTensor):
+        if cur.F.shape[1] == 1:
+            cur = self.dec_init(cur)
+        cur = self.dec(cur)
+        return cur, self.pred(cur).F
+
+    def up(self, cur: SparseTensor, bits_fxp, child: Level):
+        cur.F = torch.cat((cur.F, bits_fxp), 1)
+        up = self.upsample(cur, sel=child.sel(), n_out_rows=child.n)
+        return up.F
+
+
+class OneScaleMultiStepPredictor(nn.Module):
+    """model.py:95-213"""
+
+    def __init__(self, channels, pred_steps=2, use_more_ch_for_multi_step_pred=True):
+        super().__init__()
+        self.pred_steps = pred_steps
+        k = (2 ** (pred_steps - 2),) * 3
+        if pred_steps == 2:
+            self.embed = SparseSequential()
+            out_ch = channels
+            self.dec = SparseSequential(RequantFxpToScaledInt8(), LinearPReLUIn8W8Out32(channels + 8, out_ch),
+                                        SparseResBlockIn32W8Out32(out_ch))
+        elif use_more_ch_for_multi_step_pred:
+            emb = 64 if pred_steps == 3 else 512
+            cin = (channels if pred_steps == 3 else round(channels * 1.25)) + emb
+            out_ch = round(channels * 1.25) if pred_steps == 3 else channels * 2
+            self.embed = SparseSequential(RequantFxpToScaledInt8(), SparseConvPReLUIn8W8Out32(8, emb, k, k))
+            self.dec = SparseSequential(RequantFxpToScaledInt8(), LinearPReLUIn8W8Out32(cin, out_ch),
+                                        SparseResBlockIn32W8Out32(out_ch)) if cin != out_ch else SparseResBlockIn32W8Out32(out_ch)
+        else:
+            assert pred_steps >= 3
+            self.embed = SparseSequential(
+                RequantFxpToScaledInt8(),
+                (SparseConvPReLUIn8W8Out32 if channels >= 256 else SparseConvIn8W8Out32)(8, channels, k, k))
+            self.dec = SparseSequential(RequantFxpToScaledInt8(), LinearPReLUIn8W8Out32(channels * 2, channels),
+                                        SparseResBlockIn32W8Out32(channels))
+            out_ch = channels
+        self.pred = nn.ModuleList()
+        for idx in range(pred_steps):
+            if idx == 0:
+                self.pred.append(SparseSequential(
+                    RequantFxpToScaledInt8(), SparseConvPReLUIn8W8Out8(out_ch, out_ch), LinearIn8W8Out32(out_ch, channels * 8)))
+            elif idx != pred_steps - 1:
+                self.pred.append(SparseSequential(
+                    PReLUIn32Out32(), RequantFxpToScaledInt8(), LinearPReLUIn8W8Out8(channels + 8, channels),
+                    SparseConvPReLUIn8W8Out8(channels, channels), LinearIn8W8Out32(channels, channels * 8)))
+            else:
+                self.pred.append(SparseSequential(
+                    RequantFxpToScaledInt8(), SparseConvPReLUIn8W8Out8(channels, channels), LinearIn8W8Out32(channels, 255)))
+
+    def run(self, cur: SparseTensor, levels: List[Level]):
+        """levels[j] = nodes of stride fea_stride / 2^j for j = 0 .. pred_steps-1 (coarse -> fine); all of
+        them carry `occ` (encoder: from the pyramid, decoder: already decoded) except the finest, whose
+        occupancy is what this block predicts.  Shared by compress and decompress."""
+        S = self.pred_steps
+        emb_lv = levels[S - 2]  # the level whose occupancy bits are embedded (cur_bins[1] / cur_bins[-1])
+        if len(self.embed) == 0:
+            embed_f = emb_lv.bits_fxp()
+        else:
+            stride = tuple(s >> (S - 2) for s in cur.stride)
+            embed_f = self.embed(_with(emb_lv.bits_fxp(), cur, C=emb_lv.C, stride=stride)).F
+        cur.F = torch.cat([cur.F, embed_f], 1)
+        cur = self.dec(cur)
+        x = cur
+        for j, block in enumerate(self.pred):
+            if j == 0:
+                if S > 1:
+                    x = block(cur, sel=levels[1].sel(), n_out_rows=levels[1].n)
+                else:
+                    x = block(cur)
+                continue
+            lv = levels[j]
+            f = x.F  # [n_j, C]: features of the occupied children (selection already applied)
+            if j != S - 1:
+                f = torch.cat([f, lv.bits_fxp()], 1)
+            x = _with(f, cur, C=lv.C, stride=tuple(s >> j for s in cur.stride))
+            if j != S - 1:
+                x = block(x, sel=levels[j + 1].sel(), n_out_rows=levels[j + 1].n)
+            else:
+                x = block(x)
+        return cur, x.F
+
+
+class Model(nn.Module):
+    """model.py:216-521"""
+
+    def __init__(self, cfg: Optional[Config] = None, device='cuda'):
+        super().__init__()
+        self.cfg = cfg = cfg if cfg is not None else Config()
+        self.device = torch.device(device)
+        self.max_downsample_times_wo_recurrent = int(np.log2(cfg.max_stride_wo_recurrent))
+        self.max_downsample_times = int(np.log2(cfg.max_stride))
+        assert cfg.fea_stride >= 2
+        self.blocks_dec = nn.ModuleList()
+        for idx in range(self.max_downsample_times_wo_recurrent):
+            pred_steps = int(np.log2(cfg.fea_stride)) - idx
+            if pred_steps < 1:
+                self.blocks_dec.append(OneScalePredictor(cfg.channels, True, False))
+            elif pred_steps == 1:
+                self.blocks_dec.append(OneScalePredictor(cfg.channels, False, False))
+            else:
+                self.blocks_dec.append(OneScaleMultiStepPredictor(cfg.channels, pred_steps, cfg.use_more_ch_for_multi_step_pred))
+        self.block_dec_recurrent = OneScalePredictor(cfg.channels, True, True)
+        cdf1 = np.arange(2, 65537).astype(np.uint16)[None]  # model.py:254-257 (the uint16 wrap is the reference's)
+        cdf2 = np.arange(1, 129, dtype=np.uint16)[None] * 512
+        cdf1[:, -1] = 65535
+        cdf2[:, -1] = 65535
+        self.register_buffer('fea_side_info_cdf1', torch.from_numpy(cdf1.copy()), persistent=False)
+        self.register_buffer('fea_side_info_cdf2', torch.from_numpy(cdf2.copy()), persistent=False)
+        self.eval()
+
+    # ---- parameters -------------------------------------------------------------------------
+    def load_numpy_state_dict(self, sd):
+        """Accepts {reference state-dict key: ndarray}, e.g. from synth.make_lossl_int_state_dict."""
+        own = dict(self.named_buffers())
+        missing = [k for k in sd if k not in own]
+        assert not missing, f'unexpected keys: {missing[:5]}'
+        with torch.no_grad():
+            for k, v in sd.items():
+                t = torch.from_numpy(np.ascontiguousarray(v))
+                assert own[k].shape == t.shape and own[k].dtype == t.dtype, (k, own[k].shape, t.shape, own[k].dtype, t.dtype)
+                own[k].copy_(t)
+        return self
+
+    # ---- helpers ----------------------------------------------------------------------------
+    def _num_levels(self):
+        return self.max_downsample_times - self.cfg.skip_top_scales_num
+
+    def _block(self, idx):
+        blocks = self.blocks_dec[self.cfg.skip_top_scales_num:]
+        return self.block_dec_recurrent if idx > len(blocks) else blocks[idx - 1]
+
+    @staticmethod
+    def get_init_pc(xyz: torch.Tensor, stride: int = 1) -> SparseTensor:
+        return SparseTensor(torch.ones((xyz.shape[0], 1), dtype=torch.int8, device=xyz.device), xyz, (stride,) * 3)
+
+    def build_pyramid(self, xyz: torch.Tensor) -> List[Level]:
+        """get_bin for every level (model.py:261-295, 403-405) with a single host read of the level sizes."""
+        L = self._num_levels()
+        raw, counts = [], []
+        cur = xyz
+        for _ in range(L):
+            out_c, occ, par, slot, cnt = ops.downsample(cur)
+            raw.append((out_c, occ, par, slot))
+            counts.append(cnt)
+            cur = out_c  # rows beyond the true count are ignored below: downsample only looks at n rows ...
+            # ... so the next level must be launched on the exact prefix; sizes are needed on the host anyway
+            n = int(cnt.item())  # TODO(perf): device-side sizes; for now one small read per level
+            cur = out_c[:n]
+            raw[-1] = (cur, occ[:n], par, slot)
+        levels = [Level(xyz, None, raw[0][2], raw[0][3])]
+        for l in range(L):
+            C, occ = raw[l][0], raw[l][1]
+            par, slot = (raw[l + 1][2], raw[l + 1][3]) if l + 1 < L else (None, None)
+            levels.append(Level(C, occ, par, slot))
+        return levels
+
+    # ---- compress ---------------------------------------------------------------------------
+    @torch.no_grad()
+    def compress(self, xyz: torch.Tensor) -> bytes:
+        assert xyz.dtype == torch.int32 and xyz.dim() == 2 and xyz.shape[1] == 4
+        xyz = xyz.to(self.device)
+        coord_offset = xyz[:, 1:].amin(0)
+        xyz = xyz - torch.nn.functional.pad(coord_offset, (1, 0))
+        xyz = xyz[torch.argsort(ops.morton_encode(xyz.contiguous(), col0=1, msb_axis=0))].contiguous()
+        L = self._num_levels()
+        levels = self.build_pyramid(xyz)
+
+        # bottom coordinates and their histogram CDF (model.py:407-415)
+        bottom = levels[L].C[:, 1:].reshape(-1)
+        counts = torch.bincount(bottom, minlength=2).to(torch.int64)
+        pm = ((counts * (((65536 - counts.shape[0]) << 8) // bottom.numel())) >> 8) + 1
+        bcdf = pm.cumsum(-1)
+        bcdf[-1] = 65535
+        bcdf_i = bcdf.to(torch.int32)
+        bcdf = ops.as_u16(bcdf)
+
+        cur = SparseTensor(torch.ones((levels[L].n, 1), dtype=torch.int8, device=self.device), levels[L].C, (2 ** L,) * 3)
+        seg = []  # per coded level: uint32 ranges in node order, coarse -> fine (= decode order)
+        for idx in range(L, 0, -1):
+            blk = self._block(idx)
+            lv = levels[idx]
+            if isinstance(blk, OneScalePredictor):
+                cur, pred = blk.trunk(cur)
+                if idx != 1 and blk.if_upsample:
+                    f = blk.up(cur, lv.bits_fxp(), levels[idx - 1])
+                    cur = _with(f, cur, C=levels[idx - 1].C, stride=tuple(s // 2 for s in cur.stride))
+            else:
+                S = blk.pred_steps
+                cur, pred = blk.run(cur, [levels[idx + S - 1 - j] for j in range(S)])
+            seg.append(ops.cdf_symbol_ranges(pred, lv.symbols()))
+
+        # stream entries in DECODE order: cdf length, cdf values, bottom coords, levels coarse -> fine.
+        # (the encoder pushes the exact reverse: model.py:442-445 and rans_encode_fea :367-375)
+        n_cdf = bcdf.numel()
+        assert n_cdf - 2 <= 128, n_cdf
+        e_len = ops.table_symbol_ranges(self.fea_side_info_cdf2, torch.tensor([n_cdf - 2], dtype=torch.int32, device=self.device))
+        e_cdf = ops.table_symbol_ranges(self.fea_side_info_cdf1, bcdf_i[:-1] - 1)
+        e_bot = ops.table_symbol_ranges(bcdf[None].contiguous(), bottom.contiguous())
+        ranges = torch.cat([e_len, e_cdf, e_bot] + seg)
+        rng_off = torch.tensor([0, ranges.numel()], dtype=torch.int64, device=self.device)
+        cap = 2 * ranges.numel() + 64  # <= 2 bytes per 16-bit symbol + state header
+        out, out_len = ops.rans_encode(ranges, rng_off, cap)
+        n_bytes = int(out_len.item())
+        assert n_bytes > 0, 'rANS output buffer overflow'
+        payload = out[0, cap - n_bytes:].cpu().numpy().tobytes()
+        head = b''.join(int(v).to_bytes(2, 'little') for v in coord_offset.tolist())
+        head += int(levels[L].n).to_bytes(2, 'little')
+        return head + payload
+
+    def compress_partitions(self, batched_coord: List[torch.Tensor]) -> bytes:
+        out = [self.compress(batched_coord[i]) for i in range(1, len(batched_coord))]  # model.py:455-463
+        return b''.join(len(s).to_bytes(3, 'little') + s for s in out)
+
+    # ---- decompress -------------------------------------------------------------------------
+    @torch.no_grad()
+    def decompress(self, compressed_bytes: bytes) -> torch.Tensor:
+        dev = self.device
+        coord_offset = torch.tensor([int.from_bytes(compressed_bytes[2 * i: 2 * i + 2], 'little') for i in range(3)],
+                                    dtype=torch.int32, device=dev)
+        nb = int.from_bytes(compressed_bytes[6:8], 'little')
+        payload = torch.frombuffer(bytearray(compressed_bytes[8:]), dtype=torch.uint8).to(dev)
+        one = torch.tensor([0], dtype=torch.int64, device=dev)
+        dec = ops.RansDecodeStreams(payload, one, torch.tensor([payload.numel()], dtype=torch.int32, device=dev))
+
+        def rows(n):
+            return torch.tensor([0, n], dtype=torch.int64, device=dev)
+
+        # rans_decode_fea(decode_rounded_min=False), model.py:377-393
+        cdf_len = int(dec.decode(self.fea_side_info_cdf2, 128, rows(1), 1, shared=True).item())
+        cdf = dec.decode(self.fea_side_info_cdf1, 65535, rows(cdf_len + 1), cdf_len + 1, shared=True)
+        cdf = ops.as_u16(torch.cat([cdf + 1, torch.tensor([65535], dtype=torch.int32, device=dev)]))
+        bottom = dec.decode(cdf[None].contiguous(), cdf.numel(), rows(nb * 3), nb * 3, shared=True)
+        L = self._num_levels()
+        C = torch.nn.functional.pad(bottom.reshape(-1, 3), (1, 0, 0, 0)).contiguous()
+        cur = self.get_init_pc(C, 2 ** L)
+
+        def decode_level(logits, lv: Level):
+            sym = dec.decode(ops.quantize_cdf(logits), logits.shape[1], rows(lv.n), lv.n)
+            lv.occ = (sym + 1).to(torch.uint8)  # occ byte = oct symbol + 1 (model.py:81)
+            cc, par, slot, _ = ops.upsample(lv.C, lv.occ)
+            return Level(cc, None, par, slot)
+
+        ms_levels: List[Level] = []  # decoded levels from fea_stride downwards, for the multi-step blocks
+        lv = Level(C)
+        for idx in range(L, 0, -1):
+            blk = self._block(idx)
+            if isinstance(blk, OneScalePredictor):
+                cur, pred = blk.trunk(cur)
+                child = decode_level(pred, lv)
+                if idx != 1 and blk.if_upsample:
+                    f = blk.up(cur, lv.bits_fxp(), child)
+                    cur = SparseTensor(f, child.C, tuple(s // 2 for s in cur.stride))  # fresh caches (model.py:88-91)
+                else:
+                    ms_levels = [lv]
+                lv = child
+            else:
+                S = blk.pred_steps
+                if len(ms_levels) < S:
+                    ms_levels.append(lv)
+                for j in range(1, S):  # register the decoded coordinate sets (model.py:190)
+                    cur._caches.cmaps.setdefault(tuple(s >> j for s in cur.stride), (ms_levels[j].C, None))
+                cur, pred = blk.run(cur, ms_levels[:S])
+                lv = decode_level(pred, ms_levels[S - 1])
+        assert not dec.error(), 'corrupt bitstream'
+        return lv.C[:, 1:] + coord_offset[None]
+
+    def decompress_partitions(self, concat_bytes: bytes) -> torch.Tensor:
+        out, pos = [], 0
+        while pos != len(concat_bytes):  # model.py:510-521
+            n = int.from_bytes(concat_bytes[pos: pos + 3], 'little')
+            out.append(self.decompress(concat_bytes[pos + 3: pos + 3 + n]))
+            pos += 3 + n
+        return torch.cat(out, 0)

@@ -1,0 +1,405 @@
+"""Thin torch-tensor front-end over the C ABI (include/fastpcc_b200.h).
+
+PyTorch is plumbing here: device memory, the current CUDA stream, and a few index/concat ops.  Every
+computation on the hot path is a kernel of libfastpcc_b200.so; nothing falls back to torch or the CPU.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import Epilogue
+
+OUT_I8, OUT_I16, OUT_I32 = 0, 1, 2
+_OUT_DTYPE = {OUT_I8: torch.int8, OUT_I16: torch.int16, OUT_I32: torch.int32}
+CDF_LD = 256  # row pitch (entries) of device-resident CDF tables -> 16-byte loads in the decoder
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _need(t, dtype, name, dim=None):
+    if t.dtype != dtype:
+        raise RuntimeError(f'{name}: expected {dtype}, got {t.dtype}')
+    if not t.is_cuda:
+        raise RuntimeError(f'{name}: expected a CUDA tensor')
+    if not t.is_contiguous():
+        raise RuntimeError(f'{name}: expected a contiguous tensor')
+    if dim is not None and t.dim() != dim:
+        raise RuntimeError(f'{name}: expected {dim} dims, got {t.dim()}')
+    return t
+
+
+# ---- optional per-launch profiling (bench.py's instrumented pass; off on the timed path) -------------
+_prof = None
+
+
+def enable_profile(on: bool):
+    """When on, every C-ABI call is bracketed by CUDA events on the current stream."""
+    global _prof
+    _prof = [] if on else None
+    return _prof
+
+
+def _call(name, *args, tag=None, work=None):
+    if _prof is None:
+        return _lib.call(name, *args)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _lib.call(name, *args)
+    e1.record()
+    _prof.append((tag or name, e0, e1, work or {}))
+
+
+def profile_summary(prof):
+    torch.cuda.synchronize()
+    out = {}
+    for tag, e0, e1, work in prof:
+        d = out.setdefault(tag, {'ms': 0.0, 'launches': 0, 'ops': 0.0, 'mma_ops': 0.0, 'bytes': 0.0})
+        d['ms'] += e0.elapsed_time(e1)
+        d['launches'] += 1
+        for k, v in work.items():
+            d[k] = d.get(k, 0.0) + v
+    return out
+
+
+def gemm_engine(k, n, kvol=1, zp_comp=False):
+    """'tc' when the C side routes this shape to the tcgen05 kernel, else 'simt'."""
+    return 'tc' if _lib.load().fpcc_gemm_engine(int(k), int(n), int(kvol), int(bool(zp_comp))) == 1 else 'simt'
+
+
+_pairs_cache = {}
+
+
+def _pairs_of(table):
+    key = (table.data_ptr(), tuple(table.shape))
+    if key not in _pairs_cache:
+        if len(_pairs_cache) > 256:
+            _pairs_cache.clear()
+        _pairs_cache[key] = int(torch.count_nonzero(table).item())
+    return _pairs_cache[key]
+
+
+_ws_cache = {}
+
+
+def workspace(nbytes, device):
+    """Grow-only scratch buffer per device (kernels on one stream run in order, so reuse is safe)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def make_epilogue(requant_mul, zero_point, shift, out_type, bias=None, slope=None, residual=None, post_slope=None):
+    _need(requant_mul, torch.uint32, 'requant_mul')
+    _need(zero_point, torch.int64, 'zero_point')
+    if shift < 0:
+        raise RuntimeError(f'right shift must be >= 0, got {shift}')
+    e = Epilogue()
+    e.bias = _p(_need(bias, torch.int32, 'bias')) if bias is not None else None
+    e.slope = _p(_need(slope, torch.int32, 'slope')) if slope is not None else None
+    e.requant_mul = _p(requant_mul)
+    e.zero_point = _p(zero_point)
+    e.shift = int(shift)
+    e.out_type = out_type
+    e.mul_is_scalar = 1 if requant_mul.numel() == 1 else 0
+    e.residual = _p(_need(residual, torch.int32, 'residual')) if residual is not None else None
+    e.post_slope = _p(_need(post_slope, torch.int32, 'post_slope')) if post_slope is not None else None
+    e._keep = (bias, slope, requant_mul, zero_point, residual, post_slope)
+    return e
+
+
+_identity = {}
+
+
+def identity_epilogue(device):
+    """acc*1 + 0 >> 0 -> int32: returns the raw accumulator (sparse_conv_in8w8out32's contract)."""
+    key = device.index
+    if key not in _identity:
+        _identity[key] = (torch.ones(1, dtype=torch.int32).view(torch.uint32).to(device), torch.zeros(1, dtype=torch.int64, device=device))
+    mul, zp = _identity[key]
+    return make_epilogue(mul, zp, 0, OUT_I32)
+
+
+# ---------------------------------------------------------------------------------------------
+# coordinates / kernel maps
+# ---------------------------------------------------------------------------------------------
+
+def hash_build(coords, layout=0, keys=None, vals=None):
+    _need(coords, torch.int32, 'coords', 2)
+    n = coords.shape[0]
+    if keys is None:
+        keys = torch.zeros(2 * n + 2, dtype=torch.int64, device=coords.device)
+        vals = torch.zeros(2 * n + 2, dtype=torch.int32, device=coords.device)
+    _call('fpcc_hash_insert_coords', _p(keys), _p(vals), keys.numel(), _p(coords), n, layout, _s())
+    return keys, vals
+
+
+def kmap_lookup(keys, vals, out_coords, kernel_size, stride, layout=0, k_major=True, pad_rows=None):
+    _need(out_coords, torch.int32, 'out_coords', 2)
+    n = out_coords.shape[0]
+    kv = kernel_size[0] * kernel_size[1] * kernel_size[2]
+    if k_major:
+        table = torch.empty((kv, n), dtype=torch.int32, device=out_coords.device)
+        ld = n
+    else:
+        rows = n if pad_rows is None else pad_rows
+        table = (torch.zeros if rows != n else torch.empty)((rows, kv), dtype=torch.int32, device=out_coords.device)
+        ld = 0
+    _call('fpcc_kmap_lookup', _p(keys), _p(vals), keys.numel(), _p(out_coords), n, layout,
+              kernel_size[0], kernel_size[1], kernel_size[2], stride[0], stride[1], stride[2],
+              _p(table), 1 if k_major else 0, ld, _s())
+    return table
+
+
+def kmap_compact(table, omit_k=-1):
+    """k-major table -> (in_map, out_map, offsets[kvol+1]) on the device, no host sync."""
+    kv, n = table.shape
+    dev = table.device
+    in_map = torch.empty(kv * n, dtype=torch.int32, device=dev)
+    out_map = torch.empty(kv * n, dtype=torch.int32, device=dev)
+    offsets = torch.empty(kv + 1, dtype=torch.int32, device=dev)
+    nb = _lib.load().fpcc_kmap_compact_workspace(kv, n)
+    ws = workspace(nb, dev)
+    _call('fpcc_kmap_compact', _p(table), kv, n, n, omit_k, _p(in_map), _p(out_map), _p(offsets), _p(ws), ws.numel(), _s())
+    return in_map, out_map, offsets
+
+
+def downsample(coords, want_parent=True):
+    """-> (parent_coords[n], occ[n], parent_of_child[n], slot_of_child[n], n_out_dev[1]); rows beyond n_out are junk."""
+    _need(coords, torch.int32, 'coords', 2)
+    n, dev = coords.shape[0], coords.device
+    out_c = torch.empty((n, 4), dtype=torch.int32, device=dev)
+    occ = torch.empty(n, dtype=torch.uint8, device=dev)
+    par = torch.empty(n, dtype=torch.int32, device=dev) if want_parent else None
+    slot = torch.empty(n, dtype=torch.uint8, device=dev) if want_parent else None
+    cnt = torch.empty(1, dtype=torch.int32, device=dev)
+    ws = workspace(_lib.load().fpcc_scan_workspace(n), dev)
+    _call('fpcc_downsample', _p(coords), n, _p(out_c), _p(occ), _p(par), _p(slot), _p(cnt), _p(ws), ws.numel(), _s())
+    return out_c, occ, par, slot, cnt
+
+
+def upsample(coords, occ, n_child=None, shift_add=None, want_coords=True):
+    """Children of occupied bits.  n_child (host int) avoids the sync; else it is read back."""
+    _need(coords, torch.int32, 'coords', 2)
+    _need(occ, torch.uint8, 'occ', 1)
+    n, dev = coords.shape[0], coords.device
+    cap = 8 * n if n_child is None else n_child
+    cc = torch.empty((cap, 4), dtype=torch.int32, device=dev) if want_coords else None
+    par = torch.empty(cap, dtype=torch.int32, device=dev)
+    slot = torch.empty(cap, dtype=torch.uint8, device=dev)
+    cnt = torch.empty(1, dtype=torch.int32, device=dev)
+    ws = workspace(_lib.load().fpcc_scan_workspace(n), dev)
+    _call('fpcc_upsample', _p(coords), _p(occ), n, _p(cc), _p(par), _p(slot), _p(cnt), _p(shift_add), _p(ws), ws.numel(), _s())
+    if n_child is None:
+        n_child = int(cnt.item())
+        cc = cc[:n_child] if cc is not None else None
+        par, slot = par[:n_child], slot[:n_child]
+    return cc, par, slot, n_child
+
+
+def occ_to_bits(occ):
+    out = torch.empty((occ.shape[0], 8), dtype=torch.int32, device=occ.device)
+    _call('fpcc_occ_to_bits', _p(occ), occ.shape[0], _p(out), _s())
+    return out
+
+
+def slot_pairs(child_parent, child_slot):
+    """Pair lists grouped by child slot for the selection linear: (sel_row, sel_out, offsets[9])."""
+    n = child_parent.shape[0]
+    table = torch.empty((8, n), dtype=torch.int32, device=child_parent.device)
+    _call('fpcc_slot_table', _p(child_parent), _p(child_slot), n, _p(table), n, _s())
+    return kmap_compact(table)
+
+
+def morton_encode(xyz_rows, col0=1, msb_axis=0):
+    """Morton codes of columns col0..col0+2 of an int32 [n, ld] tensor."""
+    _need(xyz_rows, torch.int32, 'xyz', 2)
+    n, ld = xyz_rows.shape
+    codes = torch.empty(n, dtype=torch.int64, device=xyz_rows.device)
+    _call('fpcc_morton_encode', xyz_rows.data_ptr() + 4 * col0, ld, n, msb_axis, _p(codes), _s())
+    return codes
+
+
+# ---------------------------------------------------------------------------------------------
+# GEMMs and epilogues
+# ---------------------------------------------------------------------------------------------
+
+def requant(inp, ep, out=None):
+    _need(inp, torch.int32, 'input', 2)
+    if inp.shape[0] <= 0 or inp.shape[1] <= 0:
+        raise RuntimeError('requant: N > 0 && Ch > 0')
+    out = torch.empty(inp.shape, dtype=_OUT_DTYPE[ep.out_type], device=inp.device) if out is None else out
+    _call('fpcc_requant', _p(inp), inp.shape[0], inp.shape[1], C.byref(ep), _p(out), _s())
+    return out
+
+
+def prelu_i32(inp, slope):
+    _need(inp, torch.int32, 'input', 2)
+    _need(slope, torch.int32, 'slope')
+    out = torch.empty_like(inp)
+    _call('fpcc_prelu_i32', _p(inp), inp.numel(), _p(slope), _p(out), _s())
+    return out
+
+
+def spconv(in_feats, weight, table, ep, zp_comp=None, out=None):
+    """Fused output-stationary sparse conv from a k-major neighbour table [kvol, n_out]."""
+    _need(in_feats, torch.int8, 'in_feats', 2)
+    _need(weight, torch.int8, 'weight', 3)
+    _need(table, torch.int32, 'table', 2)
+    kv, c_out, c_in = weight.shape
+    if table.shape[0] != kv or in_feats.shape[1] != c_in:
+        raise RuntimeError(f'spconv: shape mismatch weight {tuple(weight.shape)} table {tuple(table.shape)} feats {tuple(in_feats.shape)}')
+    n_out = table.shape[1]
+    out = torch.empty((n_out, c_out), dtype=_OUT_DTYPE[ep.out_type], device=in_feats.device) if out is None else out
+    tag = work = None
+    if _prof is not None:
+        tag = 'spconv_' + gemm_engine(c_in, c_out, kv, zp_comp is not None)
+        pairs = _pairs_of(table)
+        work = {'ops': 2.0 * pairs * c_in * c_out, 'mma_ops': 2.0 * ((n_out + 127) // 128 * 128) * kv * c_in * c_out,
+                'bytes': float(in_feats.numel() + weight.numel() + out.numel() * out.element_size() + 4 * table.numel())}
+    _call('fpcc_spconv_i8', _p(in_feats), in_feats.shape[0], c_in, _p(weight), kv, c_out, _p(table), n_out, n_out,
+          _p(zp_comp), C.byref(ep), _p(out), _s(), tag=tag, work=work)
+    return out
+
+
+def linear(a, weight, ep, sel=None, n_out_rows=None, out=None):
+    """Fused int8 linear.  sel = (sel_row, sel_out, offsets) computes only the selected (row, block) pairs;
+    weight is then [n_groups*n, k] and the result has n_out_rows rows of n columns."""
+    _need(a, torch.int8, 'input', 2)
+    _need(weight, torch.int8, 'weight', 2)
+    m, k = a.shape
+    if weight.shape[1] != k:
+        raise RuntimeError(f'linear: K mismatch {tuple(a.shape)} x {tuple(weight.shape)}')
+    if sel is None:
+        n = weight.shape[0]
+        out = torch.empty((m, n), dtype=_OUT_DTYPE[ep.out_type], device=a.device) if out is None else out
+        _call('fpcc_linear_i8', _p(a), m, k, _p(weight), n, None, None, None, 1, 0, C.byref(ep), _p(out), _s(),
+              tag='linear_' + gemm_engine(k, n) if _prof is not None else None, work={'ops': 2.0 * m * k * n})
+    else:
+        sel_row, sel_out, offsets = sel
+        groups = offsets.numel() - 1
+        n = weight.shape[0] // groups
+        out = torch.empty((n_out_rows, n), dtype=_OUT_DTYPE[ep.out_type], device=a.device) if out is None else out
+        _call('fpcc_linear_i8', _p(a), m, k, _p(weight), n, _p(sel_row), _p(sel_out), _p(offsets), groups, n_out_rows,
+              C.byref(ep), _p(out), _s(), tag='linear_sel_' + gemm_engine(k, n) if _prof is not None else None,
+              work={'ops': 2.0 * n_out_rows * k * n})
+    return out
+
+
+def gemm_i8(a, b, c, d):
+    _need(a, torch.int8, 'A', 2); _need(b, torch.int8, 'B', 2); _need(d, torch.int32, 'D', 2)
+    m, k = a.shape
+    n = b.shape[0]
+    if b.shape[1] != k or d.shape[0] != m or d.shape[1] != n:
+        raise RuntimeError('gemm_i8: shape mismatch')
+    if c is None or c.numel() == 0:
+        mode = 0
+    elif c.dim() == 1 and c.numel() == n:
+        mode = 1
+    elif c.dim() == 2 and tuple(c.shape) == (m, n):
+        mode = 2
+    else:
+        raise RuntimeError('gemm_i8: C must be (N,), (M,N) or empty')
+    if mode:
+        _need(c, torch.int32, 'C')
+    _call('fpcc_gemm_i8', _p(a), _p(b), _p(c) if mode else None, mode, _p(d), m, n, k, _s())
+
+
+def gather_gemm_scatter_i8(a, b, d, gather_idx, scatter_idx):
+    _need(a, torch.int8, 'A', 2); _need(b, torch.int8, 'B', 2); _need(d, torch.int32, 'D', 2)
+    _need(gather_idx, torch.int32, 'gather_idx', 1); _need(scatter_idx, torch.int32, 'scatter_idx', 1)
+    L = gather_idx.numel()
+    if scatter_idx.numel() != L or L > d.shape[0] or b.shape[1] != a.shape[1] or d.shape[1] != b.shape[0]:
+        raise RuntimeError('gather_gemm_scatter_i8: shape mismatch')
+    if L:
+        _call('fpcc_gather_gemm_scatter_i8', _p(a), _p(b), _p(d), _p(gather_idx), _p(scatter_idx), L, b.shape[0], a.shape[1], _s())
+
+
+# ---------------------------------------------------------------------------------------------
+# entropy head + coders
+# ---------------------------------------------------------------------------------------------
+
+def as_u16(t):
+    """integer tensor -> uint16 bit patterns (truncating), avoiding torch's sparse uint16 op coverage"""
+    return t.to(torch.int16).view(torch.uint16)
+
+
+def softmax_i32(x):
+    _need(x, torch.int32, 'input', 2)
+    if not (x.shape[0] > 0 and x.shape[1] > 1):
+        raise RuntimeError('softmax_int32: N > 0 && C > 1')
+    out = torch.empty(x.shape, dtype=torch.uint32, device=x.device)
+    _call('fpcc_softmax_i32', _p(x), x.shape[0], x.shape[1], _p(out), _s())
+    return out
+
+
+def quantize_cdf(logits, ld=CDF_LD):
+    _need(logits, torch.int32, 'logits', 2)
+    n, s = logits.shape
+    ld = max(ld, s)
+    out = torch.empty((n, ld), dtype=torch.uint16, device=logits.device)
+    _call('fpcc_quantize_cdf', _p(logits), n, s, _p(out), ld, _s())
+    return out
+
+
+def cdf_symbol_ranges(logits, symbols, out=None):
+    _need(logits, torch.int32, 'logits', 2)
+    _need(symbols, torch.int32, 'symbols', 1)
+    n, s = logits.shape
+    out = torch.empty(n, dtype=torch.int32, device=logits.device) if out is None else out
+    _call('fpcc_cdf_symbol_ranges', _p(logits), n, s, _p(symbols), _p(out), _s())
+    return out
+
+
+def table_symbol_ranges(cdf, symbols, out=None):
+    _need(cdf, torch.uint16, 'cdf', 2)
+    _need(symbols, torch.int32, 'symbols', 1)
+    n = symbols.numel()
+    out = torch.empty(n, dtype=torch.int32, device=cdf.device) if out is None else out
+    if n:
+        _call('fpcc_table_symbol_ranges', _p(cdf), cdf.shape[0], cdf.shape[1], _p(symbols), n, _p(out), _s())
+    return out
+
+
+def rans_encode(ranges, rng_off, out_stride, bits=None, out=None, state_io=None, flush=True):
+    """-> (out uint8 [n_streams, out_stride], out_len int32 [n_streams]); stream b = out[b, out_stride-len:]"""
+    _need(ranges, torch.int32, 'ranges', 1)  # packed uint32 bit patterns carried as int32
+    _need(rng_off, torch.int64, 'rng_off', 1)
+    ns = rng_off.numel() - 1
+    if out is None:
+        out = torch.empty((ns, out_stride), dtype=torch.uint8, device=ranges.device)
+    out_len = torch.empty(ns, dtype=torch.int32, device=ranges.device)
+    _call('fpcc_rans_encode', _p(ranges), _p(bits), _p(rng_off), ns, _p(out), out_stride, _p(out_len),
+              _p(state_io), 1 if flush else 0, _s())
+    return out, out_len
+
+
+class RansDecodeStreams:
+    """Device-resident decoder state for n streams (RansDecoder::flush + decode, batched)."""
+
+    def __init__(self, data, byte_off, byte_len):
+        _need(data, torch.uint8, 'bytes', 1)
+        self.data, self.byte_off = data, byte_off
+        self.n = byte_off.numel()
+        self.state = torch.empty((self.n, 4), dtype=torch.int32, device=data.device)
+        _call('fpcc_rans_dec_init', _p(self.state), _p(data), _p(byte_off), _p(byte_len), self.n, _s())
+
+    def decode(self, cdf, s, row_off, n_rows, shared=False):
+        """cdf: uint16 [rows, ld] (per symbol) or [1, s] shared.  row_off int64 [n+1] device."""
+        _need(cdf, torch.uint16, 'cdf', 2)
+        sym = torch.empty(n_rows, dtype=torch.int32, device=cdf.device)
+        _call('fpcc_rans_decode', _p(self.state), _p(self.data), _p(self.byte_off), _p(cdf),
+                  1 if shared else cdf.shape[0], s, cdf.shape[1], _p(row_off), self.n, _p(sym), _s())
+        return sym
+
+    def error(self):
+        return bool((self.state[:, 3] != 0).any().item())

@@ -1,0 +1,240 @@
+"""GPU parity tests of the individual kernels against the CPU oracle, called through the C ABI
+(fastpcc_b200.ops -> libfastpcc_b200.so).  Bit-exact: every comparison is array equality."""
+import numpy as np
+import pytest
+import torch
+
+from fastpcc_b200 import synth
+from oracle import int_ops as K
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ops():
+    from fastpcc_b200 import ops as _ops
+    return _ops
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _cloud(seed, n=3000, bits=7, batch=1):
+    rng = np.random.default_rng(seed)
+    out = []
+    for b in range(batch):
+        pts = np.unique(rng.integers(0, 1 << bits, (n, 3)), axis=0).astype(np.int32)
+        out.append(synth.with_batch(pts, b))
+    return np.concatenate(out)
+
+
+@pytest.mark.parametrize('ks,st', [((3, 3, 3), (1, 1, 1)), ((2, 2, 2), (2, 2, 2)), ((4, 4, 4), (4, 4, 4))])
+def test_kernel_map_lookup_and_compaction(ops, ks, st):
+    C = _cloud(0, batch=2)
+    if st == (1, 1, 1):
+        out_c = C
+    else:
+        oc = C.copy(); oc[:, 1:] //= st[0]
+        out_c = np.unique(oc, axis=0)
+    want = K.lookup_coords(C, out_c, ks, st)
+    keys, vals = ops.hash_build(dev(C))
+    table = ops.kmap_lookup(keys, vals, dev(out_c), ks, st)
+    assert (table.cpu().numpy() == want).all()
+    # reference layout [n_pad, kvol] through the mirror class (coords permuted to x,y,z,b)
+    from fastpcc_b200.int_sparse_conv import ext
+    ht = ext.GPUHashTable(torch.zeros(2 * C.shape[0], dtype=torch.int64, device='cuda'),
+                          torch.zeros(2 * C.shape[0], dtype=torch.int32, device='cuda'))
+    ht.insert_coords(dev(C[:, [1, 2, 3, 0]]))
+    t2 = ht.lookup_coords(dev(out_c[:, [1, 2, 3, 0]]), torch.tensor(ks, dtype=torch.int32, device='cuda'),
+                          torch.tensor(st, dtype=torch.int32, device='cuda'), int(np.prod(ks)))
+    assert t2.shape[0] % 128 == 0 and (t2[:out_c.shape[0]].T.cpu().numpy() == want).all()
+    assert (t2[out_c.shape[0]:] == 0).all()
+    # compaction == cuda_ops.py:132-151
+    omit = 13 if ks == (3, 3, 3) else -1
+    in_map, out_map, offsets = ops.kmap_compact(table, omit)
+    off = offsets.cpu().numpy()
+    ref = K.compact_kernel_map(want, omit)
+    for k, (im, om) in enumerate(ref):
+        a, b = off[k], off[k + 1]
+        if im is None:
+            assert a == b
+        else:
+            assert (in_map[a:b].cpu().numpy() == im).all() and (out_map[a:b].cpu().numpy() == om).all()
+
+
+def test_downsample_upsample_roundtrip(ops):
+    from oracle.lossl_coord_int import morton_xmajor
+    C = _cloud(3, n=5000, bits=8, batch=2)
+    order = np.lexsort((morton_xmajor(C[:, 1:]), C[:, 0]))
+    C = C[order]
+    # morton codes agree with the oracle
+    codes = ops.morton_encode(dev(C), col0=1, msb_axis=0).cpu().numpy()
+    assert (codes == morton_xmajor(C[:, 1:])).all()
+    pc, occ, par, slot, cnt = ops.downsample(dev(C))
+    n2 = int(cnt.item())
+    oc = C.copy(); oc[:, 1:] >>= 1
+    keep = np.ones(len(oc), bool); keep[1:] = (oc[1:] != oc[:-1]).any(1)
+    want_c = oc[keep]
+    assert n2 == want_c.shape[0] and (pc[:n2].cpu().numpy() == want_c).all()
+    # occupancy bits == fold2bin conv of the reference (model.py:271-277)
+    ones = np.ones((C.shape[0], 1), np.int8)
+    f, _ = K.sparse_conv_in8w8out32(ones, np.eye(8, dtype=np.int8).reshape(8, 8, 1), C, want_c, (2, 2, 2), (2, 2, 2), None, None, True)
+    bits = ops.occ_to_bits(occ[:n2].contiguous()).cpu().numpy()
+    assert (bits == f).all()
+    assert (par.cpu().numpy() == np.cumsum(keep) - 1).all()
+    assert (slot.cpu().numpy() == ((C[:, 1] & 1) << 2 | (C[:, 2] & 1) << 1 | (C[:, 3] & 1))).all()
+    cc, cpar, cslot, nchild = ops.upsample(pc[:n2].contiguous(), occ[:n2].contiguous())
+    assert nchild == C.shape[0] and (cc.cpu().numpy() == C).all()
+    assert (cpar.cpu().numpy() == par.cpu().numpy()).all() and (cslot.cpu().numpy() == slot.cpu().numpy()).all()
+
+
+def _epi_args(rng, ch, prelu, out8, zp=True):
+    mul = rng.integers(1 << 18, 1 << 22, ch).astype(np.uint32)
+    z = np.array([int(rng.integers(-(1 << 20), 1 << 20)) if zp else 0], np.int64)
+    slope = np.array([int(0.25 * (1 << 25))], np.int32) if prelu else None
+    shift = 24 if out8 else 6
+    return mul, z, slope, shift
+
+
+@pytest.mark.parametrize('cin,cout', [(1, 16), (8, 32), (16, 16), (64, 48), (100, 30), (128, 128), (264, 64)])
+@pytest.mark.parametrize('prelu,out8', [(True, True), (False, False)])
+def test_fused_sparse_conv(ops, cin, cout, prelu, out8):
+    rng = np.random.default_rng(cin * 1000 + cout)
+    C = _cloud(5, n=2500, bits=6)
+    n = C.shape[0]
+    f = rng.integers(-128, 128, (n, cin)).astype(np.int8)
+    w = rng.integers(-127, 128, (27, cout, cin)).astype(np.int8)
+    bias = rng.integers(-5000, 5000, cout).astype(np.int32)
+    mul, zp, slope, shift = _epi_args(rng, cout, prelu, out8)
+    acc, _ = K.sparse_conv_in8w8out32(f, w, C, C, (3, 3, 3), (1, 1, 1), None, None, True)
+    want = K.requant(acc, mul, zp, shift, np.int8 if out8 else np.int32, bias=bias, slope=slope)
+    keys, vals = ops.hash_build(dev(C))
+    table = ops.kmap_lookup(keys, vals, dev(C), (3, 3, 3), (1, 1, 1))
+    ep = ops.make_epilogue(dev(mul), dev(zp), shift, ops.OUT_I8 if out8 else ops.OUT_I32, bias=dev(bias),
+                           slope=dev(slope) if prelu else None)
+    got = ops.spconv(dev(f), dev(w), table, ep)
+    assert (got.cpu().numpy() == want).all()
+    # raw accumulator + mirror API of the reference (per-offset gather-GEMM-scatter, dense centre GEMM)
+    raw = ops.spconv(dev(f), dev(w), table, ops.identity_epilogue(torch.device('cuda', 0)))
+    assert (raw.cpu().numpy() == acc).all()
+
+
+def test_residual_epilogue_and_zero_point_comp(ops):
+    rng = np.random.default_rng(9)
+    C = _cloud(6, n=1500, bits=6)
+    n, ch = C.shape[0], 32
+    f = rng.integers(-128, 128, (n, ch)).astype(np.int8)
+    w = rng.integers(-127, 128, (27, ch, ch)).astype(np.int8)
+    bias = rng.integers(-5000, 5000, ch).astype(np.int32)
+    comp = rng.integers(-3000, 3000, (27, ch)).astype(np.int32)
+    res = rng.integers(-2 ** 31, 2 ** 31 - 1, (n, ch)).astype(np.int32)
+    mul, zp, _, shift = _epi_args(rng, ch, False, False, zp=False)
+    post = np.array([int(0.1 * (1 << 25))], np.int32)
+    acc, _ = K.sparse_conv_in8w8out32(f, w, C, C, (3, 3, 3), (1, 1, 1), None, comp, True)
+    y = K.requant(acc, mul, zp, shift, np.int32, bias=bias)
+    want = K.prelu(K._wrap32(res.astype(np.int64) + y.astype(np.int64)), post)
+    keys, vals = ops.hash_build(dev(C))
+    table = ops.kmap_lookup(keys, vals, dev(C), (3, 3, 3), (1, 1, 1))
+    ep = ops.make_epilogue(dev(mul), dev(zp), shift, ops.OUT_I32, bias=dev(bias), residual=dev(res), post_slope=dev(post))
+    got = ops.spconv(dev(f), dev(w), table, ep, zp_comp=dev(comp))
+    assert (got.cpu().numpy() == want).all()
+
+
+@pytest.mark.parametrize('m,k,n', [(1, 16, 8), (777, 264, 255), (300, 128, 2048), (64, 7, 5), (1000, 512, 256)])
+def test_linear_and_gemm(ops, m, k, n):
+    rng = np.random.default_rng(m + k + n)
+    a = rng.integers(-128, 128, (m, k)).astype(np.int8)
+    w = rng.integers(-127, 128, (n, k)).astype(np.int8)
+    bias = rng.integers(-100000, 100000, n).astype(np.int32)
+    mul, zp, slope, shift = _epi_args(rng, n, True, False)
+    want = K.requant(K.gemm_int8(a, w, bias), mul, zp, shift, np.int32, slope=slope)
+    ep = ops.make_epilogue(dev(mul), dev(zp), shift, ops.OUT_I32, bias=dev(bias), slope=dev(slope))
+    got = ops.linear(dev(a), dev(w), ep)
+    assert (got.cpu().numpy() == want).all()
+    from fastpcc_b200.int_sparse_conv import ext
+    d = torch.empty((m, n), dtype=torch.int32, device='cuda')
+    ext.cutlass_gemm_int8(dev(a), dev(w), dev(bias), d)
+    assert (d.cpu().numpy() == K.gemm_int8(a, w, bias)).all()
+    full = rng.integers(-1000, 1000, (m, n)).astype(np.int32)
+    ext.cutlass_gemm_int8(dev(a), dev(w), dev(full), d)
+    assert (d.cpu().numpy() == K.gemm_int8(a, w, full)).all()
+    ext.cutlass_gemm_int8(dev(a), dev(w), torch.empty(0, dtype=torch.int32, device='cuda'), d)
+    assert (d.cpu().numpy() == K.gemm_int8(a, w, None)).all()
+
+
+def test_selected_linear_equals_masked_dense(ops):
+    """Linear(C->8C) + child mask (model.py:64-66) == occupied-children-only evaluation."""
+    rng = np.random.default_rng(4)
+    n, ch = 900, 32
+    a = rng.integers(-128, 128, (n, ch)).astype(np.int8)
+    w = rng.integers(-127, 128, (8 * ch, ch)).astype(np.int8)
+    bias = rng.integers(-100000, 100000, 8 * ch).astype(np.int32)
+    mul, zp, _, shift = _epi_args(rng, 8 * ch, False, False)
+    occ = rng.integers(1, 256, n).astype(np.uint8)
+    dense = K.requant(K.gemm_int8(a, w, bias), mul, zp, shift, np.int32)
+    bits = ((occ[:, None] >> np.arange(7, -1, -1)[None]) & 1).astype(bool)
+    want = dense.reshape(n, 8, ch)[bits]
+    coords = dev(synth.with_batch(np.stack([np.arange(n), np.zeros(n), np.zeros(n)], 1).astype(np.int32)))
+    _, par, slot, nchild = ops.upsample(coords, dev(occ), want_coords=False)
+    sel = ops.slot_pairs(par, slot)
+    ep = ops.make_epilogue(dev(mul), dev(zp), shift, ops.OUT_I32, bias=dev(bias))
+    got = ops.linear(dev(a), dev(w), ep, sel=sel, n_out_rows=nchild)
+    assert got.shape == want.shape and (got.cpu().numpy() == want).all()
+
+
+def test_mirror_gather_gemm_scatter_and_requant_family(ops):
+    from fastpcc_b200.int_sparse_conv import ext
+    rng = np.random.default_rng(8)
+    m, k, n, L = 500, 24, 40, 320
+    a = rng.integers(-128, 128, (m, k)).astype(np.int8)
+    w = rng.integers(-127, 128, (n, k)).astype(np.int8)
+    d0 = rng.integers(-10 ** 6, 10 ** 6, (600, n)).astype(np.int32)
+    g = rng.integers(0, m, L).astype(np.int32)
+    s = rng.permutation(600)[:L].astype(np.int32)
+    want = d0.copy()
+    K.gather_gemm_scatter_int8(a, w, want, g, s)
+    d = dev(d0)
+    ext.cutlass_gather_gemm_scatter_int8(dev(a), dev(w), d, d, dev(g), dev(s))
+    assert (d.cpu().numpy() == want).all()
+    x = rng.integers(-2 ** 31, 2 ** 31 - 1, (257, 33)).astype(np.int32)
+    bias = rng.integers(-2 ** 20, 2 ** 20, 33).astype(np.int32)
+    mul = rng.integers(1, 2 ** 32 - 1, 33).astype(np.uint32)
+    zp = np.array([-12345678901], np.int64)
+    slope = np.array([-(1 << 24)], np.int32)
+    for shift in (0, 1, 17, 40):
+        for name, dt in (('int8', np.int8), ('int16', np.int16), ('int32', np.int32)):
+            for kind in ('', 'bias_', 'prelu_', 'bias_prelu_'):
+                fn = getattr(ext, f'{kind}requant_to_{name}')
+                args = [dev(x)] + ([dev(bias)] if 'bias' in kind else []) + ([dev(slope)] if 'prelu' in kind else []) \
+                    + [dev(mul), dev(zp), shift]
+                got = fn(*args).cpu().numpy()
+                want = K.requant(x, mul, zp, shift, dt, bias=bias if 'bias' in kind else None,
+                                 slope=slope if 'prelu' in kind else None)
+                assert got.dtype == dt and (got == want).all(), (kind, name, shift)
+    assert (ext.prelu(dev(x), dev(slope)).cpu().numpy() == K.prelu(x, slope)).all()
+    with pytest.raises(RuntimeError):
+        ext.requant_to_int8(dev(x), dev(mul), dev(zp), -1)
+
+
+@pytest.mark.parametrize('S', [255, 2, 64, 300])
+def test_softmax_and_cdf_head(ops, S):
+    from fastpcc_b200.int_sparse_conv import ext
+    rng = np.random.default_rng(S)
+    n = 1000
+    logits = (rng.normal(0, 4, (n, S)) * (1 << 23)).clip(-2 ** 31, 2 ** 31 - 1).astype(np.int32)
+    logits[0] = 0
+    logits[1] = -2 ** 31
+    logits[2, 0] = 2 ** 31 - 1
+    sm = ext.softmax_int32(dev(logits >> 7)).cpu().numpy()
+    assert (sm.view(np.uint32) == K.softmax_int32(logits >> 7)).all()
+    want = K.batch_quantize_pmf(logits)
+    cdf = ops.quantize_cdf(dev(logits), ld=max(256, S)).cpu().numpy().view(np.uint16)
+    assert (cdf[:, :S] == want).all() and (cdf[:, S:] == 0xFFFF).all()
+    sym = rng.integers(0, S, n).astype(np.int32)
+    sym[:3] = [0, S - 1, S - 1]
+    rngs = ops.cdf_symbol_ranges(dev(logits), dev(sym)).cpu().numpy().view(np.uint32)
+    w64 = want.astype(np.int64)
+    lo = np.where(sym == 0, 0, w64[np.arange(n), np.maximum(sym - 1, 0)])
+    hi = np.where(sym == S - 1, 65536, w64[np.arange(n), sym])
+    assert ((rngs & 0xFFFF) == lo).all() and ((rngs >> 16) + 1 == hi - lo).all()
