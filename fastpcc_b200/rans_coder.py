@@ -17,7 +17,7 @@ from .ops import _p, _s
 
 
 def _dev(a, dtype=None):
-    t = torch.from_numpy(np.ascontiguousarray(a))
+    t = torch.from_numpy(np.array(a, copy=True, order='C'))
     if dtype is not None:
         t = t.to(dtype)
     return t.cuda()
@@ -211,7 +211,8 @@ class BinaryRansCoder:
         assert sym.ndim == 2 and sym.shape == prob.shape and sym.shape[0] == self.batch_size
         B, n = sym.shape
         ranges = torch.empty(B * n, dtype=torch.int32, device='cuda')
-        _lib.call('fpcc_rans_binary_ranges', _p(_dev(sym)), _p(_dev(prob.view(np.int32))), B * n, _p(ranges), _s())
+        d_sym, d_prob = _dev(sym), _dev(prob.view(np.int32))  # named: both must stay alive until the launch
+        _lib.call('fpcc_rans_binary_ranges', _p(d_sym), _p(d_prob), B * n, _p(ranges), _s())
         rng_off = torch.arange(0, (B + 1) * n, n, dtype=torch.int64, device='cuda')
         cap = 2 * n + 64
         out, out_len = ops.rans_encode(ranges, rng_off, cap)
@@ -228,7 +229,8 @@ class BinaryRansCoder:
         out = torch.empty((B, n), dtype=torch.uint8, device='cuda')
         err = torch.zeros(1, dtype=torch.int32, device='cuda')
         d_blob, d_off, d_len = _dev(blob), _dev(np.concatenate([[0], np.cumsum(lens[:-1])]).astype(np.int64)), _dev(lens)
-        _lib.call('fpcc_rans_binary_decode', _p(d_blob), _p(d_off), _p(d_len), _p(_dev(prob.view(np.int32))), n, B, _p(out), _p(err), _s())
+        d_prob = _dev(prob.view(np.int32))
+        _lib.call('fpcc_rans_binary_decode', _p(d_blob), _p(d_off), _p(d_len), _p(d_prob), n, B, _p(out), _p(err), _s())
         symbol_array[...] = out.cpu().numpy().astype(np.bool_)
         if int(err.item()):
             raise RuntimeError('BinaryRansCoder: read past the end of a stream')
