@@ -57,10 +57,12 @@ __device__ __forceinline__ uint32_t hash_slot(uint64_t key, uint32_t capacity) {
 }
 
 // ---- integer epilogue arithmetic (bias_prelu_requant.cu:6-37, prelu.cu:6-21) ---------------------
-__device__ __forceinline__ int64_t rha_shift(int64_t v, int s) {  // round half away from zero
+// round-half-away-from-zero arithmetic shift: sign(v) * ((|v| + 2^(s-1)) >> s)  (requant.cu:16-20).
+// For v < 0:  -((-v + h) >> s) = ceil((v - h) / 2^s) = (v + h - 1) >> s  with h = 2^(s-1), so one branch-free
+// form serves both signs: (v + h - [v < 0]) >> s.
+__device__ __forceinline__ int64_t rha_shift(int64_t v, int s) {
     if (s <= 0) return v;
-    int64_t half = (int64_t)1 << (s - 1);
-    return v >= 0 ? ((v + half) >> s) : -((-v + half) >> s);
+    return (v + (((int64_t)1 << (s - 1)) - (int64_t)((uint64_t)v >> 63))) >> s;
 }
 __device__ __forceinline__ int64_t prelu_q25(int64_t v, int32_t slope) {
     return v < 0 ? rha_shift(v * (int64_t)slope, 25) : v;

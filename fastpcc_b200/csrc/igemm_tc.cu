@@ -134,6 +134,7 @@ struct TcArgs {
     // MODE_PAIRS
     const int32_t *in_idx, *out_idx, *offsets;
     int n_groups, n_pairs, bias_per_group;
+    int dbg;  // FPCC_TC_DEBUG bitmask (experiments only): 1 skip A loads, 2 skip B loads, 4 skip epilogue math, 8 skip MMA
 };
 
 template <int STAGES>
@@ -242,10 +243,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_tc_kernel(TcArgs a, const
             const int32_t src = rows_s[(MODE == 0 ? k : 0) * TC_M + r];
             const int8_t *gsrc = a.A + (src >= 0 ? (int64_t)src * a.K : 0) + kc * TC_KB;
             const uint32_t dst = smem_u32(sA + stage * TcSmem<STAGES>::a_bytes) + row_smem;
+            if (!(a.dbg & 1)) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const bool ok = src >= 0 && kc * TC_KB + c * 16 < a.K;
-                cp_async16(dst + ((c ^ sw) << 4), ok ? (const void *)(gsrc + c * 16) : (const void *)a.A, ok ? 16u : 0u);
+                for (int c = 0; c < 8; ++c) {
+                    const bool ok = src >= 0 && kc * TC_KB + c * 16 < a.K;
+                    cp_async16(dst + ((c ^ sw) << 4), ok ? (const void *)(gsrc + c * 16) : (const void *)a.A, ok ? 16u : 0u);
+                }
             }
             cp_async_commit();
             if (i >= STAGES - 1) {
@@ -278,6 +281,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_tc_kernel(TcArgs a, const
                 for (int j = 0; j < 32; ++j) acc[j] = 0;
             }
             if (!row_ok) continue;
+            if (a.dbg & 4) { if (c0 == 0) ((int32_t *)out)[m] = (int32_t)acc[0]; continue; }
             const int nb = n0 + c0;
             if (nb >= a.N) continue;
             const int64_t obase = m * a.N + nb;
@@ -314,6 +318,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_tc_kernel(TcArgs a, const
                 if (kc == 0) { k = __ffs(rem) - 1; rem &= rem - 1; }
                 const int stage = i % STAGES;
                 mbar_wait(&empty[stage], ((i / STAGES) & 1) ^ 1);
+                if (a.dbg & 2) { mbar_arrive(&full[stage]); continue; }
                 mbar_expect_tx(&full[stage], (uint32_t)b_bytes);
                 const int wrow = (MODE == 0 ? k : group) * a.N + n0;
                 tma_load_2d(smem_u32(sB + (size_t)stage * b_bytes), &tmap_w, &full[stage], kc * TC_KB, wrow);
@@ -329,9 +334,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_tc_kernel(TcArgs a, const
                 tc_fence_after();
                 const uint64_t ad = umma_desc_sw128(smem_u32(sA + stage * TcSmem<STAGES>::a_bytes));
                 const uint64_t bd = umma_desc_sw128(smem_u32(sB + (size_t)stage * b_bytes));
+                if (!(a.dbg & 8)) {
 #pragma unroll
-                for (int j = 0; j < TC_KB / 32; ++j)  // kind::i8: K = 32 bytes per instruction; +32 B = +2 in the address field
-                    umma_i8(tmem_base, ad + 2 * j, bd + 2 * j, idesc, (uint32_t)(i > 0 || j > 0));
+                    for (int j = 0; j < TC_KB / 32; ++j)  // kind::i8: K = 32 bytes per instruction; +32 B = +2 in the address field
+                        umma_i8(tmem_base, ad + 2 * j, bd + 2 * j, idesc, (uint32_t)(i > 0 || j > 0));
+                }
                 umma_commit(&empty[stage]);  // frees the smem stage once these MMAs have read it
             }
             if (total > 0) umma_commit(tmem_full);
@@ -342,6 +349,366 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_tc_kernel(TcArgs a, const
     if (warp == 5) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols) : "memory");
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// persistent kernel (v2): one CTA per SM loops over tiles; the accumulator is double-buffered in TMEM so the
+// epilogue of tile t (8 warps, int64 requant arithmetic) overlaps the gathers + MMAs of tile t+1; TMEM
+// allocation, barrier setup and weight-descriptor prefetch are paid once per CTA instead of once per tile.
+//
+//   warps 0-7   epilogue: TMEM lane quarter = warp % 4, column half = warp / 4
+//   warps 8-11  gather producers (one output row per thread) + per-tile metadata (source rows, offset mask)
+//   warp 12     weight producer (TMA)          warp 13   TMEM owner + MMA issuer
+// ---------------------------------------------------------------------------------------------
+constexpr int P_THREADS = 448;
+constexpr int P_EPI_WARPS = 8;
+constexpr int P_PROD_WARP0 = 8;
+
+struct PMeta {  // per-tile metadata, double buffered
+    uint32_t kmask;
+    int32_t group, begin, end;
+};
+
+template <int STAGES>
+struct PSmem {
+    static size_t bytes(int n_tile, int rows_k) {
+        return 1024 + (size_t)STAGES * (TC_M * TC_KB + (size_t)n_tile * TC_KB) + 2 * (size_t)rows_k * TC_M * 4 +
+               (size_t)n_tile * 8 + 512;
+    }
+};
+
+__device__ __forceinline__ void pairs_tile_lookup(const TcArgs &a, int tile_m, PMeta *m) {
+    int g = 0, begin = tile_m * TC_M, end = a.n_pairs;
+    if (a.offsets) {
+        int t = tile_m;
+        begin = end = -1;
+        for (g = 0; g < a.n_groups; ++g) {
+            int lo = a.offsets[g], hi = a.offsets[g + 1];
+            int nt = (hi - lo + TC_M - 1) / TC_M;
+            if (t < nt) { begin = lo + t * TC_M; end = hi; break; }
+            t -= nt;
+        }
+    }
+    m->group = g; m->begin = begin; m->end = end;
+}
+
+template <int MODE, int STAGES>
+__global__ void __launch_bounds__(P_THREADS, 1) igemm_tc_persistent(TcArgs a, const __grid_constant__ CUtensorMap tmap_w,
+                                                                    EpiParams ep, void *__restrict__ out, int tiles_m,
+                                                                    int tiles_n) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int b_bytes = a.n_tile * TC_KB;
+    constexpr int a_bytes = TC_M * TC_KB;
+    uint8_t *sA = smem;
+    uint8_t *sB = smem + STAGES * a_bytes;
+    const int rows_k = MODE == 0 ? a.kvol : 2;
+    int32_t *rows_s = (int32_t *)(sB + (size_t)STAGES * b_bytes);  // [2 slots][rows_k][128]
+    int2 *chan_s = (int2 *)(rows_s + 2 * rows_k * TC_M);          // [n_tile] (bias, mul) of the current channel block
+    uint64_t *bars = (uint64_t *)(chan_s + a.n_tile);
+    uint64_t *full = bars, *empty = bars + STAGES;
+    uint64_t *meta_full = bars + 2 * STAGES, *tmem_full = meta_full + 2, *tmem_empty = tmem_full + 2;
+    PMeta *meta = (PMeta *)(tmem_empty + 2);
+    uint32_t *tmem_ptr = (uint32_t *)(meta + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_chunks = (a.K + TC_KB - 1) / TC_KB;
+    const int total_tiles = tiles_m * tiles_n;
+
+    if (warp == 13 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], TC_M + 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&meta_full[b], TC_M);
+            mbar_init(&tmem_full[b], 1);
+            mbar_init(&tmem_empty[b], P_EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 12 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+    if (warp == 13) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"((uint32_t)(2 * a.tmem_cols)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // per-channel epilogue constants of a single channel block are staged once (grouped weights reload per tile)
+    const bool chan_static = tiles_n == 1 && !(MODE == 1 && a.bias_per_group);
+    if (chan_static)
+        for (int c = tid; c < a.n_tile; c += P_THREADS)
+            chan_s[c] = c < a.N ? make_int2(ep.bias ? ep.bias[c] : 0, (int)ep.mul[ep.mul_is_scalar ? 0 : c]) : make_int2(0, 0);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp >= P_PROD_WARP0 && warp < P_PROD_WARP0 + 4) {
+        // ================= metadata + gather producers =================
+        const int r = tid - P_PROD_WARP0 * 32;
+        const uint32_t row_smem = r * TC_KB, sw = r & 7;
+        int it = 0;       // running pipeline step across tiles
+        int arrived = 0;  // steps [0, arrived) have been published on their full barrier
+        int j = 0;        // local tile counter
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
+            const int slot = j & 1;
+            const int tile_m = tile / tiles_n;
+            int32_t *rows = rows_s + slot * rows_k * TC_M;
+            mbar_wait(&tmem_empty[slot], ((j >> 1) & 1) ^ 1);  // slot's previous tile (j-2) fully consumed
+            if (r == 0) meta[slot].kmask = 0;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (MODE == 0) {
+                const int m = tile_m * TC_M + r;
+                uint32_t mine = 0;
+                for (int k = 0; k < a.kvol; ++k) {
+                    int32_t v = m < a.n_out ? __ldg(&a.nbr[(int64_t)k * a.ld + m]) : 0;
+                    rows[k * TC_M + r] = v - 1;
+                    mine |= (uint32_t)(v != 0) << k;
+                }
+                mine = __reduce_or_sync(0xffffffffu, mine);
+                if (lane == 0 && mine) atomicOr(&meta[slot].kmask, mine);
+            } else {
+                if (r == 0) { pairs_tile_lookup(a, tile_m, &meta[slot]); }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int p = meta[slot].begin + r;
+                const bool ok = meta[slot].begin >= 0 && p < meta[slot].end;
+                rows[r] = ok ? (a.in_idx ? __ldg(&a.in_idx[p]) : p) : -1;
+                rows[TC_M + r] = ok ? (a.out_idx ? __ldg(&a.out_idx[p]) : p) : -1;
+                if (r == 0) meta[slot].kmask = meta[slot].begin >= 0 && meta[slot].begin < meta[slot].end ? 1u : 0u;
+            }
+            __threadfence_block();
+            mbar_arrive(&meta_full[slot]);
+            mbar_wait(&meta_full[slot], (j >> 1) & 1);
+            uint32_t rem = meta[slot].kmask;
+            const int total = __popc(rem) * n_chunks;
+            int k = 0;
+            for (int i = 0; i < total; ++i, ++it) {
+                const int kc = i % n_chunks;
+                if (kc == 0) { k = __ffs(rem) - 1; rem &= rem - 1; }
+                const int stage = it % STAGES;
+                mbar_wait(&empty[stage], ((it / STAGES) & 1) ^ 1);
+                const int32_t src = rows[(MODE == 0 ? k : 0) * TC_M + r];
+                const int8_t *gsrc = a.A + (src >= 0 ? (int64_t)src * a.K : 0) + kc * TC_KB;
+                const uint32_t dst = smem_u32(sA + stage * a_bytes) + row_smem;
+                if (!(a.dbg & 1)) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const bool ok = src >= 0 && kc * TC_KB + c * 16 < a.K;
+                        cp_async16(dst + ((c ^ sw) << 4), ok ? (const void *)(gsrc + c * 16) : (const void *)a.A, ok ? 16u : 0u);
+                    }
+                }
+                cp_async_commit();
+                if (it - arrived >= STAGES - 1) {  // keep at most STAGES-1 steps in flight per thread
+                    cp_async_wait<STAGES - 1>();
+                    fence_proxy_async();
+                    for (; arrived <= it - (STAGES - 1); ++arrived) mbar_arrive(&full[arrived % STAGES]);
+                }
+            }
+            // Publish the tail of this tile before blocking on the next tile's accumulator: the MMAs of this
+            // tile (and through them the epilogue that frees that accumulator) wait for these arrivals.
+            cp_async_wait<0>();
+            fence_proxy_async();
+            for (; arrived < it; ++arrived) mbar_arrive(&full[arrived % STAGES]);
+        }
+    } else if (warp == 12) {
+        // ================= weight producer (TMA) =================
+        if (lane == 0) {
+            int it = 0, j = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
+                const int slot = j & 1;
+                const int n0 = (tile % tiles_n) * a.n_tile;
+                mbar_wait(&meta_full[slot], (j >> 1) & 1);
+                uint32_t rem = meta[slot].kmask;
+                const int total = __popc(rem) * n_chunks;
+                const int group = MODE == 1 ? meta[slot].group : 0;
+                int k = 0;
+                for (int i = 0; i < total; ++i, ++it) {
+                    const int kc = i % n_chunks;
+                    if (kc == 0) { k = __ffs(rem) - 1; rem &= rem - 1; }
+                    const int stage = it % STAGES;
+                    mbar_wait(&empty[stage], ((it / STAGES) & 1) ^ 1);
+                    if (a.dbg & 2) { mbar_arrive(&full[stage]); continue; }
+                    mbar_expect_tx(&full[stage], (uint32_t)b_bytes);
+                    const int wrow = (MODE == 0 ? k : group) * a.N + n0;
+                    tma_load_2d(smem_u32(sB + (size_t)stage * b_bytes), &tmap_w, &full[stage], kc * TC_KB, wrow);
+                }
+            }
+        }
+    } else if (warp == 13) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_i8(a.n_tile);
+            int it = 0, j = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
+                const int slot = j & 1;
+                mbar_wait(&meta_full[slot], (j >> 1) & 1);
+                const int total = __popc(meta[slot].kmask) * n_chunks;
+                mbar_wait(&tmem_empty[slot], ((j >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + (uint32_t)(slot * a.tmem_cols);
+                for (int i = 0; i < total; ++i, ++it) {
+                    const int stage = it % STAGES;
+                    mbar_wait(&full[stage], (it / STAGES) & 1);
+                    tc_fence_after();
+                    const uint64_t ad = umma_desc_sw128(smem_u32(sA + stage * a_bytes));
+                    const uint64_t bd = umma_desc_sw128(smem_u32(sB + (size_t)stage * b_bytes));
+                    if (!(a.dbg & 8)) {
+#pragma unroll
+                        for (int q = 0; q < TC_KB / 32; ++q)
+                            umma_i8(tacc, ad + 2 * q, bd + 2 * q, idesc, (uint32_t)(i > 0 || q > 0));
+                    }
+                    umma_commit(&empty[stage]);
+                }
+                if (total > 0) umma_commit(&tmem_full[slot]);
+                else mbar_arrive(&tmem_full[slot]);
+            }
+        }
+    } else if (warp < P_EPI_WARPS) {
+        // ================= epilogue =================
+        const int quarter = warp & 3, half = warp >> 2;
+        const int r = quarter * 32 + lane;  // tile row == TMEM lane
+        const bool has_slope = ep.slope != nullptr, has_post = ep.post_slope != nullptr;
+        const int32_t slope = has_slope ? ep.slope[0] : 0, post = has_post ? ep.post_slope[0] : 0;
+        const int64_t zp = ep.zp[0];
+        const int shift = ep.shift;
+        const int cols_half = ((a.n_tile / 2 + 31) / 32) * 32;  // columns per half, multiple of 32
+        const int c_begin = half * cols_half, c_end = min(a.n_tile, c_begin + cols_half);
+        int j = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
+            const int slot = j & 1;
+            const int tile_m = tile / tiles_n, n0 = (tile % tiles_n) * a.n_tile;
+            mbar_wait(&meta_full[slot], (j >> 1) & 1);
+            const bool have_acc = meta[slot].kmask != 0;
+            const int pbase = (MODE == 1 && a.bias_per_group) ? meta[slot].group * a.N : 0;
+            const int32_t *rows = rows_s + slot * rows_k * TC_M;
+            const int64_t m = MODE == 0 ? (int64_t)tile_m * TC_M + r : (int64_t)rows[TC_M + r];
+            const bool row_ok = MODE == 0 ? (m < a.n_out) : (m >= 0);
+            mbar_wait(&tmem_full[slot], (j >> 1) & 1);
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + (uint32_t)(slot * a.tmem_cols) + ((uint32_t)(quarter * 32) << 16);
+            for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+                uint32_t acc[32];
+                if (have_acc) {
+                    tmem_ld32(tacc + (uint32_t)c0, acc);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) acc[q] = 0;
+                }
+                const int nb = n0 + c0;
+                if (!row_ok || nb >= a.N) continue;
+                if (a.dbg & 4) { if (c0 == 0) ((int32_t *)out)[m] = (int32_t)acc[0]; continue; }
+                const int64_t obase = m * a.N + nb;
+                const bool full32 = nb + 32 <= a.N;
+                int32_t o32[32];
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    int2 bm;
+                    if (chan_static) bm = chan_s[c0 + q];
+                    else {
+                        const int pc = min(pbase + nb + q, pbase + a.N - 1);
+                        bm = make_int2(ep.bias ? __ldg(&ep.bias[pc]) : 0, (int)__ldg(&ep.mul[ep.mul_is_scalar ? 0 : pc]));
+                    }
+                    int64_t v = (int64_t)(int32_t)acc[q] + (int64_t)bm.x;
+                    if (has_slope) {
+                        const int64_t t = rha_shift(v * (int64_t)slope, 25);
+                        v = v < 0 ? t : v;
+                    }
+                    const int64_t o = rha_shift(v * (int64_t)(uint32_t)bm.y + zp, shift);
+                    if (ep.out_type == FPCC_OUT_I8) o32[q] = (int32_t)(o < -128 ? -128 : (o > 127 ? 127 : o));
+                    else if (ep.out_type == FPCC_OUT_I16) o32[q] = (int32_t)(o < -32768 ? -32768 : (o > 32767 ? 32767 : o));
+                    else o32[q] = clamp_i32(o);
+                }
+                if (ep.out_type == FPCC_OUT_I8 && full32 && (a.N & 15) == 0) {
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        pk[q] = (uint32_t)(o32[4 * q] & 0xff) | ((uint32_t)(o32[4 * q + 1] & 0xff) << 8) |
+                                ((uint32_t)(o32[4 * q + 2] & 0xff) << 16) | ((uint32_t)(o32[4 * q + 3] & 0xff) << 24);
+                    uint4 *dst = reinterpret_cast<uint4 *>((int8_t *)out + obase);
+                    dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                } else if (ep.out_type == FPCC_OUT_I32 && full32 && (a.N & 3) == 0) {
+                    int4 *dst = reinterpret_cast<int4 *>((int32_t *)out + obase);
+                    const int4 *res = ep.residual ? reinterpret_cast<const int4 *>(ep.residual + obase) : nullptr;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        int4 v = make_int4(o32[4 * q], o32[4 * q + 1], o32[4 * q + 2], o32[4 * q + 3]);
+                        if (res) {
+                            const int4 rr = __ldg(&res[q]);
+                            v.x = (int32_t)((uint32_t)v.x + (uint32_t)rr.x); v.y = (int32_t)((uint32_t)v.y + (uint32_t)rr.y);
+                            v.z = (int32_t)((uint32_t)v.z + (uint32_t)rr.z); v.w = (int32_t)((uint32_t)v.w + (uint32_t)rr.w);
+                            if (has_post) {
+                                v.x = clamp_i32(prelu_q25(v.x, post)); v.y = clamp_i32(prelu_q25(v.y, post));
+                                v.z = clamp_i32(prelu_q25(v.z, post)); v.w = clamp_i32(prelu_q25(v.w, post));
+                            }
+                        }
+                        dst[q] = v;
+                    }
+                } else {
+                    for (int q = 0; q < 32 && nb + q < a.N; ++q) {
+                        const int64_t idx = obase + q;
+                        if (ep.out_type == FPCC_OUT_I8) ((int8_t *)out)[idx] = (int8_t)o32[q];
+                        else if (ep.out_type == FPCC_OUT_I16) ((int16_t *)out)[idx] = (int16_t)o32[q];
+                        else {
+                            int32_t rv = o32[q];
+                            if (ep.residual) {
+                                rv = (int32_t)((uint32_t)rv + (uint32_t)ep.residual[idx]);
+                                if (has_post) rv = clamp_i32(prelu_q25((int64_t)rv, post));
+                            }
+                            ((int32_t *)out)[idx] = rv;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[slot]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 13) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * a.tmem_cols)) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tensor-pipe ceiling probe: back-to-back kind::i8 MMAs (M=128, N=256, K=32) on resident smem tiles, no
+// loads in the loop.  Gives the measured int8 peak that the roofline of this kernel is quoted against.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) mma_i8_peak_kernel(int iters, int n) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t done;
+    __shared__ uint32_t tmem_ptr;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < (TC_M * TC_KB + 256 * TC_KB) / 4; i += blockDim.x) ((uint32_t *)smem)[i] = 0x01010101u;
+    if (threadIdx.x == 0) {
+        mbar_init(&done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_ptr)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_ptr;
+    if (warp == 1 && lane == 0) {
+        const uint32_t idesc = umma_idesc_i8(n);
+        const uint64_t ad = umma_desc_sw128(smem_u32(smem));
+        const uint64_t bd = umma_desc_sw128(smem_u32(smem + TC_M * TC_KB));
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) umma_i8(tmem_base, ad + 2 * j, bd + 2 * j, idesc, 1u);
+        }
+        umma_commit(&done);
+    }
+    mbar_wait(&done, 0);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -412,11 +779,30 @@ static int pick_tile(int N, int *n_tile, int *tmem_cols) {
 template <int MODE>
 static int launch_tc(TcArgs &a, const int8_t *W, int64_t w_rows, int tiles_m, const EpiParams &ep, void *out, cudaStream_t s) {
     int n_blocks_n = pick_tile(a.N, &a.n_tile, &a.tmem_cols);
+    { const char *e = getenv("FPCC_TC_DEBUG"); a.dbg = e ? atoi(e) : 0; }
     CUtensorMap tmap;
     int rc = weight_tensor_map(W, w_rows, a.K, a.n_tile, &tmap);
     if (rc) return rc;
     constexpr int STAGES = 4;
     const int rows_k = MODE == 0 ? a.kvol : 2;
+    static int version = -1;
+    if (version < 0) { const char *e = getenv("FPCC_TC_V"); version = e ? atoi(e) : 2; }
+    if (version == 2) {
+        size_t smem2 = PSmem<STAGES>::bytes(a.n_tile, rows_k);
+        if (smem2 <= 227 * 1024) {
+            auto kern2 = igemm_tc_persistent<MODE, STAGES>;
+            static bool configured2 = false;
+            if (!configured2) {
+                FPCC_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                configured2 = true;
+            }
+            int total = tiles_m * n_blocks_n;
+            int grid = total < sm_count() ? total : sm_count();
+            kern2<<<grid, P_THREADS, smem2, s>>>(a, tmap, ep, out, tiles_m, n_blocks_n);
+            FPCC_LAUNCH_CHECK();
+            return FPCC_OK;
+        }
+    }
     size_t smem = TcSmem<STAGES>::bytes(a.n_tile, rows_k);
     auto kern = igemm_tc_kernel<MODE, STAGES>;
     static bool configured = false;
@@ -453,6 +839,29 @@ int launch_pairs_tc(const PairArgs &p, const EpiParams &ep, void *out, int max_t
 }
 
 }  // namespace fpcc
+
+extern "C" int fpcc_mma_i8_peak(int iters, int n, double *tops_out, void *stream) {
+    using namespace fpcc;
+    FPCC_REQUIRE(iters > 0 && tops_out && n >= 16 && n <= 256 && n % 16 == 0, "mma_i8_peak: bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    size_t smem = 1024 + TC_M * TC_KB + 256 * TC_KB;
+    FPCC_CUDA(cudaFuncSetAttribute(mma_i8_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEvent_t e0, e1;
+    FPCC_CUDA(cudaEventCreate(&e0));
+    FPCC_CUDA(cudaEventCreate(&e1));
+    int sms = sm_count();
+    mma_i8_peak_kernel<<<sms, 128, smem, s>>>(iters / 8 + 1, n);  // warm-up
+    FPCC_CUDA(cudaEventRecord(e0, s));
+    mma_i8_peak_kernel<<<sms, 128, smem, s>>>(iters, n);
+    FPCC_CUDA(cudaEventRecord(e1, s));
+    FPCC_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    FPCC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tops_out = 2.0 * TC_M * n * 32.0 * 4.0 * iters * sms / (ms * 1e-3) / 1e12;
+    return FPCC_OK;
+}
 
 extern "C" int fpcc_gemm_engine(int k, int n, int kvol, int has_zp_comp) {
     return fpcc::tc_enabled() && !has_zp_comp && k >= 32 && k % 16 == 0 && n >= 16 && kvol <= fpcc::TC_MAX_KVOL;

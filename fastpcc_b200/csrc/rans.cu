@@ -42,7 +42,8 @@ __device__ __forceinline__ EncSym make_enc_sym(uint32_t start, uint32_t freq, ui
 }
 
 // One warp per stream.  Entries of stream b are ranges[rng_off[b] .. rng_off[b+1]) in DECODE order and are
-// consumed back to front (rANS is LIFO).  Bytes are written backwards from the end of the stream's slot.
+// consumed back to front (rANS is LIFO).  Bytes are written backwards from the end of the stream's slot;
+// they are collected four at a time in a register and stored as aligned words.
 __global__ void __launch_bounds__(32) rans_encode_kernel(const uint32_t *__restrict__ ranges, const uint8_t *__restrict__ bits,
                                                          const int64_t *__restrict__ rng_off, uint8_t *__restrict__ out,
                                                          int64_t out_stride, int32_t *__restrict__ out_len,
@@ -59,6 +60,9 @@ __global__ void __launch_bounds__(32) rans_encode_kernel(const uint32_t *__restr
         uint32_t written = state_io[2 * b + 1];
         if (written == 0xFFFFFFFFu) overflow = true; else ptr -= written;
     }
+    const bool bytewise = ((uintptr_t)ptr & 3) != 0;  // unaligned resume point: plain byte stores
+    uint32_t acc = 0;
+    int nacc = 0;
     for (int64_t top = hi; top > lo; top -= 32) {
         int64_t i = top - 1 - lane;  // lane 0 holds the entry coded first
         EncSym es = {};
@@ -66,24 +70,32 @@ __global__ void __launch_bounds__(32) rans_encode_kernel(const uint32_t *__restr
             uint32_t r = ranges[i];
             es = make_enc_sym(r & 0xFFFFu, (r >> 16) + 1u, bits ? (uint32_t)bits[i] : 16u);
         }
+        const uint32_t my_pk = (uint32_t)es.cmpl | ((uint32_t)es.rcp_shift << 16);
         int cnt = (int)min((int64_t)32, top - lo);
         for (int j = 0; j < cnt; ++j) {
             uint32_t x_max = __shfl_sync(0xffffffffu, es.x_max, j);
             uint32_t rcp = __shfl_sync(0xffffffffu, es.rcp, j);
             uint32_t bias = __shfl_sync(0xffffffffu, es.bias, j);
-            uint32_t pk = __shfl_sync(0xffffffffu, (uint32_t)es.cmpl | ((uint32_t)es.rcp_shift << 16), j);
-            while (x >= x_max) {  // RansEncRenorm, rans_byte.h:77-89
-                if (ptr > guard) {
-                    --ptr;
-                    if (lane == 0) *ptr = (uint8_t)(x & 0xff);
-                } else {
-                    overflow = true;
-                }
+            uint32_t pk = __shfl_sync(0xffffffffu, my_pk, j);
+            while (x >= x_max) {  // RansEncRenorm, rans_byte.h:77-89 (at most two bytes at 16-bit precision)
+                uint32_t byte = x & 0xffu;
                 x >>= 8;
+                if (bytewise) {
+                    if (ptr > guard) { --ptr; if (lane == 0) *ptr = (uint8_t)byte; } else overflow = true;
+                } else {
+                    acc = (acc << 8) | byte;  // first byte emitted ends up at the highest address
+                    if (++nacc == 4) {
+                        if (ptr - 4 >= guard) { ptr -= 4; if (lane == 0) *reinterpret_cast<uint32_t *>(ptr) = acc; } else overflow = true;
+                        nacc = 0;
+                    }
+                }
             }
             uint32_t q = __umulhi(x, rcp) >> (pk >> 16);
             x = x + bias + q * (pk & 0xFFFFu);
         }
+    }
+    for (int t = 0; t < nacc; ++t) {  // bytes still held in the register
+        if (ptr > guard) { --ptr; if (lane == 0) *ptr = (uint8_t)(acc >> (8 * (nacc - 1 - t))); } else overflow = true;
     }
     if (!do_flush) {
         if (lane == 0) {
@@ -136,54 +148,92 @@ __device__ __forceinline__ uint32_t dec_advance(uint32_t x, ByteReader &br, uint
     return x;
 }
 
-// One warp per stream; all lanes carry the same state.  Fast path: per-symbol rows of S <= 256 entries
-// stored with a 256-entry (512 B) pitch -> one aligned 16-byte load per lane per symbol.
+// Big-endian window over the byte stream (next byte on top), refilled with aligned 32-bit loads that are
+// issued one refill ahead of their use.  Reads at most 3 bytes before / 7 bytes past the stream.
+struct ByteWindow {
+    const uint32_t *wp;
+    uint64_t win;
+    int avail;
+    uint32_t nextw;
+    __device__ __forceinline__ void init(const uint8_t *p) {
+        uintptr_t a = (uintptr_t)p;
+        uint32_t mis = (uint32_t)(a & 3);
+        wp = reinterpret_cast<const uint32_t *>(a - mis);
+        uint32_t w = __byte_perm(*wp++, 0, 0x0123);
+        win = (uint64_t)(w << (8 * mis)) << 32;
+        avail = 4 - (int)mis;
+        nextw = *wp++;
+        refill();
+    }
+    __device__ __forceinline__ void refill() {
+        if (avail <= 4) {
+            win |= (uint64_t)__byte_perm(nextw, 0, 0x0123) << (32 - 8 * avail);
+            avail += 4;
+            nextw = *wp++;
+        }
+    }
+    __device__ __forceinline__ uint32_t take(int n) {  // n in {0,1,2}: next n bytes, first byte most significant
+        uint32_t v = n ? (uint32_t)(win >> (64 - 8 * n)) : 0u;
+        win <<= 8 * n;
+        avail -= n;
+        refill();
+        return v;
+    }
+};
+
+// One warp per stream; all lanes carry the same state.  Fast path: per-symbol rows of S <= 256 entries with a
+// 256-entry (512 B) pitch.  The symbol search is two ballots: a coarse one over every 8th entry (prefetched 8
+// symbols ahead, it does not depend on the coder state) and a fine one over the 9 entries around the hit.
 __global__ void __launch_bounds__(32) rans_decode_kernel(fpcc_rans_dec_state *st, const uint8_t *__restrict__ bytes,
                                                          const int64_t *__restrict__ byte_off, const uint16_t *__restrict__ cdf,
                                                          int64_t n_cdf, int S, int ld, const int64_t *__restrict__ row_off,
-                                                         int32_t *__restrict__ symbols) {
+                                                         int32_t *__restrict__ symbols, int rows_per_stream,
+                                                         const int32_t *__restrict__ s_per_stream) {
     const int b = blockIdx.x, lane = threadIdx.x;
+    if (s_per_stream) S = s_per_stream[b];
     fpcc_rans_dec_state s = st[b];
     ByteReader br = {bytes + byte_off[b], s.pos, s.len, s.err};
     uint32_t x = s.x;
     const int64_t lo = row_off[b], hi = row_off[b + 1];
-    if (n_cdf != 1 && ld == 256 && S <= 256) {
-        constexpr int PF = 4;
-        uint4 buf[PF];
+    if (n_cdf != 1 && !rows_per_stream && ld == 256 && S <= 256) {
+        constexpr int PF = 8;
+        const int cidx = lane * 8 + 7;
+        const bool cvalid = cidx < S - 1;
+        uint32_t coarse[PF];
 #pragma unroll
-        for (int d = 0; d < PF; ++d)
-            if (lo + d < hi) buf[d] = reinterpret_cast<const uint4 *>(cdf + (lo + d) * 256)[lane];
+        for (int d = 0; d < PF; ++d) coarse[d] = (cvalid && lo + d < hi) ? (uint32_t)cdf[(lo + d) * 256 + cidx] : 0x10000u;
+        ByteWindow bw;
+        bw.init(br.p + br.pos);
+        uint32_t pos = br.pos;
         for (int64_t i0 = lo; i0 < hi; i0 += PF) {
 #pragma unroll
             for (int d = 0; d < PF; ++d) {
-                int64_t i = i0 + d;
+                const int64_t i = i0 + d;
                 if (i >= hi) break;
-                uint4 v = buf[d];
-                if (i + PF < hi) buf[d] = reinterpret_cast<const uint4 *>(cdf + (i + PF) * 256)[lane];
-                uint32_t cf = x & 0xFFFFu;
-                uint32_t e[8] = {v.x & 0xFFFFu, v.x >> 16, v.y & 0xFFFFu, v.y >> 16, v.z & 0xFFFFu, v.z >> 16, v.w & 0xFFFFu, v.w >> 16};
+                const uint32_t cv = coarse[d];
+                coarse[d] = (cvalid && i + PF < hi) ? (uint32_t)cdf[(i + PF) * 256 + cidx] : 0x10000u;
+                const uint32_t cf = x & 0xFFFFu;
                 // symbol = #{j < S-1 : cdf[j] <= cf}  (== upper_bound clamped to S-1, simple_rans_wrapper.cpp:225-228)
-                int cnt = 0;
-                uint32_t below = 0, above = 65536u;
-#pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    bool valid = lane * 8 + t < S - 1;
-                    bool le = valid && e[t] <= cf;
-                    cnt += le;
-                    below = le ? e[t] : below;                       // entries are non-decreasing
-                    above = (valid && !le && e[t] < above) ? e[t] : above;
-                }
-                int sym = __reduce_add_sync(0xffffffffu, cnt);
-                uint32_t start = __reduce_max_sync(0xffffffffu, below);
-                uint32_t end = __reduce_min_sync(0xffffffffu, above);
-                x = dec_advance(x, br, start, end - start, 16);
-                if (lane == 0) symbols[i] = sym;
+                const int g = __popc(__ballot_sync(0xffffffffu, cv <= cf));  // groups of 8 entries entirely <= cf
+                const int idx = 8 * g - 1 + lane;                             // lanes 0..8: entries 8g-1 .. 8g+7
+                uint32_t v = 0x10000u;
+                if (lane <= 8) v = idx < 0 ? 0u : (idx < S - 1 ? (uint32_t)cdf[i * 256 + idx] : 0x10000u);
+                const int c = __popc(__ballot_sync(0xffffffffu, v <= cf));    // >= 1: lane 0 is always <= cf
+                const uint32_t start = __shfl_sync(0xffffffffu, v, c - 1);
+                const uint32_t end = __shfl_sync(0xffffffffu, v, c);
+                x = (end - start) * (x >> 16) + cf - start;                   // RansDecAdvance, rans_byte.h:149-165
+                const int nb = (int)(x < RANS_L) + (int)(x < (1u << 15));
+                x = (x << (8 * nb)) | bw.take(nb);
+                pos += nb;
+                if (lane == 0) symbols[i] = 8 * g + c - 1;
             }
         }
+        br.pos = pos;
+        if (pos > br.len) br.err = 1;
     } else {
         // generic path: binary search by every lane on the same row (shared table, or S > 256)
         for (int64_t i = lo; i < hi; ++i) {
-            const uint16_t *row = n_cdf == 1 ? cdf : cdf + i * (int64_t)ld;
+            const uint16_t *row = n_cdf == 1 ? cdf : cdf + (rows_per_stream ? (int64_t)b : i) * (int64_t)ld;
             uint32_t cf = x & 0xFFFFu;
             int a = 0, c = S;
             while (a < c) {
@@ -415,11 +465,12 @@ extern "C" int fpcc_rans_dec_init(fpcc_rans_dec_state *st, const uint8_t *bytes,
 
 extern "C" int fpcc_rans_decode(fpcc_rans_dec_state *st, const uint8_t *bytes, const int64_t *byte_off,
                                 const uint16_t *cdf, int64_t n_cdf, int s, int ld, const int64_t *row_off, int n_streams,
-                                int32_t *symbols, void *stream) {
+                                int32_t *symbols, int rows_per_stream, const int32_t *s_per_stream, void *stream) {
     FPCC_REQUIRE(st && bytes && byte_off && cdf && row_off && symbols, "rans_decode: NULL pointer");
     FPCC_REQUIRE(n_streams > 0 && s > 0 && ld >= s, "rans_decode: bad sizes");
     FPCC_REQUIRE(ld != 256 || n_cdf == 1 || ((uintptr_t)cdf & 15) == 0, "rans_decode: padded CDF rows must be 16-byte aligned");
-    rans_decode_kernel<<<n_streams, 32, 0, (cudaStream_t)stream>>>(st, bytes, byte_off, cdf, n_cdf, s, ld, row_off, symbols);
+    rans_decode_kernel<<<n_streams, 32, 0, (cudaStream_t)stream>>>(st, bytes, byte_off, cdf, n_cdf, s, ld, row_off, symbols,
+                                                                    rows_per_stream, s_per_stream);
     FPCC_LAUNCH_CHECK();
     return FPCC_OK;
 }

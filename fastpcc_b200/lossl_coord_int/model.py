@@ -248,48 +248,75 @@ class Model(nn.Module):
         return SparseTensor(torch.ones((xyz.shape[0], 1), dtype=torch.int8, device=xyz.device), xyz, (stride,) * 3)
 
     def build_pyramid(self, xyz: torch.Tensor) -> List[Level]:
-        """get_bin for every level (model.py:261-295, 403-405) with a single host read of the level sizes."""
+        """get_bin for every level (model.py:261-295, 403-405): one scan per level over the sorted coordinates."""
         L = self._num_levels()
-        raw, counts = [], []
+        raw = []
         cur = xyz
         for _ in range(L):
             out_c, occ, par, slot, cnt = ops.downsample(cur)
-            raw.append((out_c, occ, par, slot))
-            counts.append(cnt)
-            cur = out_c  # rows beyond the true count are ignored below: downsample only looks at n rows ...
-            # ... so the next level must be launched on the exact prefix; sizes are needed on the host anyway
-            n = int(cnt.item())  # TODO(perf): device-side sizes; for now one small read per level
+            n = int(cnt.item())  # the next level is launched on the exact prefix
             cur = out_c[:n]
-            raw[-1] = (cur, occ[:n], par, slot)
+            raw.append((cur, occ[:n], par, slot))
         levels = [Level(xyz, None, raw[0][2], raw[0][3])]
         for l in range(L):
-            C, occ = raw[l][0], raw[l][1]
             par, slot = (raw[l + 1][2], raw[l + 1][3]) if l + 1 < L else (None, None)
-            levels.append(Level(C, occ, par, slot))
+            levels.append(Level(raw[l][0], raw[l][1], par, slot))
         return levels
 
+    def _frame_rows(self, C: torch.Tensor, n_frames: int) -> torch.Tensor:
+        """row range of every frame in a batch-major coordinate list -> int64 [n_frames+1] (device, no sync)"""
+        edges = torch.arange(n_frames + 1, dtype=torch.int32, device=C.device)
+        return torch.searchsorted(C[:, 0].contiguous(), edges).to(torch.int64)
+
     # ---- compress ---------------------------------------------------------------------------
+    MAX_CDF = 130  # bottom-coordinate alphabet: the stream stores len(cdf)-2 <= 128 (model.py:371)
+
     @torch.no_grad()
-    def compress(self, xyz: torch.Tensor) -> bytes:
-        assert xyz.dtype == torch.int32 and xyz.dim() == 2 and xyz.shape[1] == 4
-        xyz = xyz.to(self.device)
-        coord_offset = xyz[:, 1:].amin(0)
-        xyz = xyz - torch.nn.functional.pad(coord_offset, (1, 0))
-        xyz = xyz[torch.argsort(ops.morton_encode(xyz.contiguous(), col0=1, msb_axis=0))].contiguous()
-        L = self._num_levels()
+    def compress_batch(self, frames: List[torch.Tensor]) -> List[bytes]:
+        """Compresses independent frames together: one pass of every kernel over the concatenated nodes (the
+        batch index is part of every coordinate key), one rANS stream per frame, all streams coded
+        concurrently.  Each returned bitstream is byte-identical to `compress(frame)` of the reference."""
+        dev, B, L = self.device, len(frames), self._num_levels()
+        offs, parts = [], []
+        for b, xyz in enumerate(frames):
+            assert xyz.dtype == torch.int32 and xyz.dim() == 2 and xyz.shape[1] == 4
+            xyz = xyz.to(dev)
+            off = xyz[:, 1:].amin(0)  # model.py:396-398
+            xyz = xyz - torch.nn.functional.pad(off, (1, 0))
+            xyz[:, 0] = b
+            xyz = xyz[torch.argsort(ops.morton_encode(xyz.contiguous(), col0=1, msb_axis=0))]
+            offs.append(off)
+            parts.append(xyz)
+        xyz = torch.cat(parts).contiguous()
         levels = self.build_pyramid(xyz)
 
-        # bottom coordinates and their histogram CDF (model.py:407-415)
-        bottom = levels[L].C[:, 1:].reshape(-1)
-        counts = torch.bincount(bottom, minlength=2).to(torch.int64)
-        pm = ((counts * (((65536 - counts.shape[0]) << 8) // bottom.numel())) >> 8) + 1
-        bcdf = pm.cumsum(-1)
-        bcdf[-1] = 65535
-        bcdf_i = bcdf.to(torch.int32)
-        bcdf = ops.as_u16(bcdf)
+        # ---- bottom coordinates and their per-frame histogram CDF (model.py:407-415), vectorised over frames
+        V = self.MAX_CDF
+        bot = levels[L].C
+        frame_of = bot[:, 0].long().repeat_interleave(3)
+        bottom = bot[:, 1:].reshape(-1)                                    # int32 [3*n_bottom]
+        counts = torch.zeros((B, V), dtype=torch.int64, device=dev)
+        counts.view(-1).index_add_(0, frame_of * V + bottom.clamp(max=V - 1).long(), torch.ones_like(bottom, dtype=torch.int64))
+        n_sym = counts.sum(1)                                              # 3 * bottom points of the frame
+        ar = torch.arange(V, device=dev)
+        n_cdf = ((counts > 0) * (ar + 1)).amax(1).clamp(min=2)            # bincount(minlength=2) length
+        scale = torch.div((65536 - n_cdf) << 8, n_sym, rounding_mode='floor')
+        pm = ((counts * scale[:, None]) >> 8) + 1
+        pm = torch.where(ar[None] < n_cdf[:, None], pm, torch.zeros_like(pm))
+        bcdf = pm.cumsum(1)
+        bcdf.scatter_(1, (n_cdf - 1)[:, None], torch.full((B, 1), 65535, dtype=torch.int64, device=dev))
+        # coder ranges of the bottom coordinates (shared per-frame table; RansEncoder::encode semantics)
+        b_lo = torch.where(bottom == 0, torch.zeros_like(frame_of), bcdf[frame_of, (bottom.long() - 1).clamp(min=0)])
+        b_hi = torch.where(bottom.long() == n_cdf[frame_of] - 1, torch.full_like(frame_of, 65536), bcdf[frame_of, bottom.long()])
+        e_bot = (b_lo | ((b_hi - b_lo - 1) << 16)).to(torch.int32)
+        # side info (rans_encode_fea, model.py:367-375): CDF entries minus one under cdf1, then the length under cdf2
+        cdf_vals = (bcdf - 1).to(torch.int32).reshape(-1)                  # symbol = cdf[j]-1 for j < n_cdf-1
+        e_cdf_all = ops.table_symbol_ranges(self.fea_side_info_cdf1, cdf_vals.clamp(min=0).contiguous()).view(B, V)
+        e_len = ops.table_symbol_ranges(self.fea_side_info_cdf2, (n_cdf - 2).to(torch.int32).contiguous())
 
-        cur = SparseTensor(torch.ones((levels[L].n, 1), dtype=torch.int8, device=self.device), levels[L].C, (2 ** L,) * 3)
-        seg = []  # per coded level: uint32 ranges in node order, coarse -> fine (= decode order)
+        # ---- network, coarse -> fine; per coded level the packed (start, freq) of every node's symbol
+        cur = SparseTensor(torch.ones((levels[L].n, 1), dtype=torch.int8, device=dev), levels[L].C, (2 ** L,) * 3)
+        seg = []
         for idx in range(L, 0, -1):
             blk = self._block(idx)
             lv = levels[idx]
@@ -301,55 +328,84 @@ class Model(nn.Module):
             else:
                 S = blk.pred_steps
                 cur, pred = blk.run(cur, [levels[idx + S - 1 - j] for j in range(S)])
-            seg.append(ops.cdf_symbol_ranges(pred, lv.symbols()))
+            seg.append((lv, ops.cdf_symbol_ranges(pred, lv.symbols())))
 
-        # stream entries in DECODE order: cdf length, cdf values, bottom coords, levels coarse -> fine.
-        # (the encoder pushes the exact reverse: model.py:442-445 and rans_encode_fea :367-375)
-        n_cdf = bcdf.numel()
-        assert n_cdf - 2 <= 128, n_cdf
-        e_len = ops.table_symbol_ranges(self.fea_side_info_cdf2, torch.tensor([n_cdf - 2], dtype=torch.int32, device=self.device))
-        e_cdf = ops.table_symbol_ranges(self.fea_side_info_cdf1, bcdf_i[:-1] - 1)
-        e_bot = ops.table_symbol_ranges(bcdf[None].contiguous(), bottom.contiguous())
-        ranges = torch.cat([e_len, e_cdf, e_bot] + seg)
-        rng_off = torch.tensor([0, ranges.numel()], dtype=torch.int64, device=self.device)
-        cap = 2 * ranges.numel() + 64  # <= 2 bytes per 16-bit symbol + state header
+        # ---- per-frame streams, entries in DECODE order: cdf length, cdf values, bottom coords, levels coarse ->
+        # fine (the encoder pushes the exact reverse: model.py:442-445 and :367-375).  Assembled on the device.
+        lvl_rows = [self._frame_rows(lv.C, B) for lv, _ in seg]           # [B+1] each
+        per_frame = 1 + (n_cdf - 1) + n_sym + sum((r[1:] - r[:-1]) for r in lvl_rows)
+        start = torch.cumsum(per_frame, 0) - per_frame                     # stream start of every frame
+        total_cap = B * V + 3 * bot.shape[0] + sum(lv.n for lv, _ in seg) + B
+        ranges = torch.zeros(total_cap, dtype=torch.int32, device=dev)
+        ranges[start] = e_len
+        j = ar[None].expand(B, V)
+        keep = j < (n_cdf - 1)[:, None]
+        ranges[(start[:, None] + 1 + j)[keep]] = e_cdf_all[keep]
+        bot_rows = self._frame_rows(bot, B) * 3
+        pos_in_frame = torch.arange(bottom.shape[0], device=dev) - bot_rows[frame_of]
+        ranges[start[frame_of] + n_cdf[frame_of] + pos_in_frame] = e_bot
+        base = start + n_cdf + n_sym
+        for (lv, rng), rows in zip(seg, lvl_rows):
+            fr = lv.C[:, 0].long()
+            ranges[base[fr] + torch.arange(lv.n, device=dev) - rows[fr]] = rng
+            base = base + (rows[1:] - rows[:-1])
+        rng_off = torch.cat([start, (start[-1] + per_frame[-1])[None]]).contiguous()
+        cap = (2 * int(per_frame.max().item()) + 64 + 3) & ~3  # <= 2 bytes per entry + the 4-byte state header
         out, out_len = ops.rans_encode(ranges, rng_off, cap)
-        n_bytes = int(out_len.item())
-        assert n_bytes > 0, 'rANS output buffer overflow'
-        payload = out[0, cap - n_bytes:].cpu().numpy().tobytes()
-        head = b''.join(int(v).to_bytes(2, 'little') for v in coord_offset.tolist())
-        head += int(levels[L].n).to_bytes(2, 'little')
-        return head + payload
+        lens = out_len.tolist()
+        heads = torch.cat([torch.stack(offs).long(), (n_sym // 3)[:, None]], 1).tolist()
+        out_h = out.cpu().numpy()
+        result = []
+        for b in range(B):
+            assert lens[b] > 0, 'rANS output buffer overflow'
+            head = b''.join(int(v).to_bytes(2, 'little') for v in heads[b])
+            result.append(head + out_h[b, cap - lens[b]:].tobytes())
+        return result
+
+    def compress(self, xyz: torch.Tensor) -> bytes:
+        return self.compress_batch([xyz])[0]
 
     def compress_partitions(self, batched_coord: List[torch.Tensor]) -> bytes:
-        out = [self.compress(batched_coord[i]) for i in range(1, len(batched_coord))]  # model.py:455-463
+        out = self.compress_batch(list(batched_coord[1:]))  # model.py:455-463 (partitions are independent streams)
         return b''.join(len(s).to_bytes(3, 'little') + s for s in out)
 
     # ---- decompress -------------------------------------------------------------------------
     @torch.no_grad()
-    def decompress(self, compressed_bytes: bytes) -> torch.Tensor:
-        dev = self.device
-        coord_offset = torch.tensor([int.from_bytes(compressed_bytes[2 * i: 2 * i + 2], 'little') for i in range(3)],
-                                    dtype=torch.int32, device=dev)
-        nb = int.from_bytes(compressed_bytes[6:8], 'little')
-        payload = torch.frombuffer(bytearray(compressed_bytes[8:]), dtype=torch.uint8).to(dev)
-        one = torch.tensor([0], dtype=torch.int64, device=dev)
-        dec = ops.RansDecodeStreams(payload, one, torch.tensor([payload.numel()], dtype=torch.int32, device=dev))
+    def decompress_batch(self, streams: List[bytes]) -> List[torch.Tensor]:
+        dev, B, L, V = self.device, len(streams), self._num_levels(), self.MAX_CDF
+        heads = np.array([[int.from_bytes(s[2 * i: 2 * i + 2], 'little') for i in range(4)] for s in streams], dtype=np.int64)
+        coord_offset = torch.from_numpy(heads[:, :3].astype(np.int32)).to(dev)
+        nb = torch.from_numpy(heads[:, 3]).to(dev)                        # bottom points per frame
+        lens = np.array([len(s) - 8 for s in streams], dtype=np.int64)
+        blob = np.frombuffer(b''.join(s[8:] for s in streams) + b'\0' * ops.RansDecodeStreams.PAD, dtype=np.uint8)
+        byte_off = torch.from_numpy(np.concatenate([[0], np.cumsum(lens)[:-1]])).to(dev)
+        dec = ops.RansDecodeStreams(torch.from_numpy(blob.copy()).to(dev), byte_off,
+                                    torch.from_numpy(lens.astype(np.int32)).to(dev), padded=True)
 
-        def rows(n):
-            return torch.tensor([0, n], dtype=torch.int64, device=dev)
+        def offsets(counts):
+            return torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(counts.to(torch.int64), 0)]).contiguous()
 
-        # rans_decode_fea(decode_rounded_min=False), model.py:377-393
-        cdf_len = int(dec.decode(self.fea_side_info_cdf2, 128, rows(1), 1, shared=True).item())
-        cdf = dec.decode(self.fea_side_info_cdf1, 65535, rows(cdf_len + 1), cdf_len + 1, shared=True)
-        cdf = ops.as_u16(torch.cat([cdf + 1, torch.tensor([65535], dtype=torch.int32, device=dev)]))
-        bottom = dec.decode(cdf[None].contiguous(), cdf.numel(), rows(nb * 3), nb * 3, shared=True)
-        L = self._num_levels()
-        C = torch.nn.functional.pad(bottom.reshape(-1, 3), (1, 0, 0, 0)).contiguous()
+        # rans_decode_fea(decode_rounded_min=False), model.py:377-393, for all frames at once
+        ones = torch.ones(B, dtype=torch.int64, device=dev)
+        cdf_len = dec.decode(self.fea_side_info_cdf2, 128, offsets(ones), B, shared=True).long()      # = len(cdf)-2
+        n_vals = cdf_len + 1
+        n_vals_h = n_vals.tolist()
+        vals = dec.decode(self.fea_side_info_cdf1, 65535, offsets(n_vals), int(sum(n_vals_h)), shared=True)
+        table = torch.full((B, V), 65535, dtype=torch.int64, device=dev)
+        fr = torch.repeat_interleave(torch.arange(B, device=dev), n_vals)
+        col = torch.arange(vals.shape[0], device=dev) - offsets(n_vals)[fr]
+        table[fr, col] = vals.long() + 1                                   # np.pad(cdf + 1, (0, 1)); cdf[-1] = 65535
+        n_sym = nb * 3
+        n_sym_h = (heads[:, 3] * 3).tolist()
+        bottom = dec.decode(ops.as_u16(table).contiguous(), V, offsets(n_sym), int(sum(n_sym_h)), rows_per_stream=True,
+                            s_per_stream=(cdf_len + 2).to(torch.int32).contiguous())
+        fr = torch.repeat_interleave(torch.arange(B, device=dev, dtype=torch.int32), nb)
+        C = torch.cat([fr[:, None], bottom.reshape(-1, 3)], 1).contiguous()
         cur = self.get_init_pc(C, 2 ** L)
 
         def decode_level(logits, lv: Level):
-            sym = dec.decode(ops.quantize_cdf(logits), logits.shape[1], rows(lv.n), lv.n)
+            rows = self._frame_rows(lv.C, B)
+            sym = dec.decode(ops.quantize_cdf(logits), logits.shape[1], rows, lv.n)
             lv.occ = (sym + 1).to(torch.uint8)  # occ byte = oct symbol + 1 (model.py:81)
             cc, par, slot, _ = ops.upsample(lv.C, lv.occ)
             return Level(cc, None, par, slot)
@@ -376,12 +432,16 @@ class Model(nn.Module):
                 cur, pred = blk.run(cur, ms_levels[:S])
                 lv = decode_level(pred, ms_levels[S - 1])
         assert not dec.error(), 'corrupt bitstream'
-        return lv.C[:, 1:] + coord_offset[None]
+        rows = self._frame_rows(lv.C, B).tolist()
+        return [lv.C[rows[b]: rows[b + 1], 1:] + coord_offset[b][None] for b in range(B)]
+
+    def decompress(self, compressed_bytes: bytes) -> torch.Tensor:
+        return self.decompress_batch([compressed_bytes])[0]
 
     def decompress_partitions(self, concat_bytes: bytes) -> torch.Tensor:
-        out, pos = [], 0
+        parts, pos = [], 0
         while pos != len(concat_bytes):  # model.py:510-521
             n = int.from_bytes(concat_bytes[pos: pos + 3], 'little')
-            out.append(self.decompress(concat_bytes[pos + 3: pos + 3 + n]))
+            parts.append(concat_bytes[pos + 3: pos + 3 + n])
             pos += 3 + n
-        return torch.cat(out, 0)
+        return torch.cat(self.decompress_batch(parts), 0)

@@ -68,6 +68,13 @@ def profile_summary(prof):
     return out
 
 
+def mma_i8_peak(iters=20000, n=256):
+    """measured kind::i8 tensor-pipe ceiling of the current GPU in TOP/s (synchronises)"""
+    out = C.c_double(0.0)
+    _lib.call('fpcc_mma_i8_peak', int(iters), int(n), C.byref(out), _s())
+    return out.value
+
+
 def gemm_engine(k, n, kvol=1, zp_comp=False):
     """'tc' when the C side routes this shape to the tcgen05 kernel, else 'simt'."""
     return 'tc' if _lib.load().fpcc_gemm_engine(int(k), int(n), int(kvol), int(bool(zp_comp))) == 1 else 'simt'
@@ -386,19 +393,25 @@ def rans_encode(ranges, rng_off, out_stride, bits=None, out=None, state_io=None,
 class RansDecodeStreams:
     """Device-resident decoder state for n streams (RansDecoder::flush + decode, batched)."""
 
-    def __init__(self, data, byte_off, byte_len):
+    PAD = 16  # the decoder's byte window reads a few bytes ahead of the stream position
+
+    def __init__(self, data, byte_off, byte_len, padded=False):
         _need(data, torch.uint8, 'bytes', 1)
+        if not padded:
+            data = torch.cat([data, torch.zeros(self.PAD, dtype=torch.uint8, device=data.device)])
         self.data, self.byte_off = data, byte_off
         self.n = byte_off.numel()
         self.state = torch.empty((self.n, 4), dtype=torch.int32, device=data.device)
         _call('fpcc_rans_dec_init', _p(self.state), _p(data), _p(byte_off), _p(byte_len), self.n, _s())
 
-    def decode(self, cdf, s, row_off, n_rows, shared=False):
-        """cdf: uint16 [rows, ld] (per symbol) or [1, s] shared.  row_off int64 [n+1] device."""
+    def decode(self, cdf, s, row_off, n_rows, shared=False, rows_per_stream=False, s_per_stream=None):
+        """cdf: uint16 [rows, ld] (one row per symbol), [1, s] shared by all streams, or [n_streams, ld] with
+        rows_per_stream.  row_off int64 [n_streams+1] (device): symbol range of every stream."""
         _need(cdf, torch.uint16, 'cdf', 2)
         sym = torch.empty(n_rows, dtype=torch.int32, device=cdf.device)
         _call('fpcc_rans_decode', _p(self.state), _p(self.data), _p(self.byte_off), _p(cdf),
-                  1 if shared else cdf.shape[0], s, cdf.shape[1], _p(row_off), self.n, _p(sym), _s())
+              1 if shared else cdf.shape[0], s, cdf.shape[1], _p(row_off), self.n, _p(sym),
+              1 if rows_per_stream else 0, _p(s_per_stream), _s())
         return sym
 
     def error(self):

@@ -170,6 +170,9 @@ int fpcc_slot_table(const int32_t *child_parent, const uint8_t *child_slot, int 
  * wherever the shape allows (C_in % 16 == 0, C_in >= 32, C_out >= 16, kernel volume <= 32), 0 = the CUDA-core
  * (dp4a) kernels for every shape.  Both produce identical integers; the switch exists for A/B verification. */
 int fpcc_set_tc_mode(int mode);
+/* Measures the kind::i8 tensor-pipe ceiling of the current device: every SM issues `iters` x 4 back-to-back
+ * tcgen05.mma (M=128, N=n, K=32) on resident shared-memory tiles.  Synchronises.  *tops_out = int8 TOP/s. */
+int fpcc_mma_i8_peak(int iters, int n, double *tops_out, void *stream);
 /* 1 if a GEMM with contraction k, n output channels and `kvol` offsets runs on the tensor cores, else 0 */
 int fpcc_gemm_engine(int k, int n, int kvol, int has_zp_comp);
 
@@ -223,15 +226,18 @@ typedef struct {
 } fpcc_rans_dec_state;
 
 /* RansDecoder::flush (simple_rans_wrapper.cpp:139-145) for n_streams streams stored at
- * bytes + byte_off[b] with byte_len[b] bytes. */
+ * bytes + byte_off[b] with byte_len[b] bytes.  The buffer must stay readable for 16 bytes past the end of
+ * the last stream (the decoders read ahead through an aligned byte window; the extra bytes are never used). */
 int fpcc_rans_dec_init(fpcc_rans_dec_state *st, const uint8_t *bytes, const int64_t *byte_off,
                        const int32_t *byte_len, int n_streams, void *stream);
 
-/* RansDecoder::decode (simple_rans_wrapper.cpp:206-239): stream b decodes rows
- * [row_off[b], row_off[b+1]) with CDF row i (or the single shared row when n_cdf == 1). */
+/* RansDecoder::decode (simple_rans_wrapper.cpp:206-239): stream b decodes symbols
+ * [row_off[b], row_off[b+1]) with CDF row i (one row per symbol), the single shared row when n_cdf == 1, or
+ * row b (one table per stream, e.g. the per-frame bottom-coordinate histogram) when rows_per_stream != 0;
+ * s_per_stream (optional, device) overrides the alphabet size s per stream. */
 int fpcc_rans_decode(fpcc_rans_dec_state *st, const uint8_t *bytes, const int64_t *byte_off,
                      const uint16_t *cdf, int64_t n_cdf, int s, int ld, const int64_t *row_off, int n_streams,
-                     int32_t *symbols, void *stream);
+                     int32_t *symbols, int rows_per_stream, const int32_t *s_per_stream, void *stream);
 
 /* BinaryRansCoder (rans_wrapper.cpp:326-428): prob = P(1)*65536 in [1,65535], uint32 [n_streams, n]. */
 /* total = n_streams * n symbols; ranges come out in decode order, stream after stream */

@@ -1,0 +1,56 @@
+"""Micro-benchmark of the fused sparse-conv / linear kernels on one LiDAR pyramid level (also the ncu target).
+usage: python tests/bench_conv.py [stride_log2=4] [channels=256] [frames=1]"""
+import sys
+import os.path as osp
+import numpy as np
+import torch
+sys.path.insert(0, osp.dirname(osp.dirname(osp.abspath(__file__))))
+from fastpcc_b200 import ops, synth  # noqa: E402
+
+lvl = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+ch = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+frames = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+cs = []
+for b in range(frames):
+    xyz = synth.lidar_frame(1000 + b) >> lvl
+    cs.append(synth.with_batch(np.unique(xyz, axis=0), b))
+C = torch.from_numpy(np.concatenate(cs)).cuda()
+n = C.shape[0]
+rng = np.random.default_rng(0)
+f = torch.from_numpy(rng.integers(-128, 128, (n, ch)).astype(np.int8)).cuda()
+w = torch.from_numpy(rng.integers(-127, 128, (27, ch, ch)).astype(np.int8)).cuda()
+bias = torch.from_numpy(rng.integers(-5000, 5000, ch).astype(np.int32)).cuda()
+mul = torch.from_numpy(rng.integers(1 << 18, 1 << 22, ch).astype(np.int64)).to(torch.uint32).cuda()
+zp = torch.zeros(1, dtype=torch.int64, device='cuda')
+slope = torch.tensor([1 << 23], dtype=torch.int32, device='cuda')
+keys, vals = ops.hash_build(C)
+table = ops.kmap_lookup(keys, vals, C, (3, 3, 3), (1, 1, 1))
+pairs = int(torch.count_nonzero(table).item())
+ep = ops.make_epilogue(mul, zp, 24, ops.OUT_I8, bias=bias, slope=slope)
+
+
+def t(fn, reps=5):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record(); e1.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+import os
+alg = 2.0 * pairs * ch * ch
+mma = 2.0 * ((n + 127) // 128 * 128) * 27 * ch * ch
+w2 = torch.from_numpy(rng.integers(-127, 128, (ch, ch)).astype(np.int8)).cuda()
+for dbg in (sys.argv[4].split(',') if len(sys.argv) > 4 else ['0']):
+    os.environ['FPCC_TC_DEBUG'] = dbg  # experiment knobs of igemm_tc.cu (0 = the real kernel)
+    ms = t(lambda: ops.spconv(f, w, table, ep))
+    print(f'[dbg {dbg}] conv  stride 2^{lvl} n={n} C={ch} pairs/pt={pairs / n:.2f}: {ms:.3f} ms  algorithmic {alg / ms / 1e9:.1f} TOP/s  executed {mma / ms / 1e9:.1f} TOP/s')
+    ms = t(lambda: ops.linear(f, w2, ep))
+    print(f'[dbg {dbg}] linear n={n} {ch}->{ch}: {ms:.3f} ms  {2.0 * n * ch * ch / ms / 1e9:.1f} TOP/s')
+os.environ['FPCC_TC_DEBUG'] = '0'
+ms = t(lambda: ops.kmap_lookup(keys, vals, C, (3, 3, 3), (1, 1, 1)))
+print(f'kmap lookup n={n}: {ms:.3f} ms  {(16 * n + 8 * 27 * n + 4 * 27 * n) / ms / 1e6:.1f} GB/s (algorithmic bytes)')
+ms = t(lambda: ops.hash_build(C))
+print(f'hash build n={n}: {ms:.3f} ms')
