@@ -15,7 +15,7 @@ class Epilogue(C.Structure):
     """fpcc_epilogue (include/fastpcc_b200.h)"""
     _fields_ = [('bias', _vp), ('slope', _vp), ('requant_mul', _vp), ('zero_point', _vp),
                 ('shift', C.c_int32), ('out_type', C.c_int32), ('mul_is_scalar', C.c_int32),
-                ('residual', _vp), ('post_slope', _vp)]
+                ('residual', _vp), ('post_slope', _vp), ('row_bias', _vp), ('row_idx', _vp)]
 
 
 _EP = C.POINTER(Epilogue)
@@ -33,6 +33,7 @@ SIGNATURES = {
     'fpcc_downsample': (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'fpcc_upsample': (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'fpcc_occ_to_bits': (_i, [_vp, _i, _vp, _vp]),
+    'fpcc_gather_patches': (_i, [_vp, _i, _vp, _i64, _i, _i, _vp, _i, _vp]),
     'fpcc_slot_table': (_i, [_vp, _vp, _i, _vp, _i64, _vp]),
     'fpcc_morton_encode': (_i, [_vp, _i64, _i, _i, _vp, _vp]),
     'fpcc_gemm_i8': (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp]),
@@ -48,7 +49,7 @@ SIGNATURES = {
     'fpcc_quantize_cdf': (_i, [_vp, _i64, _i, _vp, _i, _vp]),
     'fpcc_cdf_symbol_ranges': (_i, [_vp, _i64, _i, _vp, _vp, _vp]),
     'fpcc_table_symbol_ranges': (_i, [_vp, _i64, _i, _vp, _i64, _vp, _vp]),
-    'fpcc_rans_encode': (_i, [_vp, _vp, _vp, _i, _vp, _i64, _vp, _vp, _i, _vp]),
+    'fpcc_rans_encode': (_i, [_vp, _vp, _vp, _i, _i64, _vp, _i64, _vp, _vp, _i, _vp]),
     'fpcc_rans_dec_init': (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
     'fpcc_rans_decode': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _i, _vp, _i, _vp, _vp]),
     'fpcc_rans_binary_ranges': (_i, [_vp, _vp, _i64, _vp, _vp]),

@@ -38,6 +38,8 @@ int check_epilogue(const fpcc_epilogue *e, bool allow_residual) {
     } else {
         FPCC_REQUIRE(e->post_slope == nullptr, "epilogue: post_slope without residual");
     }
+    FPCC_REQUIRE((e->row_bias == nullptr) == (e->row_idx == nullptr), "epilogue: row_bias and row_idx go together");
+    FPCC_REQUIRE(e->row_bias == nullptr || allow_residual, "epilogue: row_bias is only supported by the fused kernels");
     return FPCC_OK;
 }
 

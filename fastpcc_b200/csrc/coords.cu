@@ -414,3 +414,35 @@ extern "C" int fpcc_slot_table(const int32_t *child_parent, const uint8_t *child
     FPCC_LAUNCH_CHECK();
     return FPCC_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// im2col for thin inputs: patches[o, k*c + j] = feats[table[k][o]-1, j] (0 where there is no neighbour).
+// Turns a sparse conv with C_in = 1 / 8 (first conv, occupancy embeds with kernel = stride) into ONE dense
+// contraction of K = kvol*C_in per output row, which the tensor-core linear kernel then runs.
+// ---------------------------------------------------------------------------------------------
+namespace fpcc {
+__global__ void __launch_bounds__(256) gather_patches_kernel(const int8_t *__restrict__ feats, int c,
+                                                             const int32_t *__restrict__ table, int64_t ld, int kvol, int n_out,
+                                                             int8_t *__restrict__ patches, int kp) {
+    int o = blockIdx.x * blockDim.x + threadIdx.x;
+    int k = blockIdx.y;
+    if (o >= n_out) return;
+    int32_t v = table[(int64_t)k * ld + o];
+    int8_t *dst = patches + (int64_t)o * kp + k * c;
+    if (c == 8 && (((uintptr_t)feats | (uintptr_t)patches) & 7) == 0 && (kp & 7) == 0) {
+        *reinterpret_cast<uint2 *>(dst) = v ? *reinterpret_cast<const uint2 *>(feats + (int64_t)(v - 1) * 8) : make_uint2(0, 0);
+    } else {
+        for (int j = 0; j < c; ++j) dst[j] = v ? feats[(int64_t)(v - 1) * c + j] : (int8_t)0;
+    }
+}
+}  // namespace fpcc
+
+extern "C" int fpcc_gather_patches(const int8_t *feats, int c, const int32_t *table, int64_t ld, int kvol, int n_out,
+                                   int8_t *patches, int kp, void *stream) {
+    FPCC_REQUIRE(feats && table && patches, "gather_patches: NULL pointer");
+    FPCC_REQUIRE(c > 0 && kvol > 0 && n_out > 0 && ld >= n_out && kp >= kvol * c, "gather_patches: bad sizes");
+    dim3 grid(fpcc::ceil_div(n_out, 256), kvol);
+    fpcc::gather_patches_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(feats, c, table, ld, kvol, n_out, patches, kp);
+    FPCC_LAUNCH_CHECK();
+    return FPCC_OK;
+}

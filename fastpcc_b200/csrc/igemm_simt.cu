@@ -205,6 +205,7 @@ __global__ void __launch_bounds__(256) pairs_tile_kernel(PairArgs a, EpiParams e
                 ((int32_t *)out)[idx] = (int32_t)((uint32_t)((int32_t *)out)[idx] + (uint32_t)acc[i][j]);
             } else {
                 int pc = a.bias_per_group ? g * a.N + n : n;
+                if (ep.row_bias) acc[i][j] += ep.row_bias[(int64_t)ep.row_idx[m] * a.N + n];
                 int64_t o = epi_value(acc[i][j], ep.bias ? ep.bias[pc] : 0, sc.has_slope, sc.slope,
                                       ep.mul[ep.mul_is_scalar ? 0 : pc], sc.zp, ep.shift);
                 epi_store(out, idx, o, ep.out_type, ep.residual, sc.has_post, sc.post);

@@ -36,7 +36,6 @@ namespace fpcc {
 constexpr int TC_M = 128;         // rows per tile (UMMA M)
 constexpr int TC_KB = 128;        // K bytes per stage (one 128B swizzle atom)
 constexpr int TC_MAX_KVOL = 32;   // offsets tracked by the per-tile activity mask
-constexpr int TC_THREADS = 192;
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -137,222 +136,8 @@ struct TcArgs {
     int dbg;  // FPCC_TC_DEBUG bitmask (experiments only): 1 skip A loads, 2 skip B loads, 4 skip epilogue math, 8 skip MMA
 };
 
-template <int STAGES>
-struct TcSmem {
-    static constexpr int a_bytes = TC_M * TC_KB;
-    static size_t bytes(int n_tile, int kvol_rows) {
-        return 1024 + (size_t)STAGES * (a_bytes + (size_t)n_tile * TC_KB) + (size_t)kvol_rows * TC_M * 4 + 256;
-    }
-};
-
-template <int MODE, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS, 1) igemm_tc_kernel(TcArgs a, const __grid_constant__ CUtensorMap tmap_w,
-                                                                 EpiParams ep, void *__restrict__ out) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    const int b_bytes = a.n_tile * TC_KB;
-    uint8_t *sA = smem;
-    uint8_t *sB = smem + STAGES * TcSmem<STAGES>::a_bytes;
-    int32_t *rows_s = (int32_t *)(sB + (size_t)STAGES * b_bytes);  // CONV: [kvol][128] source rows; PAIRS: [2][128] src,dst
-    const int rows_k = MODE == 0 ? a.kvol : 2;
-    uint64_t *bars = (uint64_t *)(rows_s + rows_k * TC_M);
-    uint64_t *full = bars, *empty = bars + STAGES, *tmem_full = bars + 2 * STAGES;
-    uint32_t *tmem_ptr = (uint32_t *)(bars + 2 * STAGES + 1);
-    uint32_t *kmask = tmem_ptr + 1;
-    int32_t *tile_info = (int32_t *)(kmask + 1);  // PAIRS: group, begin, end
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m0 = blockIdx.x * TC_M, n0 = blockIdx.y * a.n_tile;
-
-    if (tid == 0) {
-        *kmask = 0;
-        if (MODE == 1) {
-            int g = 0, begin = blockIdx.x * TC_M, end = a.n_pairs;
-            if (a.offsets) {
-                int t = blockIdx.x;
-                begin = end = -1;
-                for (g = 0; g < a.n_groups; ++g) {
-                    int lo = a.offsets[g], hi = a.offsets[g + 1];
-                    int nt = (hi - lo + TC_M - 1) / TC_M;
-                    if (t < nt) { begin = lo + t * TC_M; end = hi; break; }
-                    t -= nt;
-                }
-            }
-            tile_info[0] = g; tile_info[1] = begin; tile_info[2] = end;
-        }
-    }
-    if (warp == 5 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full[s], TC_M + 1);
-            mbar_init(&empty[s], 1);
-        }
-        mbar_init(tmem_full, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 4 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
-    __syncthreads();
-    if (MODE == 1 && (tile_info[1] < 0 || tile_info[1] >= tile_info[2])) return;  // block beyond the last tile
-
-    if (warp == 5) {  // TMEM allocation (whole warp), address lands in smem
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"((uint32_t)a.tmem_cols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    // source rows of this tile -> smem, plus the mask of kernel offsets that have any neighbour
-    if (tid < TC_M) {
-        if (MODE == 0) {
-            int m = m0 + tid;
-            uint32_t mine = 0;
-            for (int k = 0; k < a.kvol; ++k) {
-                int32_t v = m < a.n_out ? __ldg(&a.nbr[(int64_t)k * a.ld + m]) : 0;
-                rows_s[k * TC_M + tid] = v - 1;
-                mine |= (v != 0) << k;
-            }
-            mine = __reduce_or_sync(0xffffffffu, mine);
-            if (lane == 0 && mine) atomicOr(kmask, mine);
-        } else {
-            int p = tile_info[1] + tid;
-            bool ok = p < tile_info[2];
-            rows_s[tid] = ok ? (a.in_idx ? __ldg(&a.in_idx[p]) : p) : -1;
-            rows_s[TC_M + tid] = ok ? (a.out_idx ? __ldg(&a.out_idx[p]) : p) : -1;
-            if (tid == 0) *kmask = 1;
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-
-    const uint32_t tmem_base = *tmem_ptr;
-    const uint32_t active = *kmask;
-    const int nk = __popc(active);
-    const int n_chunks = (a.K + TC_KB - 1) / TC_KB;
-    const int total = nk * n_chunks;
-    const int group = MODE == 1 ? tile_info[0] : 0;
-
-    if (warp < 4) {
-        // ================= gather producers =================
-        const int r = tid;
-        const uint32_t row_smem = r * TC_KB;
-        const uint32_t sw = r & 7;
-        uint32_t rem = active;
-        int k = -1;
-        for (int i = 0; i < total; ++i) {
-            const int kc = i % n_chunks;
-            if (kc == 0) { k = __ffs(rem) - 1; rem &= rem - 1; }
-            const int stage = i % STAGES;
-            mbar_wait(&empty[stage], ((i / STAGES) & 1) ^ 1);
-            const int32_t src = rows_s[(MODE == 0 ? k : 0) * TC_M + r];
-            const int8_t *gsrc = a.A + (src >= 0 ? (int64_t)src * a.K : 0) + kc * TC_KB;
-            const uint32_t dst = smem_u32(sA + stage * TcSmem<STAGES>::a_bytes) + row_smem;
-            if (!(a.dbg & 1)) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const bool ok = src >= 0 && kc * TC_KB + c * 16 < a.K;
-                    cp_async16(dst + ((c ^ sw) << 4), ok ? (const void *)(gsrc + c * 16) : (const void *)a.A, ok ? 16u : 0u);
-                }
-            }
-            cp_async_commit();
-            if (i >= STAGES - 1) {
-                cp_async_wait<STAGES - 1>();
-                fence_proxy_async();
-                mbar_arrive(&full[(i - (STAGES - 1)) % STAGES]);
-            }
-        }
-        cp_async_wait<0>();
-        fence_proxy_async();
-        for (int i = max(total - (STAGES - 1), 0); i < total; ++i) mbar_arrive(&full[i % STAGES]);
-
-        // ================= epilogue =================
-        if (total > 0) {
-            mbar_wait(tmem_full, 0);
-            tc_fence_after();
-        }
-        const int64_t m = MODE == 0 ? (int64_t)(m0 + r) : (int64_t)rows_s[TC_M + r];
-        const bool row_ok = MODE == 0 ? (m < a.n_out) : (m >= 0);
-        const bool has_slope = ep.slope != nullptr, has_post = ep.post_slope != nullptr;
-        const int32_t slope = has_slope ? ep.slope[0] : 0, post = has_post ? ep.post_slope[0] : 0;
-        const int64_t zp = ep.zp[0];
-        const int pbase = (MODE == 1 && a.bias_per_group) ? group * a.N : 0;
-        for (int c0 = 0; c0 < a.n_tile; c0 += 32) {
-            uint32_t acc[32];
-            if (total > 0) {
-                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, acc);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) acc[j] = 0;
-            }
-            if (!row_ok) continue;
-            if (a.dbg & 4) { if (c0 == 0) ((int32_t *)out)[m] = (int32_t)acc[0]; continue; }
-            const int nb = n0 + c0;
-            if (nb >= a.N) continue;
-            const int64_t obase = m * a.N + nb;
-            if (ep.out_type == FPCC_OUT_I8 && nb + 32 <= a.N && (a.N & 15) == 0) {
-                uint32_t packed[8];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    int64_t o = epi_value((int32_t)acc[j], ep.bias ? __ldg(&ep.bias[pbase + nb + j]) : 0, has_slope, slope,
-                                          __ldg(&ep.mul[ep.mul_is_scalar ? 0 : pbase + nb + j]), zp, ep.shift);
-                    int32_t q = (int32_t)(o < -128 ? -128 : (o > 127 ? 127 : o));
-                    if ((j & 3) == 0) packed[j >> 2] = 0;
-                    packed[j >> 2] |= (uint32_t)(q & 0xff) << ((j & 3) * 8);
-                }
-                uint4 *dst = reinterpret_cast<uint4 *>((int8_t *)out + obase);
-                dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-            } else {
-#pragma unroll 4
-                for (int j = 0; j < 32; ++j) {
-                    if (nb + j >= a.N) break;
-                    int64_t o = epi_value((int32_t)acc[j], ep.bias ? __ldg(&ep.bias[pbase + nb + j]) : 0, has_slope, slope,
-                                          __ldg(&ep.mul[ep.mul_is_scalar ? 0 : pbase + nb + j]), zp, ep.shift);
-                    epi_store(out, obase + j, o, ep.out_type, ep.residual, has_post, post);
-                }
-            }
-        }
-    } else if (warp == 4) {
-        // ================= weight producer (TMA) =================
-        if (lane == 0) {
-            uint32_t rem = active;
-            int k = -1;
-            for (int i = 0; i < total; ++i) {
-                const int kc = i % n_chunks;
-                if (kc == 0) { k = __ffs(rem) - 1; rem &= rem - 1; }
-                const int stage = i % STAGES;
-                mbar_wait(&empty[stage], ((i / STAGES) & 1) ^ 1);
-                if (a.dbg & 2) { mbar_arrive(&full[stage]); continue; }
-                mbar_expect_tx(&full[stage], (uint32_t)b_bytes);
-                const int wrow = (MODE == 0 ? k : group) * a.N + n0;
-                tma_load_2d(smem_u32(sB + (size_t)stage * b_bytes), &tmap_w, &full[stage], kc * TC_KB, wrow);
-            }
-        }
-    } else {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_i8(a.n_tile);
-            for (int i = 0; i < total; ++i) {
-                const int stage = i % STAGES;
-                mbar_wait(&full[stage], (i / STAGES) & 1);
-                tc_fence_after();
-                const uint64_t ad = umma_desc_sw128(smem_u32(sA + stage * TcSmem<STAGES>::a_bytes));
-                const uint64_t bd = umma_desc_sw128(smem_u32(sB + (size_t)stage * b_bytes));
-                if (!(a.dbg & 8)) {
-#pragma unroll
-                    for (int j = 0; j < TC_KB / 32; ++j)  // kind::i8: K = 32 bytes per instruction; +32 B = +2 in the address field
-                        umma_i8(tmem_base, ad + 2 * j, bd + 2 * j, idesc, (uint32_t)(i > 0 || j > 0));
-                }
-                umma_commit(&empty[stage]);  // frees the smem stage once these MMAs have read it
-            }
-            if (total > 0) umma_commit(tmem_full);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 5) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols) : "memory");
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
-// persistent kernel (v2): one CTA per SM loops over tiles; the accumulator is double-buffered in TMEM so the
+// persistent kernel: one CTA per SM loops over tiles; the accumulator is double-buffered in TMEM so the
 // epilogue of tile t (8 warps, int64 requant arithmetic) overlaps the gathers + MMAs of tile t+1; TMEM
 // allocation, barrier setup and weight-descriptor prefetch are paid once per CTA instead of once per tile.
 //
@@ -598,6 +383,12 @@ __global__ void __launch_bounds__(P_THREADS, 1) igemm_tc_persistent(TcArgs a, co
                 if (a.dbg & 4) { if (c0 == 0) ((int32_t *)out)[m] = (int32_t)acc[0]; continue; }
                 const int64_t obase = m * a.N + nb;
                 const bool full32 = nb + 32 <= a.N;
+                if (ep.row_bias) {  // occupancy-indexed bias row (the 8 bit channels of cat(F, bin << 23) folded away)
+                    const int32_t *rb = ep.row_bias + (int64_t)__ldg(&ep.row_idx[m]) * a.N + nb;
+#pragma unroll
+                    for (int q = 0; q < 32; ++q)
+                        if (nb + q < a.N) acc[q] += (uint32_t)__ldg(&rb[q]);
+                }
                 int32_t o32[32];
 #pragma unroll
                 for (int q = 0; q < 32; ++q) {
@@ -785,34 +576,17 @@ static int launch_tc(TcArgs &a, const int8_t *W, int64_t w_rows, int tiles_m, co
     if (rc) return rc;
     constexpr int STAGES = 4;
     const int rows_k = MODE == 0 ? a.kvol : 2;
-    static int version = -1;
-    if (version < 0) { const char *e = getenv("FPCC_TC_V"); version = e ? atoi(e) : 2; }
-    if (version == 2) {
-        size_t smem2 = PSmem<STAGES>::bytes(a.n_tile, rows_k);
-        if (smem2 <= 227 * 1024) {
-            auto kern2 = igemm_tc_persistent<MODE, STAGES>;
-            static bool configured2 = false;
-            if (!configured2) {
-                FPCC_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                configured2 = true;
-            }
-            int total = tiles_m * n_blocks_n;
-            int grid = total < sm_count() ? total : sm_count();
-            kern2<<<grid, P_THREADS, smem2, s>>>(a, tmap, ep, out, tiles_m, n_blocks_n);
-            FPCC_LAUNCH_CHECK();
-            return FPCC_OK;
-        }
-    }
-    size_t smem = TcSmem<STAGES>::bytes(a.n_tile, rows_k);
-    auto kern = igemm_tc_kernel<MODE, STAGES>;
+    size_t smem = PSmem<STAGES>::bytes(a.n_tile, rows_k);
+    FPCC_REQUIRE(smem <= 227 * 1024, "igemm_tc: %zu bytes of shared memory exceed the 227 KB limit", smem);
+    auto kern = igemm_tc_persistent<MODE, STAGES>;
     static bool configured = false;
     if (!configured) {
         FPCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured = true;
     }
-    FPCC_REQUIRE(smem <= 227 * 1024, "igemm_tc: %zu bytes of shared memory exceed the 227 KB limit", smem);
-    dim3 grid(tiles_m, n_blocks_n);
-    kern<<<grid, TC_THREADS, smem, s>>>(a, tmap, ep, out);
+    int total = tiles_m * n_blocks_n;
+    int grid = total < sm_count() ? total : sm_count();
+    kern<<<grid, P_THREADS, smem, s>>>(a, tmap, ep, out, tiles_m, n_blocks_n);
     FPCC_LAUNCH_CHECK();
     return FPCC_OK;
 }

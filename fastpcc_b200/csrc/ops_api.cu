@@ -27,6 +27,37 @@ __global__ void __launch_bounds__(256) requant_kernel(const int32_t *__restrict_
     }
 }
 
+// Four consecutive channels per thread (16-byte loads; 4/8/16-byte stores); needs ch % 4 == 0 and 16-byte aligned
+// tensors.  This is the shape of every requant on the codec path (RequantFxpToScaledInt8 between layers).
+template <int OUT>
+__global__ void __launch_bounds__(256) requant_vec4_kernel(const int4 *__restrict__ in, int64_t total4, int ch4, EpiParams ep,
+                                                           void *__restrict__ out) {
+    const bool has_slope = ep.slope != nullptr;
+    const int32_t slope = has_slope ? ep.slope[0] : 0;
+    const int64_t zp = ep.zp[0];
+    const uint32_t mul0 = ep.mul[0];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % ch4) * 4;
+        const int4 v = __ldg(&in[i]);
+        const int32_t a[4] = {v.x, v.y, v.z, v.w};
+        int32_t o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            int64_t r = epi_value(a[q], ep.bias ? __ldg(&ep.bias[c + q]) : 0, has_slope, slope,
+                                  ep.mul_is_scalar ? mul0 : __ldg(&ep.mul[c + q]), zp, ep.shift);
+            if (OUT == FPCC_OUT_I8) o[q] = (int32_t)(r < -128 ? -128 : (r > 127 ? 127 : r));
+            else if (OUT == FPCC_OUT_I16) o[q] = (int32_t)(r < -32768 ? -32768 : (r > 32767 ? 32767 : r));
+            else o[q] = clamp_i32(r);
+        }
+        if (OUT == FPCC_OUT_I8)
+            ((uint32_t *)out)[i] = (uint32_t)(o[0] & 0xff) | ((uint32_t)(o[1] & 0xff) << 8) | ((uint32_t)(o[2] & 0xff) << 16) | ((uint32_t)(o[3] & 0xff) << 24);
+        else if (OUT == FPCC_OUT_I16)
+            ((uint2 *)out)[i] = make_uint2((uint32_t)(o[0] & 0xffff) | ((uint32_t)o[1] << 16), (uint32_t)(o[2] & 0xffff) | ((uint32_t)o[3] << 16));
+        else
+            ((int4 *)out)[i] = make_int4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 __global__ void __launch_bounds__(256) prelu_kernel(const int32_t *__restrict__ in, int64_t total, const int32_t *__restrict__ slope,
                                                     int32_t *__restrict__ out) {
     const int32_t sl = slope[0];
@@ -36,7 +67,7 @@ __global__ void __launch_bounds__(256) prelu_kernel(const int32_t *__restrict__ 
 
 static int ew_grid(int64_t total) {
     int64_t b = (total + 255) / 256;
-    int64_t cap = (int64_t)sm_count() * 16;
+    int64_t cap = (int64_t)sm_count() * 8;  // 8 resident 256-thread blocks per SM, grid-stride beyond that
     return (int)(b < cap ? b : cap);
 }
 
@@ -50,7 +81,16 @@ extern "C" int fpcc_requant(const int32_t *in, int64_t rows, int ch, const fpcc_
     int rc = check_epilogue(e, false);
     if (rc) return rc;
     int64_t total = rows * ch;
-    requant_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(in, total, ch, to_params(e), out);
+    cudaStream_t s = (cudaStream_t)stream;
+    EpiParams ep = to_params(e);
+    if (ch % 4 == 0 && (((uintptr_t)in | (uintptr_t)out) & 15) == 0) {
+        int64_t t4 = total / 4;
+        if (e->out_type == FPCC_OUT_I8) requant_vec4_kernel<FPCC_OUT_I8><<<ew_grid(t4), 256, 0, s>>>((const int4 *)in, t4, ch / 4, ep, out);
+        else if (e->out_type == FPCC_OUT_I16) requant_vec4_kernel<FPCC_OUT_I16><<<ew_grid(t4), 256, 0, s>>>((const int4 *)in, t4, ch / 4, ep, out);
+        else requant_vec4_kernel<FPCC_OUT_I32><<<ew_grid(t4), 256, 0, s>>>((const int4 *)in, t4, ch / 4, ep, out);
+    } else {
+        requant_kernel<<<ew_grid(total), 256, 0, s>>>(in, total, ch, ep, out);
+    }
     FPCC_LAUNCH_CHECK();
     return FPCC_OK;
 }
@@ -88,6 +128,7 @@ extern "C" int fpcc_spconv_i8(const int8_t *in_feats, int n_in, int c_in, const 
     FPCC_REQUIRE(n_in > 0 && n_out > 0 && c_in > 0 && c_out > 0 && kvol > 0 && ld >= n_out, "spconv_i8: bad sizes");
     int rc = check_epilogue(e, true);
     if (rc) return rc;
+    FPCC_REQUIRE(e->row_bias == nullptr, "spconv_i8: row_bias belongs to the linear kernels");
     EpiParams ep = to_params(e);
     if (tc_enabled() && !zp_comp) {
         rc = launch_conv_tc(in_feats, n_in, c_in, weight, kvol, c_out, nbr_table, ld, n_out, ep, out, (cudaStream_t)stream);

@@ -41,18 +41,52 @@ __device__ __forceinline__ EncSym make_enc_sym(uint32_t start, uint32_t freq, ui
     return s;
 }
 
-// One warp per stream.  Entries of stream b are ranges[rng_off[b] .. rng_off[b+1]) in DECODE order and are
-// consumed back to front (rANS is LIFO).  Bytes are written backwards from the end of the stream's slot;
-// they are collected four at a time in a register and stored as aligned words.
-__global__ void __launch_bounds__(32) rans_encode_kernel(const uint32_t *__restrict__ ranges, const uint8_t *__restrict__ bits,
-                                                         const int64_t *__restrict__ rng_off, uint8_t *__restrict__ out,
-                                                         int64_t out_stride, int32_t *__restrict__ out_len,
-                                                         uint32_t *__restrict__ state_io, int do_flush) {
-    const int b = blockIdx.x, lane = threadIdx.x;
+// Encoding is two kernels.  (1) enc_prepare_kernel, fully parallel: every entry gets its exact-division
+// constants {x_max, rcp, bias, cmpl | rcp_shift << 16}.  (2) rans_encode_kernel, one warp per stream, all lanes
+// uniform: entries of stream b are [rng_off[b], rng_off[b+1]) in DECODE order and are consumed back to front
+// (rANS is LIFO) with 8 records prefetched ahead of the state recurrence; bytes are written backwards from the
+// end of the stream's slot, collected in a register and stored as aligned 32-bit words.
+__global__ void __launch_bounds__(256) enc_prepare_kernel(const uint32_t *__restrict__ ranges, const uint8_t *__restrict__ bits,
+                                                          int64_t total, uint4 *__restrict__ recs) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    uint32_t r = ranges[i];
+    EncSym es = make_enc_sym(r & 0xFFFFu, (r >> 16) + 1u, bits ? (uint32_t)bits[i] : 16u);
+    recs[i] = make_uint4(es.x_max, es.rcp, es.bias, (uint32_t)es.cmpl | ((uint32_t)es.rcp_shift << 16));
+}
+
+// predicated 32-bit store (keeps the serial loop free of branches)
+__device__ __forceinline__ void st_u32_if(void *p, uint32_t v, bool pred) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.u32 [%0], %1;\n\t}" ::"l"(p), "r"(v), "r"((uint32_t)pred) : "memory");
+}
+
+// One rANS step on record r: branch-free.  Emitted bytes collect in `acc` (oldest byte most significant) and
+// leave as aligned 32-bit words written backwards.
+__device__ __forceinline__ void enc_step(uint32_t &x, const uint4 r, uint64_t &acc, int &nacc, uint8_t *&ptr) {
+    // RansEncRenorm, rans_byte.h:77-89: x < 2^31 and x_max >= 2^15, so at most two bytes leave
+    const int nb = (int)(x >= r.x) + (int)((x >> 8) >= r.x);
+    const uint32_t two = ((x & 0xffu) << 8) | ((x >> 8) & 0xffu);  // first emitted byte (higher address) on top
+    acc = (acc << (8 * nb)) | (uint64_t)(two >> (16 - 8 * nb));
+    nacc += nb;
+    x >>= 8 * nb;
+    const bool fl = nacc >= 4;
+    st_u32_if(ptr - 4, (uint32_t)(acc >> ((8 * (nacc - 4)) & 63)), fl);
+    ptr -= fl ? 4 : 0;
+    nacc -= fl ? 4 : 0;
+    const uint32_t q = __umulhi(x, r.y) >> (r.w >> 16);  // exact x / freq (rans_byte.h:201-259)
+    x = x + r.z + q * (r.w & 0xFFFFu);
+}
+
+// One thread per stream (the recurrence is serial; a lone thread needs no divergence bookkeeping).
+__global__ void __launch_bounds__(32) rans_encode_kernel(const uint4 *__restrict__ recs, const int64_t *__restrict__ rng_off,
+                                                         uint8_t *__restrict__ out, int64_t out_stride,
+                                                         int32_t *__restrict__ out_len, uint32_t *__restrict__ state_io,
+                                                         int do_flush) {
+    if (threadIdx.x != 0) return;
+    const int b = blockIdx.x;
     const int64_t lo = rng_off[b], hi = rng_off[b + 1];
     uint8_t *const base = out + (int64_t)b * out_stride;
     uint8_t *ptr = base + out_stride;
-    uint8_t *const guard = base + 8;
     uint32_t x = RANS_L;
     bool overflow = false;
     if (state_io) {  // resume a stream left open by an earlier call (RansEncoder keeps its state between encode() calls)
@@ -60,57 +94,45 @@ __global__ void __launch_bounds__(32) rans_encode_kernel(const uint32_t *__restr
         uint32_t written = state_io[2 * b + 1];
         if (written == 0xFFFFFFFFu) overflow = true; else ptr -= written;
     }
-    const bool bytewise = ((uintptr_t)ptr & 3) != 0;  // unaligned resume point: plain byte stores
-    uint32_t acc = 0;
-    int nacc = 0;
-    for (int64_t top = hi; top > lo; top -= 32) {
-        int64_t i = top - 1 - lane;  // lane 0 holds the entry coded first
-        EncSym es = {};
-        if (i >= lo) {
-            uint32_t r = ranges[i];
-            es = make_enc_sym(r & 0xFFFFu, (r >> 16) + 1u, bits ? (uint32_t)bits[i] : 16u);
+    int64_t top = hi;
+    if (!overflow && ((uintptr_t)ptr & 3) == 0) {
+        // fast path: aligned write position, eight records prefetched ahead of the recurrence
+        uint64_t acc = 0;
+        int nacc = 0;
+        constexpr int U = 8;
+        while (top - lo >= U && ptr - base >= 4 * U + 16) {
+            uint4 r[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) r[u] = __ldg(&recs[top - 1 - u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) enc_step(x, r[u], acc, nacc, ptr);
+            top -= U;
         }
-        const uint32_t my_pk = (uint32_t)es.cmpl | ((uint32_t)es.rcp_shift << 16);
-        int cnt = (int)min((int64_t)32, top - lo);
-        for (int j = 0; j < cnt; ++j) {
-            uint32_t x_max = __shfl_sync(0xffffffffu, es.x_max, j);
-            uint32_t rcp = __shfl_sync(0xffffffffu, es.rcp, j);
-            uint32_t bias = __shfl_sync(0xffffffffu, es.bias, j);
-            uint32_t pk = __shfl_sync(0xffffffffu, my_pk, j);
-            while (x >= x_max) {  // RansEncRenorm, rans_byte.h:77-89 (at most two bytes at 16-bit precision)
-                uint32_t byte = x & 0xffu;
-                x >>= 8;
-                if (bytewise) {
-                    if (ptr > guard) { --ptr; if (lane == 0) *ptr = (uint8_t)byte; } else overflow = true;
-                } else {
-                    acc = (acc << 8) | byte;  // first byte emitted ends up at the highest address
-                    if (++nacc == 4) {
-                        if (ptr - 4 >= guard) { ptr -= 4; if (lane == 0) *reinterpret_cast<uint32_t *>(ptr) = acc; } else overflow = true;
-                        nacc = 0;
-                    }
-                }
-            }
-            uint32_t q = __umulhi(x, rcp) >> (pk >> 16);
-            x = x + bias + q * (pk & 0xFFFFu);
-        }
+        for (int t = nacc - 1; t >= 0; --t) *--ptr = (uint8_t)(acc >> (8 * t));  // bytes still held in the register
     }
-    for (int t = 0; t < nacc; ++t) {  // bytes still held in the register
-        if (ptr > guard) { --ptr; if (lane == 0) *ptr = (uint8_t)(acc >> (8 * (nacc - 1 - t))); } else overflow = true;
+    // tail (and unaligned resume points): plain loop with byte stores
+    uint8_t *const guard = base + 8;
+    for (; top > lo; --top) {
+        const uint4 r = __ldg(&recs[top - 1]);
+        while (x >= r.x) {
+            if (ptr > guard) *--ptr = (uint8_t)(x & 0xff); else overflow = true;
+            x >>= 8;
+        }
+        const uint32_t q = __umulhi(x, r.y) >> (r.w >> 16);
+        x = x + r.z + q * (r.w & 0xFFFFu);
     }
     if (!do_flush) {
-        if (lane == 0) {
-            state_io[2 * b] = x;
-            state_io[2 * b + 1] = overflow ? 0xFFFFFFFFu : (uint32_t)(base + out_stride - ptr);
-            out_len[b] = overflow ? -1 : (int32_t)(base + out_stride - ptr);
-        }
+        state_io[2 * b] = x;
+        state_io[2 * b + 1] = overflow ? 0xFFFFFFFFu : (uint32_t)(base + out_stride - ptr);
+        out_len[b] = overflow ? -1 : (int32_t)(base + out_stride - ptr);
         return;
     }
     // RansEncFlush, rans_byte.h:109-121
     if (ptr - 4 >= base && !overflow) {
         ptr -= 4;
-        if (lane < 4) ptr[lane] = (uint8_t)(x >> (8 * lane));
-        if (lane == 0) out_len[b] = (int32_t)(base + out_stride - ptr);
-    } else if (lane == 0) {
+        for (int t = 0; t < 4; ++t) ptr[t] = (uint8_t)(x >> (8 * t));
+        out_len[b] = (int32_t)(base + out_stride - ptr);
+    } else {
         out_len[b] = -1;
     }
 }
@@ -165,25 +187,121 @@ struct ByteWindow {
         nextw = *wp++;
         refill();
     }
-    __device__ __forceinline__ void refill() {
-        if (avail <= 4) {
-            win |= (uint64_t)__byte_perm(nextw, 0, 0x0123) << (32 - 8 * avail);
-            avail += 4;
+    __device__ __forceinline__ void refill() {  // written with selects: no branch in the serial loop
+        const bool need = avail <= 4;
+        const uint64_t w = (uint64_t)__byte_perm(nextw, 0, 0x0123) << ((32 - 8 * avail) & 63);
+        win |= need ? w : 0ull;
+        avail += need ? 4 : 0;
+        if (need) {
             nextw = *wp++;
+            if (((uintptr_t)wp & 127) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(wp + 64));  // two lines ahead
         }
     }
-    __device__ __forceinline__ uint32_t take(int n) {  // n in {0,1,2}: next n bytes, first byte most significant
-        uint32_t v = n ? (uint32_t)(win >> (64 - 8 * n)) : 0u;
+    // Shifts the next n (0..2) bytes of the stream into x from the right: x = (x << 8n) | bytes.
+    __device__ __forceinline__ uint32_t shift_in(uint32_t x, int n) {
+        x = __funnelshift_l((uint32_t)(win >> 32), x, 8 * n);
         win <<= 8 * n;
         avail -= n;
         refill();
-        return v;
+        return x;
     }
 };
 
-// One warp per stream; all lanes carry the same state.  Fast path: per-symbol rows of S <= 256 entries with a
-// 256-entry (512 B) pitch.  The symbol search is two ballots: a coarse one over every 8th entry (prefetched 8
-// symbols ahead, it does not depend on the coder state) and a fine one over the 9 entries around the hit.
+// ---- fast path: one CDF row per symbol, S <= 256 entries, 256-entry (512 B) row pitch -----------------------
+// Two warps per stream.  Warp 1 is a one-thread producer: it streams the rows, which do not depend on the coder
+// state, into a shared-memory ring with bulk async copies (8 rows = 4 KB per copy, 8 slots), so the decoder never
+// waits on L2/HBM.  Warp 0 decodes; all its lanes carry the same state.  The symbol search is two ballots: a
+// coarse one over every 8th entry and a fine one over the 9 entries around the hit.
+constexpr int DEC_SLOT_ROWS = 8, DEC_SLOTS = 8;
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "DEC_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra.uni DEC_DONE;\n\t"
+        "bra.uni DEC_WAIT;\n\t"
+        "DEC_DONE:\n\t"
+        "}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+
+__global__ void __launch_bounds__(64) rans_decode_rows_kernel(fpcc_rans_dec_state *st, const uint8_t *__restrict__ bytes,
+                                                              const int64_t *__restrict__ byte_off, const uint16_t *__restrict__ cdf,
+                                                              int S, const int64_t *__restrict__ row_off, int32_t *__restrict__ symbols) {
+    __shared__ __align__(128) uint16_t ring[DEC_SLOTS][DEC_SLOT_ROWS][256];
+    __shared__ uint64_t full[DEC_SLOTS], empty[DEC_SLOTS];
+    const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t lo = row_off[b], hi = row_off[b + 1];
+    const int64_t n = hi - lo;
+    const int64_t nslots = (n + DEC_SLOT_ROWS - 1) / DEC_SLOT_ROWS;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < DEC_SLOTS; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&full[i])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&empty[i])));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int64_t sl = 0; sl < nslots; ++sl) {
+                const int slot = (int)(sl % DEC_SLOTS);
+                bar_wait(&empty[slot], (uint32_t)(((sl / DEC_SLOTS) & 1) ^ 1));
+                const int64_t rows = min((int64_t)DEC_SLOT_ROWS, n - sl * DEC_SLOT_ROWS);
+                const uint32_t nbytes = (uint32_t)(rows * 512);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&full[slot])), "r"(nbytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(smem_addr(&ring[slot][0][0])), "l"(cdf + (lo + sl * DEC_SLOT_ROWS) * 256), "r"(nbytes),
+                               "r"(smem_addr(&full[slot])) : "memory");
+            }
+        }
+        return;
+    }
+    fpcc_rans_dec_state s = st[b];
+    const uint8_t *p = bytes + byte_off[b];
+    uint32_t x = s.x, pos = s.pos;
+    ByteWindow bw;
+    bw.init(p + pos);
+    const int cidx = lane * 8 + 7;
+    const bool cvalid = cidx < S - 1;
+    for (int64_t sl = 0; sl < nslots; ++sl) {
+        const int slot = (int)(sl % DEC_SLOTS);
+        bar_wait(&full[slot], (uint32_t)((sl / DEC_SLOTS) & 1));
+        const int rows = (int)min((int64_t)DEC_SLOT_ROWS, n - sl * DEC_SLOT_ROWS);
+        const int64_t i0 = lo + sl * DEC_SLOT_ROWS;
+        uint32_t cv = cvalid ? (uint32_t)ring[slot][0][cidx] : 0x10000u;
+        for (int r = 0; r < rows; ++r) {
+            const uint16_t *row = ring[slot][r];
+            const uint32_t cv_next = (cvalid && r + 1 < rows) ? (uint32_t)ring[slot][r + 1][cidx] : 0x10000u;
+            const uint32_t cf = x & 0xFFFFu;
+            // symbol = #{j < S-1 : cdf[j] <= cf}  (== upper_bound clamped to S-1, simple_rans_wrapper.cpp:225-228)
+            const int g = __popc(__ballot_sync(0xffffffffu, cv <= cf));  // groups of 8 entries entirely <= cf
+            const int idx = 8 * g - 1 + lane;                             // lanes 0..8: entries 8g-1 .. 8g+7
+            const uint32_t w = row[min(max(idx, 0), 255)];                // always in the row: no divergent load
+            uint32_t v = idx < 0 ? 0u : w;
+            v = (lane > 8 || idx >= S - 1) ? 0x10000u : v;
+            const int c = __popc(__ballot_sync(0xffffffffu, v <= cf));    // >= 1: lane 0 is always <= cf
+            const uint32_t start = __shfl_sync(0xffffffffu, v, c - 1);
+            const uint32_t end = __shfl_sync(0xffffffffu, v, c);
+            x = (end - start) * (x >> 16) + cf - start;                   // RansDecAdvance, rans_byte.h:149-165
+            const int nb = (int)(x < RANS_L) + (int)(x < (1u << 15));     // renormalisation: 0..2 bytes
+            x = bw.shift_in(x, nb);
+            pos += nb;
+            if (lane == 0) symbols[i0 + r] = 8 * g + c - 1;
+            cv = cv_next;
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&empty[slot])) : "memory");
+    }
+    if (lane == 0) {
+        s.x = x; s.pos = pos; s.err = s.err | (uint32_t)(pos > s.len);
+        st[b] = s;
+    }
+}
+
+// ---- generic path: one warp per stream; binary search on a shared table, a per-stream table, or long rows ----
 __global__ void __launch_bounds__(32) rans_decode_kernel(fpcc_rans_dec_state *st, const uint8_t *__restrict__ bytes,
                                                          const int64_t *__restrict__ byte_off, const uint16_t *__restrict__ cdf,
                                                          int64_t n_cdf, int S, int ld, const int64_t *__restrict__ row_off,
@@ -195,42 +313,7 @@ __global__ void __launch_bounds__(32) rans_decode_kernel(fpcc_rans_dec_state *st
     ByteReader br = {bytes + byte_off[b], s.pos, s.len, s.err};
     uint32_t x = s.x;
     const int64_t lo = row_off[b], hi = row_off[b + 1];
-    if (n_cdf != 1 && !rows_per_stream && ld == 256 && S <= 256) {
-        constexpr int PF = 8;
-        const int cidx = lane * 8 + 7;
-        const bool cvalid = cidx < S - 1;
-        uint32_t coarse[PF];
-#pragma unroll
-        for (int d = 0; d < PF; ++d) coarse[d] = (cvalid && lo + d < hi) ? (uint32_t)cdf[(lo + d) * 256 + cidx] : 0x10000u;
-        ByteWindow bw;
-        bw.init(br.p + br.pos);
-        uint32_t pos = br.pos;
-        for (int64_t i0 = lo; i0 < hi; i0 += PF) {
-#pragma unroll
-            for (int d = 0; d < PF; ++d) {
-                const int64_t i = i0 + d;
-                if (i >= hi) break;
-                const uint32_t cv = coarse[d];
-                coarse[d] = (cvalid && i + PF < hi) ? (uint32_t)cdf[(i + PF) * 256 + cidx] : 0x10000u;
-                const uint32_t cf = x & 0xFFFFu;
-                // symbol = #{j < S-1 : cdf[j] <= cf}  (== upper_bound clamped to S-1, simple_rans_wrapper.cpp:225-228)
-                const int g = __popc(__ballot_sync(0xffffffffu, cv <= cf));  // groups of 8 entries entirely <= cf
-                const int idx = 8 * g - 1 + lane;                             // lanes 0..8: entries 8g-1 .. 8g+7
-                uint32_t v = 0x10000u;
-                if (lane <= 8) v = idx < 0 ? 0u : (idx < S - 1 ? (uint32_t)cdf[i * 256 + idx] : 0x10000u);
-                const int c = __popc(__ballot_sync(0xffffffffu, v <= cf));    // >= 1: lane 0 is always <= cf
-                const uint32_t start = __shfl_sync(0xffffffffu, v, c - 1);
-                const uint32_t end = __shfl_sync(0xffffffffu, v, c);
-                x = (end - start) * (x >> 16) + cf - start;                   // RansDecAdvance, rans_byte.h:149-165
-                const int nb = (int)(x < RANS_L) + (int)(x < (1u << 15));
-                x = (x << (8 * nb)) | bw.take(nb);
-                pos += nb;
-                if (lane == 0) symbols[i] = 8 * g + c - 1;
-            }
-        }
-        br.pos = pos;
-        if (pos > br.len) br.err = 1;
-    } else {
+    {
         // generic path: binary search by every lane on the same row (shared table, or S > 256)
         for (int64_t i = lo; i < hi; ++i) {
             const uint16_t *row = n_cdf == 1 ? cdf : cdf + (rows_per_stream ? (int64_t)b : i) * (int64_t)ld;
@@ -445,13 +528,25 @@ __global__ void pmf_to_cdf_kernel(double *__restrict__ pmf, int n_tables, int pm
 using namespace fpcc;
 
 extern "C" int fpcc_rans_encode(const uint32_t *ranges, const uint8_t *bits, const int64_t *rng_off, int n_streams,
-                                uint8_t *out, int64_t out_stride, int32_t *out_len, uint32_t *state_io, int do_flush,
-                                void *stream) {
+                                int64_t total_entries, uint8_t *out, int64_t out_stride, int32_t *out_len,
+                                uint32_t *state_io, int do_flush, void *stream) {
     FPCC_REQUIRE(rng_off && out && out_len, "rans_encode: NULL pointer");
-    FPCC_REQUIRE(n_streams > 0 && out_stride >= 16, "rans_encode: bad sizes");
+    FPCC_REQUIRE(n_streams > 0 && out_stride >= 16 && total_entries >= 0, "rans_encode: bad sizes");
+    FPCC_REQUIRE(total_entries == 0 || ranges, "rans_encode: NULL ranges");
     FPCC_REQUIRE(do_flush || state_io, "rans_encode: an open (unflushed) stream needs state_io");
-    rans_encode_kernel<<<n_streams, 32, 0, (cudaStream_t)stream>>>(ranges, bits, rng_off, out, out_stride, out_len, state_io, do_flush);
-    FPCC_LAUNCH_CHECK();
+    cudaStream_t s = (cudaStream_t)stream;
+    uint4 *recs = nullptr;
+    if (total_entries > 0) {
+        FPCC_CUDA(cudaMallocAsync((void **)&recs, (size_t)total_entries * sizeof(uint4), s));
+        enc_prepare_kernel<<<ceil_div(total_entries, 256), 256, 0, s>>>(ranges, bits, total_entries, recs);
+    }
+    rans_encode_kernel<<<n_streams, 32, 0, s>>>(recs, rng_off, out, out_stride, out_len, state_io, do_flush);
+    cudaError_t le = cudaGetLastError();
+    if (recs) cudaFreeAsync(recs, s);
+    if (le != cudaSuccess) {
+        fpcc::set_error("rans_encode: kernel launch failed: %s", cudaGetErrorString(le));
+        return FPCC_ERR_CUDA;
+    }
     return FPCC_OK;
 }
 
@@ -469,8 +564,11 @@ extern "C" int fpcc_rans_decode(fpcc_rans_dec_state *st, const uint8_t *bytes, c
     FPCC_REQUIRE(st && bytes && byte_off && cdf && row_off && symbols, "rans_decode: NULL pointer");
     FPCC_REQUIRE(n_streams > 0 && s > 0 && ld >= s, "rans_decode: bad sizes");
     FPCC_REQUIRE(ld != 256 || n_cdf == 1 || ((uintptr_t)cdf & 15) == 0, "rans_decode: padded CDF rows must be 16-byte aligned");
-    rans_decode_kernel<<<n_streams, 32, 0, (cudaStream_t)stream>>>(st, bytes, byte_off, cdf, n_cdf, s, ld, row_off, symbols,
-                                                                    rows_per_stream, s_per_stream);
+    if (n_cdf != 1 && !rows_per_stream && !s_per_stream && ld == 256 && s <= 256 && ((uintptr_t)cdf & 15) == 0)
+        rans_decode_rows_kernel<<<n_streams, 64, 0, (cudaStream_t)stream>>>(st, bytes, byte_off, cdf, s, row_off, symbols);
+    else
+        rans_decode_kernel<<<n_streams, 32, 0, (cudaStream_t)stream>>>(st, bytes, byte_off, cdf, n_cdf, s, ld, row_off, symbols,
+                                                                        rows_per_stream, s_per_stream);
     FPCC_LAUNCH_CHECK();
     return FPCC_OK;
 }

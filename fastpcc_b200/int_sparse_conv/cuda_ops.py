@@ -157,7 +157,7 @@ class _AffineIn8(LoadSaveUint32RequantMul):
         self.register_buffer('scale_out', torch.zeros((1,), dtype=torch.float32) - 1, persistent=True)
         self.register_buffer('zero_point_out', torch.zeros((1,), dtype=torch.float32), persistent=True)
 
-    def epilogue(self, with_bias: bool, residual=None, post_slope=None):
+    def epilogue(self, with_bias: bool, residual=None, post_slope=None, row_bias=None):
         shift = _shift_of(self)
         if self.out_scaled_int:
             out_type = ops.OUT_I8
@@ -166,7 +166,7 @@ class _AffineIn8(LoadSaveUint32RequantMul):
         return ops.make_epilogue(self.requant_mul, self.int_zero_point_out, shift, out_type,
                                  bias=self.bias if with_bias else None,
                                  slope=self.slope if self.with_prelu else None,
-                                 residual=residual, post_slope=post_slope)
+                                 residual=residual, post_slope=post_slope, row_bias=row_bias)
 
     def _import_scales(self, scale_in, scale_out):
         assert scale_in.dtype == torch.float32 and scale_in.numel() == 1
@@ -290,6 +290,22 @@ class SparseConvIn8Out8(_AffineIn8):
                             if_in_coords_equals_out_coords: bool = False, residual=None, post_slope=None):
         """-> (out N2 x C2 int8 | Q8.23 int32, hashmap_kv, in_out_maps); conv + epilogue in one kernel."""
         ep = self.epilogue(True, residual, post_slope)
+        if self.in_ch < 32 and not self.use_zero_point_in:
+            # thin input (first conv C_in = 1, occupancy embeds C_in = 8): im2col + one tensor-core linear
+            kv = self.kernel_volume
+            if in_out_maps is None:
+                in_out_maps, hashmap_kv = build_kernel_map(in_coords, out_coords, self.kernel_size, self.stride, hashmap_kv)
+            kmap = _as_kernel_map(in_out_maps, out_coords.shape[0], kv, -1, in_feats.device)
+            kp = max(32, (kv * self.in_ch + 15) // 16 * 16)
+            cache = getattr(self, '_patch_weight', None)
+            key = (self.weight._version, self.weight.data_ptr(), kp)
+            if cache is None or cache[0] != key:
+                wf = torch.zeros((self.out_ch, kp), dtype=torch.int8, device=self.weight.device)
+                wf[:, :kv * self.in_ch] = self.weight.permute(1, 0, 2).reshape(self.out_ch, kv * self.in_ch)
+                cache = (key, wf)
+                self._patch_weight = cache
+            patches = ops.gather_patches(in_feats, kmap.table, kp)
+            return ops.linear(patches, cache[1], ep), hashmap_kv, kmap
         return sparse_conv_in8w8out32(
             in_feats, self.weight, in_coords, out_coords, self.kernel_size, self.stride, in_out_maps, hashmap_kv,
             self.int_zero_point_in_comp if self.use_zero_point_in else None, if_in_coords_equals_out_coords, _epilogue=ep)
@@ -376,6 +392,17 @@ class RequantFxpToScaledInt8(LoadSaveUint32RequantMul):
         ep = ops.make_epilogue(self.requant_mul, self.int_zero_point_out, SharedFxpShift + _shift_of(self), ops.OUT_I8)
         return ops.requant(input, ep)
 
+    def bit_levels(self):
+        """int8 images of the Q8.23 values 0 and 1.0 (an occupancy bit << 23) under this requant, cached."""
+        key = (self.requant_mul._version, self.requant_shift._version, self.int_zero_point_out._version)
+        cache = getattr(self, '_bit_levels', None)
+        if cache is None or cache[0] != key:
+            probe = torch.tensor([[0, 1 << SharedFxpShift, 0, 0]], dtype=torch.int32, device=self.requant_mul.device)
+            q = self.forward(probe)[0, :2].tolist()
+            cache = (key, int(q[0]), int(q[1]))
+            self._bit_levels = cache
+        return cache[1], cache[2]
+
 
 class LinearIn8W8(_AffineIn8):
     def __init__(self, in_ch: int, out_ch: int, with_prelu: bool, out_scaled_int: bool, eps=None, requant_mul_guard_bits=None):
@@ -414,6 +441,24 @@ class LinearIn8W8(_AffineIn8):
         """GEMM + bias + [PReLU] + requant in one kernel.  `sel` (from ops.slot_pairs) evaluates only the
         occupied (row, child) blocks of a C -> 8C linear: identical values, 4-8x less work."""
         return ops.linear(input, self.weight, self.epilogue(True), sel=sel, n_out_rows=n_out_rows)
+
+    def forward_with_bits(self, input: torch.Tensor, occ: torch.Tensor, q0: int, q1: int) -> torch.Tensor:
+        """Linear over cat(input, bits) where `bits` are the 8 occupancy channels of `occ` (channel k = bit 7-k)
+        already requantised to the two int8 values q0 (bit clear) / q1 (bit set).  Their contribution
+        sum_k q[bit_k] * W[:, C+k] depends only on the occupancy byte, so it is a 256-row bias table and the
+        contraction keeps K = C (identical integers, no concat, tensor-core friendly K)."""
+        C = self.in_ch - 8
+        key = (q0, q1, self.weight._version, self.weight.data_ptr())
+        cache = getattr(self, '_bits_cache', None)
+        if cache is None or cache[0] != key:
+            w = self.weight
+            pat = ((torch.arange(256, device=w.device)[:, None] >> torch.arange(7, -1, -1, device=w.device)[None]) & 1).double()
+            q = pat * float(q1) + (1.0 - pat) * float(q0)                       # [256, 8]
+            table = (q @ w[:, C:].double().T).round().to(torch.int32).contiguous()  # exact: |values| < 2^53
+            cache = (key, w[:, :C].contiguous(), table)
+            self._bits_cache = cache
+        _, w_main, table = cache
+        return ops.linear(input, w_main, self.epilogue(True, row_bias=(table, occ)))
 
 
 class LinearIn8W8Out8(LinearIn8W8):

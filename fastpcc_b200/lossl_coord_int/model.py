@@ -85,6 +85,16 @@ class Level:
         return self.occ.to(torch.int32) - 1  # model.py:60
 
 
+def linear_with_bits(requant: RequantFxpToScaledInt8, linear: LinearIn8W8, f: torch.Tensor, occ: torch.Tensor,
+                     prelu: Optional[PReLUIn32Out32] = None) -> torch.Tensor:
+    """`linear(requant([prelu](cat(f, bits << 23))))` (model.py:63-64, 147, 172) without the concat: the bit
+    channels requantise to two constants, so their share of the contraction is a bias row chosen by the
+    occupancy byte (LinearIn8W8.forward_with_bits) and the GEMM keeps K = C."""
+    q0, q1 = requant.bit_levels()
+    x = f if prelu is None else prelu(f)
+    return linear.forward_with_bits(requant(x), occ, q0, q1)
+
+
 def _with(f, ref: SparseTensor, C=None, stride=None):
     x = SparseTensor(f, ref.C if C is None else C, ref.stride if stride is None else stride, None)
     x._caches = ref._caches
@@ -115,10 +125,13 @@ class OneScalePredictor(nn.Module):
         cur = self.dec(cur)
         return cur, self.pred(cur).F
 
-    def up(self, cur: SparseTensor, bits_fxp, child: Level):
-        cur.F = torch.cat((cur.F, bits_fxp), 1)
-        up = self.upsample(cur, sel=child.sel(), n_out_rows=child.n)
-        return up.F
+    def up(self, cur: SparseTensor, occ, child: Level):
+        """upsample branch (model.py:62-69): cat(F, bin << 23) -> Requant -> LinearPReLU(C+8 -> C) -> ResBlock ->
+        Requant -> Linear(C -> 8C)[child mask]; the concat and the masked 8C output are never materialised."""
+        u = self.upsample
+        x = _with(linear_with_bits(u[0], u[1], cur.F, occ), cur)
+        x = u[2](x)
+        return u[4](u[3](x.F), sel=child.sel(), n_out_rows=child.n)
 
 
 class OneScaleMultiStepPredictor(nn.Module):
@@ -167,13 +180,14 @@ class OneScaleMultiStepPredictor(nn.Module):
         occupancy is what this block predicts.  Shared by compress and decompress."""
         S = self.pred_steps
         emb_lv = levels[S - 2]  # the level whose occupancy bits are embedded (cur_bins[1] / cur_bins[-1])
-        if len(self.embed) == 0:
-            embed_f = emb_lv.bits_fxp()
+        if len(self.embed) == 0:  # pred_steps == 2: the embedding is the occupancy itself
+            f = linear_with_bits(self.dec[0], self.dec[1], cur.F, emb_lv.occ)
+            cur = self.dec[2](_with(f, cur))
         else:
             stride = tuple(s >> (S - 2) for s in cur.stride)
             embed_f = self.embed(_with(emb_lv.bits_fxp(), cur, C=emb_lv.C, stride=stride)).F
-        cur.F = torch.cat([cur.F, embed_f], 1)
-        cur = self.dec(cur)
+            cur.F = torch.cat([cur.F, embed_f], 1)
+            cur = self.dec(cur)
         x = cur
         for j, block in enumerate(self.pred):
             if j == 0:
@@ -184,13 +198,14 @@ class OneScaleMultiStepPredictor(nn.Module):
                 continue
             lv = levels[j]
             f = x.F  # [n_j, C]: features of the occupied children (selection already applied)
+            st = tuple(s >> j for s in cur.stride)
             if j != S - 1:
-                f = torch.cat([f, lv.bits_fxp()], 1)
-            x = _with(f, cur, C=lv.C, stride=tuple(s >> j for s in cur.stride))
-            if j != S - 1:
-                x = block(x, sel=levels[j + 1].sel(), n_out_rows=levels[j + 1].n)
+                # PReLU -> Requant -> LinearPReLU(C+8 -> C) on cat(f, bits) -> Conv -> Linear(C -> 8C)[child mask]
+                f = linear_with_bits(block[1], block[2], f, lv.occ, prelu=block[0])
+                x = block[3](_with(f, cur, C=lv.C, stride=st))
+                x.F = block[4](x.F, sel=levels[j + 1].sel(), n_out_rows=levels[j + 1].n)
             else:
-                x = block(x)
+                x = block(_with(f, cur, C=lv.C, stride=st))
         return cur, x.F
 
 
@@ -323,7 +338,7 @@ class Model(nn.Module):
             if isinstance(blk, OneScalePredictor):
                 cur, pred = blk.trunk(cur)
                 if idx != 1 and blk.if_upsample:
-                    f = blk.up(cur, lv.bits_fxp(), levels[idx - 1])
+                    f = blk.up(cur, lv.occ, levels[idx - 1])
                     cur = _with(f, cur, C=levels[idx - 1].C, stride=tuple(s // 2 for s in cur.stride))
             else:
                 S = blk.pred_steps
@@ -418,7 +433,7 @@ class Model(nn.Module):
                 cur, pred = blk.trunk(cur)
                 child = decode_level(pred, lv)
                 if idx != 1 and blk.if_upsample:
-                    f = blk.up(cur, lv.bits_fxp(), child)
+                    f = blk.up(cur, lv.occ, child)
                     cur = SparseTensor(f, child.C, tuple(s // 2 for s in cur.stride))  # fresh caches (model.py:88-91)
                 else:
                     ms_levels = [lv]

@@ -105,7 +105,8 @@ def workspace(nbytes, device):
     return buf
 
 
-def make_epilogue(requant_mul, zero_point, shift, out_type, bias=None, slope=None, residual=None, post_slope=None):
+def make_epilogue(requant_mul, zero_point, shift, out_type, bias=None, slope=None, residual=None, post_slope=None,
+                  row_bias=None):
     _need(requant_mul, torch.uint32, 'requant_mul')
     _need(zero_point, torch.int64, 'zero_point')
     if shift < 0:
@@ -120,7 +121,11 @@ def make_epilogue(requant_mul, zero_point, shift, out_type, bias=None, slope=Non
     e.mul_is_scalar = 1 if requant_mul.numel() == 1 else 0
     e.residual = _p(_need(residual, torch.int32, 'residual')) if residual is not None else None
     e.post_slope = _p(_need(post_slope, torch.int32, 'post_slope')) if post_slope is not None else None
-    e._keep = (bias, slope, requant_mul, zero_point, residual, post_slope)
+    if row_bias is not None:
+        table, idx = row_bias
+        e.row_bias = _p(_need(table, torch.int32, 'row_bias table', 2))
+        e.row_idx = _p(_need(idx, torch.uint8, 'row_bias index', 1))
+    e._keep = (bias, slope, requant_mul, zero_point, residual, post_slope, row_bias)
     return e
 
 
@@ -225,6 +230,18 @@ def slot_pairs(child_parent, child_slot):
     table = torch.empty((8, n), dtype=torch.int32, device=child_parent.device)
     _call('fpcc_slot_table', _p(child_parent), _p(child_slot), n, _p(table), n, _s())
     return kmap_compact(table)
+
+
+def gather_patches(feats, table, kp):
+    """im2col of a thin (C_in = 1 / 8) input along the neighbour table -> int8 [n_out, kp]"""
+    _need(feats, torch.int8, 'feats', 2)
+    _need(table, torch.int32, 'table', 2)
+    kv, n_out = table.shape
+    c = feats.shape[1]
+    alloc = torch.empty if kp == kv * c else torch.zeros
+    out = alloc((n_out, kp), dtype=torch.int8, device=feats.device)
+    _call('fpcc_gather_patches', _p(feats), c, _p(table), n_out, kv, n_out, _p(out), kp, _s())
+    return out
 
 
 def morton_encode(xyz_rows, col0=1, msb_axis=0):
@@ -377,7 +394,7 @@ def table_symbol_ranges(cdf, symbols, out=None):
     return out
 
 
-def rans_encode(ranges, rng_off, out_stride, bits=None, out=None, state_io=None, flush=True):
+def rans_encode(ranges, rng_off, out_stride, bits=None, out=None, state_io=None, flush=True, total=None):
     """-> (out uint8 [n_streams, out_stride], out_len int32 [n_streams]); stream b = out[b, out_stride-len:]"""
     _need(ranges, torch.int32, 'ranges', 1)  # packed uint32 bit patterns carried as int32
     _need(rng_off, torch.int64, 'rng_off', 1)
@@ -385,15 +402,16 @@ def rans_encode(ranges, rng_off, out_stride, bits=None, out=None, state_io=None,
     if out is None:
         out = torch.empty((ns, out_stride), dtype=torch.uint8, device=ranges.device)
     out_len = torch.empty(ns, dtype=torch.int32, device=ranges.device)
-    _call('fpcc_rans_encode', _p(ranges), _p(bits), _p(rng_off), ns, _p(out), out_stride, _p(out_len),
-              _p(state_io), 1 if flush else 0, _s())
+    total = ranges.numel() if total is None else int(total)
+    _call('fpcc_rans_encode', _p(ranges), _p(bits), _p(rng_off), ns, total, _p(out), out_stride, _p(out_len),
+          _p(state_io), 1 if flush else 0, _s())
     return out, out_len
 
 
 class RansDecodeStreams:
     """Device-resident decoder state for n streams (RansDecoder::flush + decode, batched)."""
 
-    PAD = 16  # the decoder's byte window reads a few bytes ahead of the stream position
+    PAD = 512  # the decoder's byte window reads (and prefetches) ahead of the stream position
 
     def __init__(self, data, byte_off, byte_len, padded=False):
         _need(data, torch.uint8, 'bytes', 1)

@@ -41,7 +41,7 @@ class RansEncoder:
         if ranges is None:
             ranges = torch.empty(1, dtype=torch.int32, device='cuda')
         off = torch.tensor([0, n], dtype=torch.int64, device='cuda')
-        _, out_len = ops.rans_encode(ranges, off, self._cap, out=self._buf, state_io=self._state, flush=flush)
+        _, out_len = ops.rans_encode(ranges, off, self._cap, out=self._buf, state_io=self._state, flush=flush, total=n)
         size = int(out_len.item())
         if size < 0:
             raise RuntimeError('RansEncoder: enc_buf_size exceeded')

@@ -123,7 +123,9 @@ int fpcc_gather_gemm_scatter_i8(const int8_t *A, const int8_t *B, int32_t *D,
  * v = acc + bias[ch]; if (slope && v<0) v = rha(v*slope, 25); p = v*mul[ch] + zero_point;
  * o = clamp(rha(p, shift));  rha = round-half-away arithmetic shift (bias_prelu_requant.cu:6-37).
  * residual/post_slope (fused kernels only, out_type I32): o = prelu32(wrap32(o + residual), post_slope)
- * i.e. the tail of SparseResBlockIn32W8Out32.forward (cuda_ops.py:90). */
+ * i.e. the tail of SparseResBlockIn32W8Out32.forward (cuda_ops.py:90).
+ * row_bias/row_idx (fused linear only) fold the 8 occupancy-bit input channels of `cat(F, bin << 23)` ->
+ * Linear(C+8 -> C) (model.py:63-64) into a 256-entry per-row bias table: the contraction keeps K = C. */
 typedef struct {
     const int32_t *bias;         /* [ch] or NULL                                    */
     const int32_t *slope;        /* device [1] Q6.25 or NULL                        */
@@ -134,6 +136,8 @@ typedef struct {
     int32_t mul_is_scalar;
     const int32_t *residual;     /* [rows, ch] int32 or NULL                        */
     const int32_t *post_slope;   /* device [1] Q6.25 or NULL                        */
+    const int32_t *row_bias;     /* fused kernels: [256, ch] table or NULL: v += row_bias[row_idx[row]][ch] */
+    const uint8_t *row_idx;      /* [rows] table row of every output row            */
 } fpcc_epilogue;
 
 /* replaces the 12 requant entry points of binding.cu:118-129 */
@@ -161,6 +165,12 @@ int fpcc_spconv_i8(const int8_t *in_feats, int n_in, int c_in,
 int fpcc_linear_i8(const int8_t *A, int m, int k, const int8_t *W, int n,
                    const int32_t *sel_row, const int32_t *sel_out, const int32_t *sel_offsets, int n_groups, int n_sel,
                    const fpcc_epilogue *ep, void *out, void *stream);
+
+/* im2col for thin inputs (C_in = 1 or 8): patches[o, k*c + j] = feats[table[k*ld + o] - 1, j], 0 where the
+ * table holds 0.  patches is [n_out, kp] int8 with kp >= kvol*c; columns >= kvol*c are left untouched (zero them
+ * once).  A sparse conv then becomes fpcc_linear_i8 over K = kp with the weight reshaped to [C_out, kp]. */
+int fpcc_gather_patches(const int8_t *feats, int c, const int32_t *table, int64_t ld, int kvol, int n_out,
+                        int8_t *patches, int kp, void *stream);
 
 /* k-major table for the selection above: table[g*ld + j] = child_parent[j]+1 if child_slot[j]==g else 0 */
 int fpcc_slot_table(const int32_t *child_parent, const uint8_t *child_slot, int n_child, int32_t *table, int64_t ld,
@@ -214,6 +224,7 @@ int fpcc_table_symbol_ranges(const uint16_t *cdf, int64_t n_cdf, int s, const in
  * state is stored back and out_len reports the bytes so far; do_flush = 1 writes the 4-byte state header
  * (RansEncoder::flush, simple_rans_wrapper.cpp:126-134). */
 int fpcc_rans_encode(const uint32_t *ranges, const uint8_t *bits, const int64_t *rng_off, int n_streams,
+                     int64_t total_entries /* = rng_off[n_streams], as a host value */,
                      uint8_t *out, int64_t out_stride, int32_t *out_len, uint32_t *state_io, int do_flush,
                      void *stream);
 
@@ -226,7 +237,7 @@ typedef struct {
 } fpcc_rans_dec_state;
 
 /* RansDecoder::flush (simple_rans_wrapper.cpp:139-145) for n_streams streams stored at
- * bytes + byte_off[b] with byte_len[b] bytes.  The buffer must stay readable for 16 bytes past the end of
+ * bytes + byte_off[b] with byte_len[b] bytes.  The buffer must stay readable for 512 bytes past the end of
  * the last stream (the decoders read ahead through an aligned byte window; the extra bytes are never used). */
 int fpcc_rans_dec_init(fpcc_rans_dec_state *st, const uint8_t *bytes, const int64_t *byte_off,
                        const int32_t *byte_len, int n_streams, void *stream);
