@@ -1,0 +1,74 @@
+"""Frame / partition sharding across the GPUs of one box.
+
+Frames and kd-tree partitions are independent units (each becomes its own self-contained bitstream,
+models/convolutional/lossl_coord_int/model.py:455-463), so the path shards with NO data-path collective: every
+rank codes its own units; the only exchange is the host-side gather of the finished byte strings in original
+order.  One process per GPU (`torch.distributed`, NCCL on the GPU box, gloo in the CPU tests).
+"""
+from typing import Callable, Dict, List, Optional, Sequence
+
+import torch.distributed as dist
+
+
+def assign(sizes: Sequence[int], world: int) -> List[List[int]]:
+    """Size-balanced deterministic assignment (longest-processing-time first); ties keep index order."""
+    order = sorted(range(len(sizes)), key=lambda i: (-int(sizes[i]), i))
+    loads = [0] * world
+    out: List[List[int]] = [[] for _ in range(world)]
+    for i in order:
+        r = min(range(world), key=lambda k: (loads[k], k))
+        out[r].append(i)
+        loads[r] += int(sizes[i])
+    for lst in out:
+        lst.sort()
+    return out
+
+
+def local_indices(sizes: Sequence[int], rank: Optional[int] = None, world: Optional[int] = None) -> List[int]:
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    return assign(sizes, world)[rank]
+
+
+def gather_ordered(local: Dict[int, bytes], n_total: int, dst: int = 0, group=None) -> Optional[List[bytes]]:
+    """Collects {unit index: bytes} from every rank on `dst`, returned in unit order (None elsewhere)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        assert len(local) == n_total
+        return [local[i] for i in range(n_total)]
+    rank = dist.get_rank(group)
+    bucket = [None] * dist.get_world_size(group) if rank == dst else None
+    dist.gather_object(local, bucket, dst=dst, group=group)
+    if rank != dst:
+        return None
+    merged: Dict[int, bytes] = {}
+    for part in bucket:
+        for k, v in part.items():
+            assert k not in merged, f'unit {k} coded twice'
+            merged[k] = v
+    assert len(merged) == n_total, f'{n_total - len(merged)} units missing'
+    return [merged[i] for i in range(n_total)]
+
+
+def compress_sharded(compress_batch: Callable[[list], List[bytes]], units: list, sizes: Sequence[int],
+                     dst: int = 0, group=None) -> Optional[List[bytes]]:
+    """Every rank codes its share of `units` with `compress_batch` (e.g. Model.compress_batch); rank `dst` gets
+    all bitstreams in the original order."""
+    mine = local_indices(sizes)
+    coded = compress_batch([units[i] for i in mine]) if mine else []
+    return gather_ordered(dict(zip(mine, coded)), len(units), dst=dst, group=group)
+
+
+def pack_partitions(streams: List[bytes]) -> bytes:
+    """3-byte little-endian length prefix per stream (model.py:462)."""
+    return b''.join(len(s).to_bytes(3, 'little') + s for s in streams)
+
+
+def unpack_partitions(blob: bytes) -> List[bytes]:
+    out, pos = [], 0
+    while pos != len(blob):
+        n = int.from_bytes(blob[pos: pos + 3], 'little')
+        out.append(blob[pos + 3: pos + 3 + n])
+        pos += 3 + n
+    return out
