@@ -23,7 +23,6 @@ import os
 import os.path as osp
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -44,35 +43,39 @@ def load_peaks():
     return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback'
 
 
-class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons of one GPU during the timed region."""
+class ClockSampler:
+    """One long-lived `nvidia-smi -lms` process logging clocks / throttle reasons of one GPU during the timed region
+    (spawning nvidia-smi repeatedly from Python perturbs the run it is supposed to watch)."""
     Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '250'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            pass
 
-    def run(self):
-        while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits'],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([v.strip() for v in out.split(',')])
-            except Exception:
-                pass
-            self.stop_flag.wait(0.2)
+    def start(self):
+        pass
 
     def summary(self):
-        self.stop_flag.set()
-        if not self.samples:
+        samples = []
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+                samples = [[v.strip() for v in line.split(',')] for line in out.strip().splitlines() if line.count(',') >= 6]
+            except Exception:
+                self.proc.kill()
+        if not samples:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        sm = sorted(float(s[0]) for s in self.samples)
+        sm = sorted(float(s[0]) for s in samples)
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith('active') for s in self.samples)]
-        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.samples[0][1]), 'reasons': reasons,
-                'samples': len(sm), 'power_w_max': max(float(s[2]) for s in self.samples)}
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith('active') for s in samples)]
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(samples[0][1]), 'reasons': reasons,
+                'samples': len(sm), 'power_w_max': max(float(s[2]) for s in samples)}
 
 
 def make_frames(n, rank):
@@ -118,7 +121,8 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--frames', type=int, default=8, help='frames per step per GPU (coded together, one stream each)')
+    ap.add_argument('--frames', type=int, default=32, help='frames per step per GPU (coded together, one stream each)')
+    ap.add_argument('--groups', type=int, default=1, help='slices of the batch coded concurrently (CUDA streams)')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--cpu-stride', type=int, default=8, help='subsampling of the CPU baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -150,9 +154,11 @@ def main():
     n_pts = sum(f.shape[0] for f in frames_host)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
+    G = args.groups
+
     def step_device():
-        data = model.compress_batch(frames_dev)   # one rANS stream per frame, all frames through every kernel together
-        return model.decompress_batch(data)
+        data = model.compress_batch(frames_dev, n_groups=G)  # one rANS stream per frame; G slices coded concurrently
+        return model.decompress_batch(data, n_groups=G)
 
     h2d = d2h = 0
 
@@ -160,8 +166,8 @@ def main():
         nonlocal h2d, d2h
         h2d = d2h = 0
         xs = [p.to(dev, non_blocking=True) for p in pinned]
-        data = model.compress_batch(xs)         # bytes on the host: D2H of the bitstreams inside
-        rec = model.decompress_batch(data)      # H2D of the bitstreams inside
+        data = model.compress_batch(xs, n_groups=G)     # bytes on the host: D2H of the bitstreams inside
+        rec = model.decompress_batch(data, n_groups=G)  # H2D of the bitstreams inside
         rec_h = [r.cpu() for r in rec]          # D2H of the decoded coordinates
         nbytes = sum(len(d) for d in data)
         h2d += sum(p.numel() * 4 for p in pinned) + nbytes
@@ -191,13 +197,15 @@ def main():
             total_ms += e0.elapsed_time(e1)
         barrier()
         clocks = sampler.summary() if sampler else None
+        sys.stderr.write(f'[bench] {fn.__name__}: {steps} steps, {total_ms / steps:.1f} ms/step, peak mem '
+                         f'{torch.cuda.max_memory_allocated() / 2**30:.1f} GiB reserved {torch.cuda.memory_reserved() / 2**30:.1f} GiB\n')
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()) / steps, clocks
 
     ms_dev, clocks = timed(step_device, args.steps, args.warmup, sample_clocks=True)
-    ms_e2e, _ = timed(step_e2e, args.steps, 1)
+    ms_e2e, _ = timed(step_e2e, args.steps, max(1, args.warmup - 1))
     pts_all = torch.tensor([n_pts], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(pts_all)
@@ -205,17 +213,19 @@ def main():
 
     # ---- instrumented pass: CUDA-event time and algorithmic work of every GEMM-class launch -------------
     prof = ops.enable_profile(True)
-    step_device()
+    model.decompress_batch(model.compress_batch(frames_dev))  # single group: per-launch events on one stream
     torch.cuda.synchronize()
     ops.enable_profile(False)
     stats = ops.profile_summary(prof)
     peaks, peak_kind = load_peaks()
-    int8_peak = 2.0 * peaks['bf16_tflops']  # kind::i8 runs at twice the bf16 rate; measured bf16 burst x 2
+    int8_probe = ops.mma_i8_peak(20000, 256)  # back-to-back tcgen05.mma.kind::i8 on resident tiles, this GPU, now
+    int8_peak = int8_probe
     conv = stats.get('spconv_tc', {'ms': 0.0, 'ops': 0.0, 'launches': 0, 'mma_ops': 0.0})
     roof = {'bound': 'tensor', 'kernel': 'igemm_tc_kernel<conv> (tcgen05.mma.kind::i8)',
             'achieved': (conv['ops'] / (conv['ms'] * 1e-3) / 1e12) if conv['ms'] else 0.0,
             'peak': int8_peak, 'unit': 'TOP/s', 'traffic': None,
-            'peak_source': f'2 x bf16_tflops of MEASURED_PEAKS.json ({peak_kind})',
+            'peak_source': 'measured in this run: fpcc_mma_i8_peak (tcgen05.mma.kind::i8 M128 N256 K32 back to back on all SMs); '
+                           f'for scale, 2 x bf16_tflops of MEASURED_PEAKS.json ({peak_kind}) = {2.0 * peaks["bf16_tflops"]:.1f}',
             'launches': conv['launches'], 'ms_per_step': conv['ms'],
             'executed_mma_tops': (conv['mma_ops'] / (conv['ms'] * 1e-3) / 1e12) if conv['ms'] else 0.0,
             'share_of_step': conv['ms'] / ms_dev if ms_dev else 0.0}
@@ -239,7 +249,7 @@ def main():
             'metric': 'encode+decode Mpts/s', 'value': pts_all / (ms_dev * 1e-3) / 1e6, 'unit': 'Mpts/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_dev,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int8', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'frames_per_step_per_gpu': args.frames, 'points_per_step': pts_all,
+            'config': {'workload': WORKLOAD, 'frames_per_step_per_gpu': args.frames, 'concurrent_groups': G, 'points_per_step': pts_all,
                        'l2': 'flushed between timed iterations (256 MB write)', 'weights': 'seeded random int8 (seed 7)'},
             'clocks': clocks,
             'e2e': {'value': pts_all / (ms_e2e * 1e-3) / 1e6, 'unit': 'Mpts/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,

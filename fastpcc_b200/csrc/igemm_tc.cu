@@ -145,6 +145,86 @@ struct TcArgs {
 //   warps 8-11  gather producers (one output row per thread) + per-tile metadata (source rows, offset mask)
 //   warp 12     weight producer (TMA)          warp 13   TMEM owner + MMA issuer
 // ---------------------------------------------------------------------------------------------
+// Epilogue of one 32-column chunk of one output row.  Values stay in registers; the body is specialised at compile
+// time on the output type, the PReLU and the occupancy row-bias so that the 32x unrolled arithmetic carries no
+// per-element selects: ~22 (no PReLU) / ~32 (PReLU) integer instructions per element, all 64-bit exact.
+struct EpiCtx {
+    const int2 *chan;          // smem (bias, mul) pairs of this chunk
+    int32_t slope, post;
+    int64_t zp, half;          // half = 2^(shift-1) (0 when shift == 0)
+    int shift, sgn;            // sgn = 1 when shift > 0 (round-half-away correction for negatives)
+    const int32_t *row_bias;   // 32 entries of the occupancy-indexed bias row (ROWBIAS)
+    const int32_t *residual;   // 32 entries, or NULL
+    bool has_post;
+    int nvalid;
+};
+
+__device__ __forceinline__ int32_t sat_s8(int64_t r) { int32_t o; asm("cvt.sat.s8.s64 %0, %1;" : "=r"(o) : "l"(r)); return o; }
+__device__ __forceinline__ int32_t sat_s16(int64_t r) { int32_t o; asm("cvt.sat.s16.s64 %0, %1;" : "=r"(o) : "l"(r)); return o; }
+__device__ __forceinline__ int32_t sat_s32(int64_t r) { int32_t o; asm("cvt.sat.s32.s64 %0, %1;" : "=r"(o) : "l"(r)); return o; }
+
+template <int OUT, bool SLOPE, bool ROWBIAS>
+__device__ __forceinline__ void epi_chunk(const uint32_t (&acc)[32], const EpiCtx &cx, void *optr, bool vec) {
+    int32_t o[32];
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+        const int2 bm = cx.chan[q];
+        int32_t a32 = (int32_t)acc[q];
+        if (ROWBIAS) a32 = (int32_t)((uint32_t)a32 + (uint32_t)__ldg(&cx.row_bias[q < cx.nvalid ? q : 0]));
+        int64_t v = (int64_t)a32 + (int64_t)bm.x;
+        if (SLOPE) {  // Q6.25 PReLU on negatives, round half away (bias_prelu_requant.cu:17-22)
+            int64_t t = v * (int64_t)cx.slope;
+            t = (t + ((1ll << 24) - (int64_t)((uint64_t)t >> 63))) >> 25;
+            v = v < 0 ? t : v;
+        }
+        int64_t r = v * (int64_t)(uint32_t)bm.y + cx.zp;
+        r = (r + (cx.half - (int64_t)(((uint64_t)r >> 63) & (uint64_t)cx.sgn))) >> cx.shift;
+        o[q] = OUT == FPCC_OUT_I8 ? sat_s8(r) : (OUT == FPCC_OUT_I16 ? sat_s16(r) : sat_s32(r));
+    }
+    if (OUT == FPCC_OUT_I32 && cx.residual) {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+            int32_t rv = (int32_t)((uint32_t)o[q] + (uint32_t)__ldg(&cx.residual[q < cx.nvalid ? q : 0]));  // int32 add wraps
+            o[q] = cx.has_post ? sat_s32(prelu_q25((int64_t)rv, cx.post)) : rv;
+        }
+    }
+    if (vec) {
+        if (OUT == FPCC_OUT_I8) {
+            uint4 *dst = reinterpret_cast<uint4 *>(optr);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t w[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int q = h * 16 + t * 4;
+                    w[t] = (uint32_t)(o[q] & 0xff) | ((uint32_t)(o[q + 1] & 0xff) << 8) | ((uint32_t)(o[q + 2] & 0xff) << 16) |
+                           ((uint32_t)(o[q + 3] & 0xff) << 24);
+                }
+                dst[h] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        } else {
+            int4 *dst = reinterpret_cast<int4 *>(optr);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) dst[t] = make_int4(o[4 * t], o[4 * t + 1], o[4 * t + 2], o[4 * t + 3]);
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+            if (q < cx.nvalid) {
+                if (OUT == FPCC_OUT_I8) ((int8_t *)optr)[q] = (int8_t)o[q];
+                else if (OUT == FPCC_OUT_I16) ((int16_t *)optr)[q] = (int16_t)o[q];
+                else ((int32_t *)optr)[q] = o[q];
+            }
+        }
+    }
+}
+
+template <int OUT>
+__device__ __forceinline__ void epi_dispatch(const uint32_t (&acc)[32], const EpiCtx &cx, void *optr, bool vec, bool slope, bool rb) {
+    if (slope) { if (rb) epi_chunk<OUT, true, true>(acc, cx, optr, vec); else epi_chunk<OUT, true, false>(acc, cx, optr, vec); }
+    else { if (rb) epi_chunk<OUT, false, true>(acc, cx, optr, vec); else epi_chunk<OUT, false, false>(acc, cx, optr, vec); }
+}
+
 constexpr int P_THREADS = 448;
 constexpr int P_EPI_WARPS = 8;
 constexpr int P_PROD_WARP0 = 8;
@@ -364,6 +444,15 @@ __global__ void __launch_bounds__(P_THREADS, 1) igemm_tc_persistent(TcArgs a, co
             mbar_wait(&meta_full[slot], (j >> 1) & 1);
             const bool have_acc = meta[slot].kmask != 0;
             const int pbase = (MODE == 1 && a.bias_per_group) ? meta[slot].group * a.N : 0;
+            if (!chan_static) {  // grouped weights / several channel blocks: restage (bias, mul) of this tile's block
+                asm volatile("bar.sync 2, 256;" ::: "memory");  // every epilogue warp is done with the previous tile's values
+                const int t = warp * 32 + lane;
+                if (t < a.n_tile) {
+                    const int pc = pbase + min(n0 + t, a.N - 1);
+                    chan_s[t] = make_int2(ep.bias ? __ldg(&ep.bias[pc]) : 0, (int)__ldg(&ep.mul[ep.mul_is_scalar ? 0 : pc]));
+                }
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+            }
             const int32_t *rows = rows_s + slot * rows_k * TC_M;
             const int64_t m = MODE == 0 ? (int64_t)tile_m * TC_M + r : (int64_t)rows[TC_M + r];
             const bool row_ok = MODE == 0 ? (m < a.n_out) : (m >= 0);
@@ -381,74 +470,20 @@ __global__ void __launch_bounds__(P_THREADS, 1) igemm_tc_persistent(TcArgs a, co
                 const int nb = n0 + c0;
                 if (!row_ok || nb >= a.N) continue;
                 if (a.dbg & 4) { if (c0 == 0) ((int32_t *)out)[m] = (int32_t)acc[0]; continue; }
-                const int64_t obase = m * a.N + nb;
-                const bool full32 = nb + 32 <= a.N;
-                if (ep.row_bias) {  // occupancy-indexed bias row (the 8 bit channels of cat(F, bin << 23) folded away)
-                    const int32_t *rb = ep.row_bias + (int64_t)__ldg(&ep.row_idx[m]) * a.N + nb;
-#pragma unroll
-                    for (int q = 0; q < 32; ++q)
-                        if (nb + q < a.N) acc[q] += (uint32_t)__ldg(&rb[q]);
-                }
-                int32_t o32[32];
-#pragma unroll
-                for (int q = 0; q < 32; ++q) {
-                    int2 bm;
-                    if (chan_static) bm = chan_s[c0 + q];
-                    else {
-                        const int pc = min(pbase + nb + q, pbase + a.N - 1);
-                        bm = make_int2(ep.bias ? __ldg(&ep.bias[pc]) : 0, (int)__ldg(&ep.mul[ep.mul_is_scalar ? 0 : pc]));
-                    }
-                    int64_t v = (int64_t)(int32_t)acc[q] + (int64_t)bm.x;
-                    if (has_slope) {
-                        const int64_t t = rha_shift(v * (int64_t)slope, 25);
-                        v = v < 0 ? t : v;
-                    }
-                    const int64_t o = rha_shift(v * (int64_t)(uint32_t)bm.y + zp, shift);
-                    if (ep.out_type == FPCC_OUT_I8) o32[q] = (int32_t)(o < -128 ? -128 : (o > 127 ? 127 : o));
-                    else if (ep.out_type == FPCC_OUT_I16) o32[q] = (int32_t)(o < -32768 ? -32768 : (o > 32767 ? 32767 : o));
-                    else o32[q] = clamp_i32(o);
-                }
-                if (ep.out_type == FPCC_OUT_I8 && full32 && (a.N & 15) == 0) {
-                    uint32_t pk[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        pk[q] = (uint32_t)(o32[4 * q] & 0xff) | ((uint32_t)(o32[4 * q + 1] & 0xff) << 8) |
-                                ((uint32_t)(o32[4 * q + 2] & 0xff) << 16) | ((uint32_t)(o32[4 * q + 3] & 0xff) << 24);
-                    uint4 *dst = reinterpret_cast<uint4 *>((int8_t *)out + obase);
-                    dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                    dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                } else if (ep.out_type == FPCC_OUT_I32 && full32 && (a.N & 3) == 0) {
-                    int4 *dst = reinterpret_cast<int4 *>((int32_t *)out + obase);
-                    const int4 *res = ep.residual ? reinterpret_cast<const int4 *>(ep.residual + obase) : nullptr;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        int4 v = make_int4(o32[4 * q], o32[4 * q + 1], o32[4 * q + 2], o32[4 * q + 3]);
-                        if (res) {
-                            const int4 rr = __ldg(&res[q]);
-                            v.x = (int32_t)((uint32_t)v.x + (uint32_t)rr.x); v.y = (int32_t)((uint32_t)v.y + (uint32_t)rr.y);
-                            v.z = (int32_t)((uint32_t)v.z + (uint32_t)rr.z); v.w = (int32_t)((uint32_t)v.w + (uint32_t)rr.w);
-                            if (has_post) {
-                                v.x = clamp_i32(prelu_q25(v.x, post)); v.y = clamp_i32(prelu_q25(v.y, post));
-                                v.z = clamp_i32(prelu_q25(v.z, post)); v.w = clamp_i32(prelu_q25(v.w, post));
-                            }
-                        }
-                        dst[q] = v;
-                    }
-                } else {
-                    for (int q = 0; q < 32 && nb + q < a.N; ++q) {
-                        const int64_t idx = obase + q;
-                        if (ep.out_type == FPCC_OUT_I8) ((int8_t *)out)[idx] = (int8_t)o32[q];
-                        else if (ep.out_type == FPCC_OUT_I16) ((int16_t *)out)[idx] = (int16_t)o32[q];
-                        else {
-                            int32_t rv = o32[q];
-                            if (ep.residual) {
-                                rv = (int32_t)((uint32_t)rv + (uint32_t)ep.residual[idx]);
-                                if (has_post) rv = clamp_i32(prelu_q25((int64_t)rv, post));
-                            }
-                            ((int32_t *)out)[idx] = rv;
-                        }
-                    }
-                }
+                EpiCtx cx;
+                cx.chan = chan_s + c0;
+                cx.slope = slope; cx.post = post; cx.zp = zp; cx.shift = shift;
+                cx.half = shift > 0 ? (int64_t)1 << (shift - 1) : 0; cx.sgn = shift > 0;
+                cx.row_bias = ep.row_bias ? ep.row_bias + (int64_t)__ldg(&ep.row_idx[m]) * a.N + nb : nullptr;
+                cx.residual = ep.residual ? ep.residual + m * a.N + nb : nullptr;
+                cx.has_post = has_post;
+                cx.nvalid = min(32, a.N - nb);
+                void *optr = (char *)out + (m * a.N + nb) * (ep.out_type == FPCC_OUT_I8 ? 1 : (ep.out_type == FPCC_OUT_I16 ? 2 : 4));
+                const bool vec = cx.nvalid == 32 && (a.N & 15) == 0;
+                const bool rb = ep.row_bias != nullptr;
+                if (ep.out_type == FPCC_OUT_I8) epi_dispatch<FPCC_OUT_I8>(acc, cx, optr, vec, has_slope, rb);
+                else if (ep.out_type == FPCC_OUT_I32) epi_dispatch<FPCC_OUT_I32>(acc, cx, optr, vec, has_slope, rb);
+                else epi_dispatch<FPCC_OUT_I16>(acc, cx, optr, false, has_slope, rb);
             }
             tc_fence_before();
             __syncwarp();
@@ -506,6 +541,7 @@ __global__ void __launch_bounds__(128, 1) mma_i8_peak_kernel(int iters, int n) {
 // host side
 // ---------------------------------------------------------------------------------------------
 static int g_tc_mode = -1;  // -1: read FPCC_TC from the environment on first use
+static int g_sm_budget = 0;  // persistent GEMM grids use at most this many SMs (0 = all)
 
 bool tc_enabled() {
     if (g_tc_mode < 0) {
@@ -585,7 +621,8 @@ static int launch_tc(TcArgs &a, const int8_t *W, int64_t w_rows, int tiles_m, co
         configured = true;
     }
     int total = tiles_m * n_blocks_n;
-    int grid = total < sm_count() ? total : sm_count();
+    int sms = g_sm_budget > 0 && g_sm_budget < sm_count() ? g_sm_budget : sm_count();
+    int grid = total < sms ? total : sms;
     kern<<<grid, P_THREADS, smem, s>>>(a, tmap, ep, out, tiles_m, n_blocks_n);
     FPCC_LAUNCH_CHECK();
     return FPCC_OK;
@@ -639,6 +676,11 @@ extern "C" int fpcc_mma_i8_peak(int iters, int n, double *tops_out, void *stream
 
 extern "C" int fpcc_gemm_engine(int k, int n, int kvol, int has_zp_comp) {
     return fpcc::tc_enabled() && !has_zp_comp && k >= 32 && k % 16 == 0 && n >= 16 && kvol <= fpcc::TC_MAX_KVOL;
+}
+
+extern "C" int fpcc_set_sm_budget(int sms) {
+    fpcc::g_sm_budget = sms > 0 ? sms : 0;
+    return FPCC_OK;
 }
 
 extern "C" int fpcc_set_tc_mode(int mode) {

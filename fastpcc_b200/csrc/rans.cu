@@ -529,24 +529,22 @@ using namespace fpcc;
 
 extern "C" int fpcc_rans_encode(const uint32_t *ranges, const uint8_t *bits, const int64_t *rng_off, int n_streams,
                                 int64_t total_entries, uint8_t *out, int64_t out_stride, int32_t *out_len,
-                                uint32_t *state_io, int do_flush, void *stream) {
+                                uint32_t *state_io, int do_flush, void *workspace, size_t workspace_bytes, void *stream) {
     FPCC_REQUIRE(rng_off && out && out_len, "rans_encode: NULL pointer");
     FPCC_REQUIRE(n_streams > 0 && out_stride >= 16 && total_entries >= 0, "rans_encode: bad sizes");
     FPCC_REQUIRE(total_entries == 0 || ranges, "rans_encode: NULL ranges");
     FPCC_REQUIRE(do_flush || state_io, "rans_encode: an open (unflushed) stream needs state_io");
+    FPCC_REQUIRE(total_entries == 0 || (workspace && workspace_bytes >= (size_t)total_entries * sizeof(uint4) &&
+                                        ((uintptr_t)workspace & 15) == 0),
+                 "rans_encode: workspace must hold 16 bytes per entry (16-byte aligned)");
     cudaStream_t s = (cudaStream_t)stream;
-    uint4 *recs = nullptr;
+    uint4 *recs = (uint4 *)workspace;
     if (total_entries > 0) {
-        FPCC_CUDA(cudaMallocAsync((void **)&recs, (size_t)total_entries * sizeof(uint4), s));
         enc_prepare_kernel<<<ceil_div(total_entries, 256), 256, 0, s>>>(ranges, bits, total_entries, recs);
+        FPCC_LAUNCH_CHECK();
     }
     rans_encode_kernel<<<n_streams, 32, 0, s>>>(recs, rng_off, out, out_stride, out_len, state_io, do_flush);
-    cudaError_t le = cudaGetLastError();
-    if (recs) cudaFreeAsync(recs, s);
-    if (le != cudaSuccess) {
-        fpcc::set_error("rans_encode: kernel launch failed: %s", cudaGetErrorString(le));
-        return FPCC_ERR_CUDA;
-    }
+    FPCC_LAUNCH_CHECK();
     return FPCC_OK;
 }
 

@@ -39,6 +39,32 @@ class Config:
     skip_top_scales_num: int = 0
 
 
+class _Trace:
+    """FPCC_TRACE=1: synchronising wall-clock marks of the codec phases (diagnostics only)."""
+
+    def __init__(self):
+        import os
+        self.on = os.environ.get('FPCC_TRACE', '0') == '1'
+        self.t = None
+        self.rows = []
+
+    def mark(self, name):
+        if not self.on:
+            return
+        import time
+        torch.cuda.synchronize()
+        now = time.perf_counter()
+        if self.t is not None:
+            self.rows.append((name, 1e3 * (now - self.t)))
+        self.t = now
+
+    def dump(self, title):
+        if self.on and self.rows:
+            import sys
+            sys.stderr.write(f'[trace] {title}: ' + ', '.join(f'{n} {ms:.1f}' for n, ms in self.rows) + '\n')
+        self.rows, self.t = [], None
+
+
 class SparseSequential(nn.Sequential):
     """model.py:524-534; `sel`/`n_out_rows` are forwarded to the LAST linear (occupied-children form)."""
 
@@ -286,12 +312,66 @@ class Model(nn.Module):
     # ---- compress ---------------------------------------------------------------------------
     MAX_CDF = 130  # bottom-coordinate alphabet: the stream stores len(cdf)-2 <= 128 (model.py:371)
 
+    def _run_groups(self, fn, items: list, n_groups: int) -> list:
+        """Runs `fn` on `n_groups` contiguous slices of `items`, each in its own thread and CUDA stream, so that the
+        serial range-coder kernels of one group overlap the tensor-core kernels of another.  Order is preserved."""
+        n_groups = max(1, min(n_groups, len(items)))
+        if n_groups == 1:
+            return fn(items)
+        import threading
+        bounds = [len(items) * g // n_groups for g in range(n_groups + 1)]
+        out: list = [None] * n_groups
+        err: list = []
+        cur = torch.cuda.current_stream(self.device)
+
+        def work(g):
+            try:
+                s = self._side_streams[g]
+                s.wait_stream(cur)
+                with torch.cuda.stream(s):
+                    out[g] = fn(items[bounds[g]: bounds[g + 1]])
+                    s.synchronize()
+            except BaseException as e:  # re-raised on the caller's thread
+                err.append(e)
+
+        if not hasattr(self, '_side_streams') or len(self._side_streams) < n_groups:
+            self._side_streams = [torch.cuda.Stream(self.device) for _ in range(n_groups)]
+        import sys
+        from .. import _lib
+        old_interval = sys.getswitchinterval()
+        sys.setswitchinterval(1e-4)  # the groups interleave thousands of short launches: hand the GIL over quickly
+        # leave one SM per concurrently coded stream of the other groups to the serial range-coder kernels
+        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        _lib.load().fpcc_set_sm_budget(max(sms // 2, sms - (len(items) - len(items) // n_groups)))
+        try:
+            threads = [threading.Thread(target=work, args=(g,)) for g in range(n_groups)]
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join()
+        finally:
+            sys.setswitchinterval(old_interval)
+            _lib.load().fpcc_set_sm_budget(0)
+        if err:
+            raise err[0]
+        return [x for part in out for x in part]
+
+    def compress_batch(self, frames: List[torch.Tensor], n_groups: int = 1) -> List[bytes]:
+        """Compresses independent frames together (see `_compress_group`); `n_groups` > 1 codes that many slices of
+        the batch concurrently on separate CUDA streams."""
+        return self._run_groups(self._compress_group, list(frames), n_groups)
+
+    def decompress_batch(self, streams: List[bytes], n_groups: int = 1) -> List[torch.Tensor]:
+        return self._run_groups(self._decompress_group, list(streams), n_groups)
+
     @torch.no_grad()
-    def compress_batch(self, frames: List[torch.Tensor]) -> List[bytes]:
-        """Compresses independent frames together: one pass of every kernel over the concatenated nodes (the
-        batch index is part of every coordinate key), one rANS stream per frame, all streams coded
-        concurrently.  Each returned bitstream is byte-identical to `compress(frame)` of the reference."""
+    def _compress_group(self, frames: List[torch.Tensor]) -> List[bytes]:
+        """One pass of every kernel over the concatenated nodes of all frames (the batch index is part of every
+        coordinate key), one rANS stream per frame, all streams coded concurrently.  Each returned bitstream is
+        byte-identical to `compress(frame)` of the reference."""
         dev, B, L = self.device, len(frames), self._num_levels()
+        tr = _Trace()
+        tr.mark('start')
         offs, parts = [], []
         for b, xyz in enumerate(frames):
             assert xyz.dtype == torch.int32 and xyz.dim() == 2 and xyz.shape[1] == 4
@@ -303,7 +383,9 @@ class Model(nn.Module):
             offs.append(off)
             parts.append(xyz)
         xyz = torch.cat(parts).contiguous()
+        tr.mark('sort')
         levels = self.build_pyramid(xyz)
+        tr.mark('pyramid')
 
         # ---- bottom coordinates and their per-frame histogram CDF (model.py:407-415), vectorised over frames
         V = self.MAX_CDF
@@ -329,6 +411,7 @@ class Model(nn.Module):
         e_cdf_all = ops.table_symbol_ranges(self.fea_side_info_cdf1, cdf_vals.clamp(min=0).contiguous()).view(B, V)
         e_len = ops.table_symbol_ranges(self.fea_side_info_cdf2, (n_cdf - 2).to(torch.int32).contiguous())
 
+        tr.mark('bottom')
         # ---- network, coarse -> fine; per coded level the packed (start, freq) of every node's symbol
         cur = SparseTensor(torch.ones((levels[L].n, 1), dtype=torch.int8, device=dev), levels[L].C, (2 ** L,) * 3)
         seg = []
@@ -347,6 +430,7 @@ class Model(nn.Module):
 
         # ---- per-frame streams, entries in DECODE order: cdf length, cdf values, bottom coords, levels coarse ->
         # fine (the encoder pushes the exact reverse: model.py:442-445 and :367-375).  Assembled on the device.
+        tr.mark('network')
         lvl_rows = [self._frame_rows(lv.C, B) for lv, _ in seg]           # [B+1] each
         per_frame = 1 + (n_cdf - 1) + n_sym + sum((r[1:] - r[:-1]) for r in lvl_rows)
         start = torch.cumsum(per_frame, 0) - per_frame                     # stream start of every frame
@@ -366,8 +450,10 @@ class Model(nn.Module):
             base = base + (rows[1:] - rows[:-1])
         rng_off = torch.cat([start, (start[-1] + per_frame[-1])[None]]).contiguous()
         cap = (2 * int(per_frame.max().item()) + 64 + 3) & ~3  # <= 2 bytes per entry + the 4-byte state header
+        tr.mark('assemble')
         out, out_len = ops.rans_encode(ranges, rng_off, cap)
         lens = out_len.tolist()
+        tr.mark('rans')
         heads = torch.cat([torch.stack(offs).long(), (n_sym // 3)[:, None]], 1).tolist()
         out_h = out.cpu().numpy()
         result = []
@@ -375,6 +461,8 @@ class Model(nn.Module):
             assert lens[b] > 0, 'rANS output buffer overflow'
             head = b''.join(int(v).to_bytes(2, 'little') for v in heads[b])
             result.append(head + out_h[b, cap - lens[b]:].tobytes())
+        tr.mark('d2h')
+        tr.dump(f'compress B={B}')
         return result
 
     def compress(self, xyz: torch.Tensor) -> bytes:
@@ -386,7 +474,7 @@ class Model(nn.Module):
 
     # ---- decompress -------------------------------------------------------------------------
     @torch.no_grad()
-    def decompress_batch(self, streams: List[bytes]) -> List[torch.Tensor]:
+    def _decompress_group(self, streams: List[bytes]) -> List[torch.Tensor]:
         dev, B, L, V = self.device, len(streams), self._num_levels(), self.MAX_CDF
         heads = np.array([[int.from_bytes(s[2 * i: 2 * i + 2], 'little') for i in range(4)] for s in streams], dtype=np.int64)
         coord_offset = torch.from_numpy(heads[:, :3].astype(np.int32)).to(dev)

@@ -96,8 +96,8 @@ _ws_cache = {}
 
 
 def workspace(nbytes, device):
-    """Grow-only scratch buffer per device (kernels on one stream run in order, so reuse is safe)."""
-    key = (device.index if device.index is not None else torch.cuda.current_device())
+    """Grow-only scratch buffer per (device, stream): kernels on one stream run in order, so reuse is safe."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), _s())
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
@@ -403,8 +403,9 @@ def rans_encode(ranges, rng_off, out_stride, bits=None, out=None, state_io=None,
         out = torch.empty((ns, out_stride), dtype=torch.uint8, device=ranges.device)
     out_len = torch.empty(ns, dtype=torch.int32, device=ranges.device)
     total = ranges.numel() if total is None else int(total)
+    ws = workspace(16 * max(total, 1), ranges.device)
     _call('fpcc_rans_encode', _p(ranges), _p(bits), _p(rng_off), ns, total, _p(out), out_stride, _p(out_len),
-          _p(state_io), 1 if flush else 0, _s())
+          _p(state_io), 1 if flush else 0, _p(ws), ws.numel(), _s())
     return out, out_len
 
 

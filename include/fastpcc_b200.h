@@ -180,6 +180,9 @@ int fpcc_slot_table(const int32_t *child_parent, const uint8_t *child_slot, int 
  * wherever the shape allows (C_in % 16 == 0, C_in >= 32, C_out >= 16, kernel volume <= 32), 0 = the CUDA-core
  * (dp4a) kernels for every shape.  Both produce identical integers; the switch exists for A/B verification. */
 int fpcc_set_tc_mode(int mode);
+/* Persistent GEMM kernels occupy one whole SM per CTA.  When serial range-coder kernels of another CUDA stream
+ * should run beside them, cap the GEMM grids at `sms` SMs (0 = all SMs) so that the coder blocks find free SMs. */
+int fpcc_set_sm_budget(int sms);
 /* Measures the kind::i8 tensor-pipe ceiling of the current device: every SM issues `iters` x 4 back-to-back
  * tcgen05.mma (M=128, N=n, K=32) on resident shared-memory tiles.  Synchronises.  *tops_out = int8 TOP/s. */
 int fpcc_mma_i8_peak(int iters, int n, double *tops_out, void *stream);
@@ -226,7 +229,7 @@ int fpcc_table_symbol_ranges(const uint16_t *cdf, int64_t n_cdf, int s, const in
 int fpcc_rans_encode(const uint32_t *ranges, const uint8_t *bits, const int64_t *rng_off, int n_streams,
                      int64_t total_entries /* = rng_off[n_streams], as a host value */,
                      uint8_t *out, int64_t out_stride, int32_t *out_len, uint32_t *state_io, int do_flush,
-                     void *stream);
+                     void *workspace, size_t workspace_bytes /* >= 16 * total_entries */, void *stream);
 
 /* Decoder state of one stream (device resident, 16 bytes) */
 typedef struct {
