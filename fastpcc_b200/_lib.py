@@ -26,7 +26,7 @@ SIGNATURES = {
     'fpcc_version': (_i, []),
     'fpcc_device_check': (_i, [_vp, _vp, _vp]),
     'fpcc_hash_insert_coords': (_i, [_vp, _vp, _i, _vp, _i, _i, _vp]),
-    'fpcc_kmap_lookup': (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i64, _vp]),
+    'fpcc_kmap_lookup': (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i64, _vp]),
     'fpcc_kmap_compact_workspace': (_sz, [_i, _i]),
     'fpcc_kmap_compact': (_i, [_vp, _i, _i, _i64, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     'fpcc_scan_workspace': (_sz, [_i]),
@@ -42,6 +42,8 @@ SIGNATURES = {
     'fpcc_prelu_i32': (_i, [_vp, _i64, _vp, _vp, _vp]),
     'fpcc_spconv_i8': (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _i64, _i, _vp, _EP, _vp, _vp]),
     'fpcc_linear_i8': (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _EP, _vp, _vp]),
+    'fpcc_spconv_f16': (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp, _i64, _i, _vp, _i, C.c_float, _vp, _i, C.c_float, _vp, _i, _vp]),
+    'fpcc_linear_f16': (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _i, C.c_float, _vp, _i, C.c_float, _vp, _i, _vp]),
     'fpcc_set_tc_mode': (_i, [_i]),
     'fpcc_set_sm_budget': (_i, [_i]),
     'fpcc_mma_i8_peak': (_i, [_i, _i, _vp, _vp]),

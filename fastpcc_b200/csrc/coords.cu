@@ -56,13 +56,20 @@ struct KernelGeom {
     int ks[3];
     int st[3];
     int kvol;
+    int me;  // 1: MinkowskiEngine convention (absolute coordinates, x fastest, even kernels 0..k-1, offsets scaled by st)
 };
 
 // offset of kernel index k along each axis, in the reference's enumeration order
 // (hashmap_cuda.cuh:239-258): odd volume -> x fastest, even volume -> z fastest.
 __device__ __forceinline__ void kernel_offset(const KernelGeom &g, int k, int &dx, int &dy, int &dz) {
     int d[3];
-    if (g.kvol & 1) {
+    if (g.me) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            d[a] = (k % g.ks[a] - ((g.ks[a] & 1) ? (g.ks[a] - 1) / 2 : 0)) * g.st[a];
+            k /= g.ks[a];
+        }
+    } else if (g.kvol & 1) {
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
             d[a] = k % g.ks[a] - (g.ks[a] - 1) / 2;
@@ -90,7 +97,9 @@ __global__ void __launch_bounds__(256) kmap_lookup_kernel(const unsigned long lo
     int dx, dy, dz;
     kernel_offset(g, k, dx, dy, dz);
     int4 c = load_bxyz(out_coords, o, layout);
-    int x = c.y * g.st[0] + dx, y = c.z * g.st[1] + dy, z = c.w * g.st[2] + dz;
+    int x, y, z;
+    if (g.me) { x = c.y + dx; y = c.z + dy; z = c.w + dz; }
+    else { x = c.y * g.st[0] + dx; y = c.z * g.st[1] + dy; z = c.w * g.st[2] + dz; }
     int32_t v = 0;
     if (coord_in_range(c.x, x, y, z)) v = hash_find(keys, vals, capacity, pack_key(c.x, x, y, z));
     if (k_major) table[(int64_t)k * ld + o] = v;
@@ -272,7 +281,7 @@ extern "C" int fpcc_hash_insert_coords(int64_t *keys, int32_t *vals, int capacit
 }
 
 extern "C" int fpcc_kmap_lookup(const int64_t *keys, const int32_t *vals, int capacity, const int32_t *out_coords,
-                                int n_out, int layout, int ksx, int ksy, int ksz, int sx, int sy, int sz,
+                                int n_out, int layout, int ksx, int ksy, int ksz, int sx, int sy, int sz, int convention,
                                 int32_t *table, int k_major, int64_t ld, void *stream) {
     FPCC_REQUIRE(keys && vals && out_coords && table, "kmap_lookup: NULL pointer");
     FPCC_REQUIRE(ksx > 0 && ksy > 0 && ksz > 0 && sx > 0 && sy > 0 && sz > 0, "kmap_lookup: bad kernel geometry");
@@ -284,6 +293,8 @@ extern "C" int fpcc_kmap_lookup(const int64_t *keys, const int32_t *vals, int ca
     g.ks[0] = ksx; g.ks[1] = ksy; g.ks[2] = ksz;
     g.st[0] = sx; g.st[1] = sy; g.st[2] = sz;
     g.kvol = ksx * ksy * ksz;
+    g.me = convention == 1;
+    FPCC_REQUIRE(convention == 0 || convention == 1, "kmap_lookup: unknown convention");
     FPCC_REQUIRE(g.kvol <= 65535, "kmap_lookup: kernel volume too large");
     dim3 grid(ceil_div(n_out, 256), g.kvol);
     kmap_lookup_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const unsigned long long *)keys, vals, (uint32_t)capacity,

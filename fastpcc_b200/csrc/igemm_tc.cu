@@ -24,6 +24,8 @@
 // mma.sync m16n8k32, one launch per kernel offset, read-modify-write of D per offset) plus the separate
 // element-wise epilogue kernels of src/element_wise/*.cu.
 #include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <map>
 #include <mutex>
@@ -91,6 +93,18 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // kind::i8 instruction descriptor: D = s32, A = B = s8, both K-major, M = 128, N = n
 __device__ __forceinline__ uint32_t umma_idesc_i8(int n) {
     return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+}
+// kind::f16 instruction descriptor: D = f32, A = B = f16 (fmt 0) or bf16 (fmt 1), K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t umma_idesc_f16(int n, int bf16) {
+    return (1u << 4) | ((uint32_t)bf16 << 7) | ((uint32_t)bf16 << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -225,6 +239,59 @@ __device__ __forceinline__ void epi_dispatch(const uint32_t (&acc)[32], const Ep
     else { if (rb) epi_chunk<OUT, false, true>(acc, cx, optr, vec); else epi_chunk<OUT, false, false>(acc, cx, optr, vec); }
 }
 
+// ---- floating-point epilogue (kind::f16 path): v = acc + bias; act; [+ residual; post act]; cast -------------
+// act codes: 0 none, 1 relu, 2 leaky-relu / PReLU with one slope.  out_type: 0 fp16, 1 bf16, 2 fp32.
+struct FEpi {
+    const float *bias;      // [N] or NULL
+    const void *residual;   // [rows, N] in the OUTPUT dtype, or NULL
+    float slope, post_slope;
+    int act, post_act, out_type;
+};
+__device__ __forceinline__ float f_act(float v, int act, float slope) {
+    return act == 1 ? fmaxf(v, 0.f) : (act == 2 ? (v < 0.f ? v * slope : v) : v);
+}
+__device__ __forceinline__ float f_load(const void *p, int64_t i, int t) {
+    return t == 0 ? __half2float(((const __half *)p)[i]) : (t == 1 ? __bfloat162float(((const __nv_bfloat16 *)p)[i]) : ((const float *)p)[i]);
+}
+__device__ __forceinline__ void epi_chunk_f(const uint32_t (&acc)[32], const int2 *chan, const FEpi &fe, const void *res,
+                                            void *optr, int nvalid, bool vec) {
+    float o[32];
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+        float v = __uint_as_float(acc[q]) + __int_as_float(chan[q].x);
+        v = f_act(v, fe.act, fe.slope);
+        if (res) v += f_load(res, q < nvalid ? q : 0, fe.out_type);
+        o[q] = f_act(v, fe.post_act, fe.post_slope);
+    }
+    if (vec && fe.out_type != 2) {
+        uint4 *dst = reinterpret_cast<uint4 *>(optr);
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            uint32_t w[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int q = h * 8 + t * 2;
+                if (fe.out_type == 0) { __half2 hv = __floats2half2_rn(o[q], o[q + 1]); w[t] = *reinterpret_cast<uint32_t *>(&hv); }
+                else { __nv_bfloat162 bv = __floats2bfloat162_rn(o[q], o[q + 1]); w[t] = *reinterpret_cast<uint32_t *>(&bv); }
+            }
+            dst[h] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    } else if (vec) {
+        float4 *dst = reinterpret_cast<float4 *>(optr);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) dst[t] = make_float4(o[4 * t], o[4 * t + 1], o[4 * t + 2], o[4 * t + 3]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+            if (q < nvalid) {
+                if (fe.out_type == 0) ((__half *)optr)[q] = __float2half_rn(o[q]);
+                else if (fe.out_type == 1) ((__nv_bfloat16 *)optr)[q] = __float2bfloat16_rn(o[q]);
+                else ((float *)optr)[q] = o[q];
+            }
+        }
+    }
+}
+
 constexpr int P_THREADS = 448;
 constexpr int P_EPI_WARPS = 8;
 constexpr int P_PROD_WARP0 = 8;
@@ -257,9 +324,11 @@ __device__ __forceinline__ void pairs_tile_lookup(const TcArgs &a, int tile_m, P
     m->group = g; m->begin = begin; m->end = end;
 }
 
-template <int MODE, int STAGES>
+// KIND: 0 = int8 x int8 -> int32 (kind::i8, integer requant epilogue), 1 = fp16, 2 = bf16 (kind::f16, fp32
+// accumulation, floating-point epilogue).  a.K is the contraction length in BYTES in every case.
+template <int MODE, int STAGES, int KIND>
 __global__ void __launch_bounds__(P_THREADS, 1) igemm_tc_persistent(TcArgs a, const __grid_constant__ CUtensorMap tmap_w,
-                                                                    EpiParams ep, void *__restrict__ out, int tiles_m,
+                                                                    EpiParams ep, FEpi fe, void *__restrict__ out, int tiles_m,
                                                                     int tiles_n) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -300,8 +369,10 @@ __global__ void __launch_bounds__(P_THREADS, 1) igemm_tc_persistent(TcArgs a, co
     // per-channel epilogue constants of a single channel block are staged once (grouped weights reload per tile)
     const bool chan_static = tiles_n == 1 && !(MODE == 1 && a.bias_per_group);
     if (chan_static)
-        for (int c = tid; c < a.n_tile; c += P_THREADS)
-            chan_s[c] = c < a.N ? make_int2(ep.bias ? ep.bias[c] : 0, (int)ep.mul[ep.mul_is_scalar ? 0 : c]) : make_int2(0, 0);
+        for (int c = tid; c < a.n_tile; c += P_THREADS) {
+            if (KIND == 0) chan_s[c] = c < a.N ? make_int2(ep.bias ? ep.bias[c] : 0, (int)ep.mul[ep.mul_is_scalar ? 0 : c]) : make_int2(0, 0);
+            else chan_s[c] = make_int2(c < a.N && fe.bias ? __float_as_int(fe.bias[c]) : 0, 0);
+        }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -401,7 +472,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) igemm_tc_persistent(TcArgs a, co
     } else if (warp == 13) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_i8(a.n_tile);
+            const uint32_t idesc = KIND == 0 ? umma_idesc_i8(a.n_tile) : umma_idesc_f16(a.n_tile, KIND == 2);
             int it = 0, j = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
                 const int slot = j & 1;
@@ -418,8 +489,10 @@ __global__ void __launch_bounds__(P_THREADS, 1) igemm_tc_persistent(TcArgs a, co
                     const uint64_t bd = umma_desc_sw128(smem_u32(sB + (size_t)stage * b_bytes));
                     if (!(a.dbg & 8)) {
 #pragma unroll
-                        for (int q = 0; q < TC_KB / 32; ++q)
-                            umma_i8(tacc, ad + 2 * q, bd + 2 * q, idesc, (uint32_t)(i > 0 || q > 0));
+                        for (int q = 0; q < TC_KB / 32; ++q) {  // 32 bytes of K per instruction for both kinds
+                            if (KIND == 0) umma_i8(tacc, ad + 2 * q, bd + 2 * q, idesc, (uint32_t)(i > 0 || q > 0));
+                            else umma_f16(tacc, ad + 2 * q, bd + 2 * q, idesc, (uint32_t)(i > 0 || q > 0));
+                        }
                     }
                     umma_commit(&empty[stage]);
                 }
@@ -431,9 +504,9 @@ __global__ void __launch_bounds__(P_THREADS, 1) igemm_tc_persistent(TcArgs a, co
         // ================= epilogue =================
         const int quarter = warp & 3, half = warp >> 2;
         const int r = quarter * 32 + lane;  // tile row == TMEM lane
-        const bool has_slope = ep.slope != nullptr, has_post = ep.post_slope != nullptr;
+        const bool has_slope = KIND == 0 && ep.slope != nullptr, has_post = KIND == 0 && ep.post_slope != nullptr;
         const int32_t slope = has_slope ? ep.slope[0] : 0, post = has_post ? ep.post_slope[0] : 0;
-        const int64_t zp = ep.zp[0];
+        const int64_t zp = KIND == 0 ? ep.zp[0] : 0;
         const int shift = ep.shift;
         const int cols_half = ((a.n_tile / 2 + 31) / 32) * 32;  // columns per half, multiple of 32
         const int c_begin = half * cols_half, c_end = min(a.n_tile, c_begin + cols_half);
@@ -449,7 +522,8 @@ __global__ void __launch_bounds__(P_THREADS, 1) igemm_tc_persistent(TcArgs a, co
                 const int t = warp * 32 + lane;
                 if (t < a.n_tile) {
                     const int pc = pbase + min(n0 + t, a.N - 1);
-                    chan_s[t] = make_int2(ep.bias ? __ldg(&ep.bias[pc]) : 0, (int)__ldg(&ep.mul[ep.mul_is_scalar ? 0 : pc]));
+                    if (KIND == 0) chan_s[t] = make_int2(ep.bias ? __ldg(&ep.bias[pc]) : 0, (int)__ldg(&ep.mul[ep.mul_is_scalar ? 0 : pc]));
+                    else chan_s[t] = make_int2(fe.bias ? __float_as_int(__ldg(&fe.bias[pc])) : 0, 0);
                 }
                 asm volatile("bar.sync 2, 256;" ::: "memory");
             }
@@ -470,6 +544,14 @@ __global__ void __launch_bounds__(P_THREADS, 1) igemm_tc_persistent(TcArgs a, co
                 const int nb = n0 + c0;
                 if (!row_ok || nb >= a.N) continue;
                 if (a.dbg & 4) { if (c0 == 0) ((int32_t *)out)[m] = (int32_t)acc[0]; continue; }
+                if (KIND != 0) {
+                    const int esz = fe.out_type == 2 ? 4 : 2;
+                    const int nvalid = min(32, a.N - nb);
+                    const void *res = fe.residual ? (const char *)fe.residual + (m * a.N + nb) * esz : nullptr;
+                    epi_chunk_f(acc, chan_s + c0, fe, res, (char *)out + (m * a.N + nb) * esz, nvalid,
+                                nvalid == 32 && (a.N & 7) == 0);
+                    continue;
+                }
                 EpiCtx cx;
                 cx.chan = chan_s + c0;
                 cx.slope = slope; cx.post = post; cx.zp = zp; cx.shift = shift;
@@ -603,18 +685,19 @@ static int pick_tile(int N, int *n_tile, int *tmem_cols) {
     return (N + nt - 1) / nt;
 }
 
-template <int MODE>
-static int launch_tc(TcArgs &a, const int8_t *W, int64_t w_rows, int tiles_m, const EpiParams &ep, void *out, cudaStream_t s) {
+template <int MODE, int KIND>
+static int launch_tc(TcArgs &a, const void *W, int64_t w_rows, int tiles_m, const EpiParams &ep, const FEpi &fe, void *out,
+                     cudaStream_t s) {
     int n_blocks_n = pick_tile(a.N, &a.n_tile, &a.tmem_cols);
     { const char *e = getenv("FPCC_TC_DEBUG"); a.dbg = e ? atoi(e) : 0; }
     CUtensorMap tmap;
-    int rc = weight_tensor_map(W, w_rows, a.K, a.n_tile, &tmap);
+    int rc = weight_tensor_map((const int8_t *)W, w_rows, a.K, a.n_tile, &tmap);
     if (rc) return rc;
     constexpr int STAGES = 4;
     const int rows_k = MODE == 0 ? a.kvol : 2;
     size_t smem = PSmem<STAGES>::bytes(a.n_tile, rows_k);
     FPCC_REQUIRE(smem <= 227 * 1024, "igemm_tc: %zu bytes of shared memory exceed the 227 KB limit", smem);
-    auto kern = igemm_tc_persistent<MODE, STAGES>;
+    auto kern = igemm_tc_persistent<MODE, STAGES, KIND>;
     static bool configured = false;
     if (!configured) {
         FPCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -623,7 +706,7 @@ static int launch_tc(TcArgs &a, const int8_t *W, int64_t w_rows, int tiles_m, co
     int total = tiles_m * n_blocks_n;
     int sms = g_sm_budget > 0 && g_sm_budget < sm_count() ? g_sm_budget : sm_count();
     int grid = total < sms ? total : sms;
-    kern<<<grid, P_THREADS, smem, s>>>(a, tmap, ep, out, tiles_m, n_blocks_n);
+    kern<<<grid, P_THREADS, smem, s>>>(a, tmap, ep, fe, out, tiles_m, n_blocks_n);
     FPCC_LAUNCH_CHECK();
     return FPCC_OK;
 }
@@ -635,7 +718,8 @@ int launch_conv_tc(const int8_t *feats, int n_in, int c_in, const int8_t *weight
     TcArgs a = {};
     a.A = feats; a.K = c_in; a.N = c_out;
     a.nbr = nbr; a.ld = ld; a.n_out = n_out; a.kvol = kvol;
-    return launch_tc<0>(a, weight, (int64_t)kvol * c_out, ceil_div(n_out, TC_M), ep, out, s);
+    FEpi fe = {};
+    return launch_tc<0, 0>(a, weight, (int64_t)kvol * c_out, ceil_div(n_out, TC_M), ep, fe, out, s);
 }
 
 int launch_pairs_tc(const PairArgs &p, const EpiParams &ep, void *out, int max_tiles, cudaStream_t s) {
@@ -646,10 +730,64 @@ int launch_pairs_tc(const PairArgs &p, const EpiParams &ep, void *out, int max_t
     a.in_idx = p.in_idx; a.out_idx = p.out_idx; a.offsets = p.offsets;
     a.n_groups = p.n_groups; a.n_pairs = p.n_pairs; a.bias_per_group = p.bias_per_group;
     int tiles = ceil_div(p.n_pairs, TC_M) + (p.offsets ? p.n_groups : 0);
-    return launch_tc<1>(a, p.W, (int64_t)p.n_groups * p.N, tiles, ep, out, s);
+    FEpi fe = {};
+    return launch_tc<1, 0>(a, p.W, (int64_t)p.n_groups * p.N, tiles, ep, fe, out, s);
 }
 
 }  // namespace fpcc
+
+// ---- fp16 / bf16 entry points (MinkowskiEngine / torchsparse float layers) ---------------------------------
+static int f16_common(int dtype, int out_type, int act, int post_act, int c_in, int c_out, const void *A, const void *W, const void *out) {
+    FPCC_REQUIRE(dtype == 0 || dtype == 1, "f16 GEMM: dtype must be 0 (fp16) or 1 (bf16)");
+    FPCC_REQUIRE(out_type >= 0 && out_type <= 2, "f16 GEMM: out_type must be 0 (fp16), 1 (bf16) or 2 (fp32)");
+    FPCC_REQUIRE(act >= 0 && act <= 2 && post_act >= 0 && post_act <= 2, "f16 GEMM: bad activation code");
+    FPCC_REQUIRE(c_in >= 16 && c_in % 8 == 0 && c_out >= 16, "f16 GEMM: needs C_in %% 8 == 0, C_in >= 16, C_out >= 16 (got %d -> %d)", c_in, c_out);
+    FPCC_REQUIRE((((uintptr_t)A | (uintptr_t)W | (uintptr_t)out) & 15) == 0, "f16 GEMM: pointers must be 16-byte aligned");
+    return FPCC_OK;
+}
+
+extern "C" int fpcc_spconv_f16(const void *feats, int dtype, int n_in, int c_in, const void *weight, int kvol, int c_out,
+                               const int32_t *nbr_table, int64_t ld, int n_out, const float *bias, int act, float slope,
+                               const void *residual, int post_act, float post_slope, void *out, int out_type, void *stream) {
+    using namespace fpcc;
+    FPCC_REQUIRE(feats && weight && nbr_table && out, "spconv_f16: NULL pointer");
+    FPCC_REQUIRE(n_in > 0 && n_out > 0 && kvol > 0 && kvol <= TC_MAX_KVOL && ld >= n_out, "spconv_f16: bad sizes");
+    int rc = f16_common(dtype, out_type, act, post_act, c_in, c_out, feats, weight, out);
+    if (rc) return rc;
+    TcArgs a = {};
+    a.A = (const int8_t *)feats; a.K = 2 * c_in; a.N = c_out;
+    a.nbr = nbr_table; a.ld = ld; a.n_out = n_out; a.kvol = kvol;
+    FEpi fe = {bias, residual, slope, post_slope, act, post_act, out_type};
+    EpiParams ep = {};
+    if (dtype == 0) return launch_tc<0, 1>(a, weight, (int64_t)kvol * c_out, ceil_div(n_out, TC_M), ep, fe, out, (cudaStream_t)stream);
+    return launch_tc<0, 2>(a, weight, (int64_t)kvol * c_out, ceil_div(n_out, TC_M), ep, fe, out, (cudaStream_t)stream);
+}
+
+extern "C" int fpcc_linear_f16(const void *A, int dtype, int m, int k, const void *W, int n, const int32_t *sel_row,
+                               const int32_t *sel_out, const int32_t *sel_offsets, int n_groups, int n_sel, const float *bias,
+                               int act, float slope, const void *residual, int post_act, float post_slope, void *out,
+                               int out_type, void *stream) {
+    using namespace fpcc;
+    FPCC_REQUIRE(A && W && out && m > 0, "linear_f16: bad arguments");
+    int rc = f16_common(dtype, out_type, act, post_act, k, n, A, W, out);
+    if (rc) return rc;
+    TcArgs a = {};
+    a.A = (const int8_t *)A; a.K = 2 * k; a.N = n;
+    int tiles;
+    if (sel_row) {
+        FPCC_REQUIRE(sel_out && sel_offsets && n_groups > 0 && n_sel > 0, "linear_f16: incomplete selection");
+        a.in_idx = sel_row; a.out_idx = sel_out; a.offsets = sel_offsets; a.n_groups = n_groups; a.n_pairs = n_sel; a.bias_per_group = 0;
+        tiles = ceil_div(n_sel, TC_M) + n_groups;
+    } else {
+        a.n_groups = 1; a.n_pairs = m;
+        tiles = ceil_div(m, TC_M);
+        n_groups = 1;
+    }
+    FEpi fe = {bias, residual, slope, post_slope, act, post_act, out_type};
+    EpiParams ep = {};
+    if (dtype == 0) return launch_tc<1, 1>(a, W, (int64_t)n_groups * n, tiles, ep, fe, out, (cudaStream_t)stream);
+    return launch_tc<1, 2>(a, W, (int64_t)n_groups * n, tiles, ep, fe, out, (cudaStream_t)stream);
+}
 
 extern "C" int fpcc_mma_i8_peak(int iters, int n, double *tops_out, void *stream) {
     using namespace fpcc;

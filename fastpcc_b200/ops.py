@@ -155,7 +155,7 @@ def hash_build(coords, layout=0, keys=None, vals=None):
     return keys, vals
 
 
-def kmap_lookup(keys, vals, out_coords, kernel_size, stride, layout=0, k_major=True, pad_rows=None):
+def kmap_lookup(keys, vals, out_coords, kernel_size, stride, layout=0, k_major=True, pad_rows=None, convention=0):
     _need(out_coords, torch.int32, 'out_coords', 2)
     n = out_coords.shape[0]
     kv = kernel_size[0] * kernel_size[1] * kernel_size[2]
@@ -167,7 +167,7 @@ def kmap_lookup(keys, vals, out_coords, kernel_size, stride, layout=0, k_major=T
         table = (torch.zeros if rows != n else torch.empty)((rows, kv), dtype=torch.int32, device=out_coords.device)
         ld = 0
     _call('fpcc_kmap_lookup', _p(keys), _p(vals), keys.numel(), _p(out_coords), n, layout,
-              kernel_size[0], kernel_size[1], kernel_size[2], stride[0], stride[1], stride[2],
+              kernel_size[0], kernel_size[1], kernel_size[2], stride[0], stride[1], stride[2], convention,
               _p(table), 1 if k_major else 0, ld, _s())
     return table
 
@@ -435,3 +435,69 @@ class RansDecodeStreams:
 
     def error(self):
         return bool((self.state[:, 3] != 0).any().item())
+
+
+# ---------------------------------------------------------------------------------------------
+# fp16 / bf16 tensor-core path (float layer API)
+# ---------------------------------------------------------------------------------------------
+_F_DT = {torch.float16: 0, torch.bfloat16: 1}
+_F_OUT = {torch.float16: 0, torch.bfloat16: 1, torch.float32: 2}
+ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+
+
+def _fargs(bias, residual, out_dtype):
+    if bias is not None:
+        _need(bias, torch.float32, 'bias', 1)
+    if residual is not None and residual.dtype != out_dtype:
+        raise RuntimeError('residual must have the output dtype')
+    return _p(bias), _p(residual)
+
+
+def spconv_f16(feats, weight_t, table, bias=None, act=ACT_NONE, slope=0.0, residual=None, post_act=ACT_NONE,
+               post_slope=0.0, out_dtype=None):
+    """Fused fp16/bf16 sparse conv: feats [n_in, c_in], weight_t [kvol, c_out, c_in] (same dtype), k-major table."""
+    if feats.dtype not in _F_DT or weight_t.dtype != feats.dtype:
+        raise RuntimeError(f'spconv_f16: fp16/bf16 features and weights of one dtype expected, got {feats.dtype}/{weight_t.dtype}')
+    if not (feats.is_cuda and feats.is_contiguous() and weight_t.is_contiguous() and table.is_contiguous()):
+        raise RuntimeError('spconv_f16: contiguous CUDA tensors expected')
+    kv, c_out, c_in = weight_t.shape
+    if table.shape[0] != kv or feats.shape[1] != c_in:
+        raise RuntimeError('spconv_f16: shape mismatch')
+    out_dtype = feats.dtype if out_dtype is None else out_dtype
+    n_out = table.shape[1]
+    out = torch.empty((n_out, c_out), dtype=out_dtype, device=feats.device)
+    pb, pr = _fargs(bias, residual, out_dtype)
+    work = None
+    if _prof is not None:
+        work = {'ops': 2.0 * _pairs_of(table) * c_in * c_out, 'mma_ops': 2.0 * ((n_out + 127) // 128 * 128) * kv * c_in * c_out}
+    _call('fpcc_spconv_f16', _p(feats), _F_DT[feats.dtype], feats.shape[0], c_in, _p(weight_t), kv, c_out, _p(table), n_out,
+          n_out, pb, act, float(slope), pr, post_act, float(post_slope), _p(out), _F_OUT[out_dtype], _s(),
+          tag='spconv_f16_tc', work=work)
+    return out
+
+
+def linear_f16(a, weight, bias=None, act=ACT_NONE, slope=0.0, residual=None, post_act=ACT_NONE, post_slope=0.0,
+               out_dtype=None, sel=None, n_out_rows=None):
+    """Fused fp16/bf16 linear: a [m, k], weight [n_groups*n, k]; sel = (sel_row, sel_out, offsets) as in `linear`."""
+    if a.dtype not in _F_DT or weight.dtype != a.dtype:
+        raise RuntimeError('linear_f16: fp16/bf16 inputs of one dtype expected')
+    if not (a.is_cuda and a.is_contiguous() and weight.is_contiguous()):
+        raise RuntimeError('linear_f16: contiguous CUDA tensors expected')
+    m, k = a.shape
+    out_dtype = a.dtype if out_dtype is None else out_dtype
+    if sel is None:
+        n = weight.shape[0]
+        out = torch.empty((m, n), dtype=out_dtype, device=a.device)
+        pb, pr = _fargs(bias, residual, out_dtype)
+        _call('fpcc_linear_f16', _p(a), _F_DT[a.dtype], m, k, _p(weight), n, None, None, None, 1, 0, pb, act, float(slope), pr,
+              post_act, float(post_slope), _p(out), _F_OUT[out_dtype], _s(), tag='linear_f16_tc', work={'ops': 2.0 * m * k * n})
+    else:
+        sel_row, sel_out, offsets = sel
+        groups = offsets.numel() - 1
+        n = weight.shape[0] // groups
+        out = torch.empty((n_out_rows, n), dtype=out_dtype, device=a.device)
+        pb, pr = _fargs(bias, residual, out_dtype)
+        _call('fpcc_linear_f16', _p(a), _F_DT[a.dtype], m, k, _p(weight), n, _p(sel_row), _p(sel_out), _p(offsets), groups,
+              n_out_rows, pb, act, float(slope), pr, post_act, float(post_slope), _p(out), _F_OUT[out_dtype], _s(),
+              tag='linear_sel_f16_tc', work={'ops': 2.0 * n_out_rows * k * n})
+    return out

@@ -62,10 +62,14 @@ int fpcc_hash_insert_coords(int64_t *keys, int32_t *vals, int capacity,
  * enumerated as in the reference (odd kernel volume: x fastest, even: z fastest; per-axis offset
  * k%ks - (ks-1)/2).  Writes row index + 1 or 0.
  * k_major = 1 writes table[k*ld + o] (ld >= n_out), k_major = 0 writes table[o*kvol + k] (the
- * reference's layout).  Every entry of the addressed region is written (no pre-zeroing needed). */
+ * reference's layout).  Every entry of the addressed region is written (no pre-zeroing needed).
+ * convention 0 = the torchsparse-derived rule above (compact per-level coordinates).  convention 1 =
+ * MinkowskiEngine HYPER_CUBE (lib/minkowski_sparse_conv_layers.py; offsets as minkowski_expand_coord_2x :401-408):
+ * absolute coordinates, neighbour = o + offset(k) * s, x fastest for every kernel, odd kernels centred, even
+ * kernels 0..k-1, with s = the input tensor stride. */
 int fpcc_kmap_lookup(const int64_t *keys, const int32_t *vals, int capacity,
                      const int32_t *out_coords, int n_out, int layout,
-                     int ksx, int ksy, int ksz, int sx, int sy, int sz,
+                     int ksx, int ksy, int ksz, int sx, int sy, int sz, int convention,
                      int32_t *table, int k_major, int64_t ld, void *stream);
 
 /* replaces the host-synchronising compaction at cuda_ops.py:132-151.  table is k-major [kvol, ld].
@@ -183,6 +187,21 @@ int fpcc_set_tc_mode(int mode);
 /* Persistent GEMM kernels occupy one whole SM per CTA.  When serial range-coder kernels of another CUDA stream
  * should run beside them, cap the GEMM grids at `sms` SMs (0 = all SMs) so that the coder blocks find free SMs. */
 int fpcc_set_sm_budget(int sms);
+/* fp16 / bf16 twins of fpcc_spconv_i8 / fpcc_linear_i8 on tcgen05.mma.kind::f16 with fp32 accumulation in TMEM,
+ * for the float layer API (MinkowskiEngine blocks of lib/minkowski_sparse_conv_layers.py:31-280, torchsparse
+ * spnn.Conv3d of lossl_coord/model.py:34-46).  dtype: 0 fp16, 1 bf16 (features and weights); weight is
+ * [kvol, c_out, c_in] (the layer keeps ME's [kvol, c_in, c_out] parameter and caches this transposed copy).
+ * Epilogue: v = acc + bias; v = act(v); [v += residual; v = post_act(v)]; cast to out_type (0 fp16, 1 bf16, 2 fp32).
+ * act codes: 0 none, 1 ReLU, 2 LeakyReLU / single-slope PReLU.  Accumulation order is fixed (offset-major, K
+ * ascending), so encoder and decoder of a float codec see identical bits run to run.  c_in % 8 == 0, >= 16. */
+int fpcc_spconv_f16(const void *feats, int dtype, int n_in, int c_in, const void *weight, int kvol, int c_out,
+                    const int32_t *nbr_table, int64_t ld, int n_out, const float *bias, int act, float slope,
+                    const void *residual, int post_act, float post_slope, void *out, int out_type, void *stream);
+int fpcc_linear_f16(const void *A, int dtype, int m, int k, const void *W, int n, const int32_t *sel_row,
+                    const int32_t *sel_out, const int32_t *sel_offsets, int n_groups, int n_sel, const float *bias,
+                    int act, float slope, const void *residual, int post_act, float post_slope, void *out,
+                    int out_type, void *stream);
+
 /* Measures the kind::i8 tensor-pipe ceiling of the current device: every SM issues `iters` x 4 back-to-back
  * tcgen05.mma (M=128, N=n, K=32) on resident shared-memory tiles.  Synchronises.  *tops_out = int8 TOP/s. */
 int fpcc_mma_i8_peak(int iters, int n, double *tops_out, void *stream);

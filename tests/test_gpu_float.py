@@ -1,0 +1,82 @@
+"""fp16 / bf16 tensor-core sparse convolution and linear (tcgen05.mma.kind::f16) against a plain fp32 reference of
+the same op.  Tolerance (stated by BASELINE.json north_star): 1e-2 relative in fp16; bf16 has 3 fewer mantissa bits
+so its bound is 4e-2.  'Relative' = max |got - want| / max |want| over the tensor."""
+import numpy as np
+import pytest
+import torch
+
+from fastpcc_b200 import synth
+from oracle import float_ops as FO
+
+pytestmark = pytest.mark.gpu
+TOL = {torch.float16: 1e-2, torch.bfloat16: 4e-2}
+
+
+def _rel(got, want):
+    return float(np.abs(got.astype(np.float64) - want).max() / max(np.abs(want).max(), 1e-12))
+
+
+def _cloud(seed, n, bits, stride=1):
+    rng = np.random.default_rng(seed)
+    pts = np.unique(rng.integers(0, 1 << bits, (n, 3)), axis=0).astype(np.int32) * stride
+    return synth.with_batch(pts)
+
+
+@pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize('cin,cout,ks', [(16, 16, 3), (64, 128, 3), (128, 128, 3), (32, 64, 2), (128, 1, 3)])
+def test_spconv_f16_matches_fp32_reference(dtype, cin, cout, ks):
+    from fastpcc_b200 import ops
+    if cout < 16:
+        pytest.skip('C_out < 16 runs through the padded path of the layer API (tested there)')
+    rng = np.random.default_rng(cin + cout)
+    ts = 2
+    C = _cloud(1, 4000, 6, stride=ts)
+    if ks == 3:
+        out_c = C
+        table_ref = FO.me_lookup(C, out_c, 3, ts)
+    else:  # stride-2 downsampling conv: outputs on the 2*ts lattice
+        oc = C.copy(); oc[:, 1:] = oc[:, 1:] // (2 * ts) * (2 * ts)
+        out_c = np.unique(oc, axis=0)
+        table_ref = FO.me_lookup(C, out_c, 2, ts)
+    keys, vals = ops.hash_build(torch.from_numpy(C).cuda())
+    table = ops.kmap_lookup(keys, vals, torch.from_numpy(out_c).cuda(), (ks,) * 3, (ts,) * 3, convention=1)
+    assert (table.cpu().numpy() == table_ref).all()
+    f = torch.from_numpy(rng.normal(0, 1, (C.shape[0], cin)).astype(np.float32)).to(dtype)
+    w = torch.from_numpy((rng.normal(0, 1, (ks ** 3, cin, cout)) / np.sqrt(cin * 4)).astype(np.float32)).to(dtype)
+    b = rng.normal(0, 0.1, cout).astype(np.float32)
+    want = FO.act(FO.sparse_conv_f32(f.float().numpy(), w.float().numpy(), table_ref, b), 'relu')
+    got = ops.spconv_f16(f.cuda(), w.permute(0, 2, 1).contiguous().cuda(), table, bias=torch.from_numpy(b).cuda(), act=ops.ACT_RELU)
+    assert got.dtype == dtype
+    assert _rel(got.float().cpu().numpy(), want) < TOL[dtype]
+    # residual + post activation (ResBlock tail), fp32 output
+    res = torch.from_numpy(rng.normal(0, 1, (out_c.shape[0], cout)).astype(np.float32))
+    want2 = FO.act(FO.sparse_conv_f32(f.float().numpy(), w.float().numpy(), table_ref, b) + res.numpy(), 'leaky_relu', 0.2)
+    got2 = ops.spconv_f16(f.cuda(), w.permute(0, 2, 1).contiguous().cuda(), table, bias=torch.from_numpy(b).cuda(),
+                          residual=res.cuda(), post_act=ops.ACT_LEAKY, post_slope=0.2, out_dtype=torch.float32)
+    assert _rel(got2.cpu().numpy(), want2) < TOL[dtype]
+    # determinism: the same launch twice gives identical bits (encoder/decoder of a float codec rely on it)
+    again = ops.spconv_f16(f.cuda(), w.permute(0, 2, 1).contiguous().cuda(), table, bias=torch.from_numpy(b).cuda(), act=ops.ACT_RELU)
+    assert torch.equal(got, again)
+
+
+@pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16])
+def test_linear_f16_and_selected_children(dtype):
+    from fastpcc_b200 import ops
+    rng = np.random.default_rng(3)
+    m, k, n = 3000, 128, 64
+    a = torch.from_numpy(rng.normal(0, 1, (m, k)).astype(np.float32)).to(dtype)
+    w = torch.from_numpy((rng.normal(0, 1, (n, k)) / np.sqrt(k)).astype(np.float32)).to(dtype)
+    b = rng.normal(0, 0.1, n).astype(np.float32)
+    want = a.float().numpy() @ w.float().numpy().T + b
+    got = ops.linear_f16(a.cuda(), w.cuda(), bias=torch.from_numpy(b).cuda())
+    assert _rel(got.float().cpu().numpy(), want) < TOL[dtype]
+    # transposed conv k2 s2 onto existing children == one weight block per child slot (selection linear)
+    occ = rng.integers(1, 256, m).astype(np.uint8)
+    w8 = torch.from_numpy((rng.normal(0, 1, (8 * n, k)) / np.sqrt(k)).astype(np.float32)).to(dtype)
+    coords = torch.from_numpy(synth.with_batch(np.stack([np.arange(m), np.zeros(m), np.zeros(m)], 1).astype(np.int32))).cuda()
+    _, par, slot, nchild = ops.upsample(coords, torch.from_numpy(occ).cuda(), want_coords=False)
+    sel = ops.slot_pairs(par, slot)
+    got = ops.linear_f16(a.cuda(), w8.cuda(), sel=sel, n_out_rows=nchild).float().cpu().numpy()
+    dense = (a.float().numpy() @ w8.float().numpy().T).reshape(m, 8, n)
+    bits = ((occ[:, None] >> np.arange(7, -1, -1)[None]) & 1).astype(bool)
+    assert _rel(got, dense[bits]) < TOL[dtype]
