@@ -477,7 +477,7 @@ def spconv_f16(feats, weight_t, table, bias=None, act=ACT_NONE, slope=0.0, resid
 
 
 def linear_f16(a, weight, bias=None, act=ACT_NONE, slope=0.0, residual=None, post_act=ACT_NONE, post_slope=0.0,
-               out_dtype=None, sel=None, n_out_rows=None):
+               out_dtype=None, sel=None, n_out_rows=None, out=None):
     """Fused fp16/bf16 linear: a [m, k], weight [n_groups*n, k]; sel = (sel_row, sel_out, offsets) as in `linear`."""
     if a.dtype not in _F_DT or weight.dtype != a.dtype:
         raise RuntimeError('linear_f16: fp16/bf16 inputs of one dtype expected')
@@ -495,7 +495,7 @@ def linear_f16(a, weight, bias=None, act=ACT_NONE, slope=0.0, residual=None, pos
         sel_row, sel_out, offsets = sel
         groups = offsets.numel() - 1
         n = weight.shape[0] // groups
-        out = torch.empty((n_out_rows, n), dtype=out_dtype, device=a.device)
+        out = torch.empty((n_out_rows, n), dtype=out_dtype, device=a.device) if out is None else out
         pb, pr = _fargs(bias, residual, out_dtype)
         _call('fpcc_linear_f16', _p(a), _F_DT[a.dtype], m, k, _p(weight), n, _p(sel_row), _p(sel_out), _p(offsets), groups,
               n_out_rows, pb, act, float(slope), pr, post_act, float(post_slope), _p(out), _F_OUT[out_dtype], _s(),
