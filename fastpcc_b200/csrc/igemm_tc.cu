@@ -117,15 +117,12 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -147,7 +144,8 @@ struct TcArgs {
     // MODE_PAIRS
     const int32_t *in_idx, *out_idx, *offsets;
     int n_groups, n_pairs, bias_per_group;
-    int dbg;  // FPCC_TC_DEBUG bitmask (experiments only): 1 skip A loads, 2 skip B loads, 4 skip epilogue math, 8 skip MMA
+    int dbg;  // FPCC_TC_DEBUG bitmask (experiments only): 1 skip A loads, 2 skip B loads, 4 skip epilogue math, 8 skip MMA,
+              // 16 force the 64-bit epilogue
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -162,8 +160,19 @@ struct TcArgs {
 // Epilogue of one 32-column chunk of one output row.  Values stay in registers; the body is specialised at compile
 // time on the output type, the PReLU and the occupancy row-bias so that the 32x unrolled arithmetic carries no
 // per-element selects: ~22 (no PReLU) / ~32 (PReLU) integer instructions per element, all 64-bit exact.
+constexpr int EC = 16;  // accumulator columns per epilogue step (one tcgen05.ld.32x32b.x16)
+
+// 16-byte vector stores of the packed words of one chunk (nbytes is a multiple of 16)
+template <int WORDS>
+__device__ __forceinline__ void store_words(char *optr, const uint32_t (&w)[WORDS], int nbytes) {
+#pragma unroll
+    for (int t = 0; t < WORDS / 4; ++t)
+        if (t * 16 < nbytes) reinterpret_cast<uint4 *>(optr)[t] = make_uint4(w[4 * t], w[4 * t + 1], w[4 * t + 2], w[4 * t + 3]);
+}
+
 struct EpiCtx {
-    const int2 *chan;          // smem (bias, mul) pairs of this chunk
+    const int2 *chan;          // smem (bias, mul) pairs of this chunk (unused when chan4 is set)
+    const int4 *chan4;         // smem (bias, mul, B, -B) of this chunk
     int32_t slope, post;
     int64_t zp, half;          // half = 2^(shift-1) (0 when shift == 0)
     int shift, sgn;            // sgn = 1 when shift > 0 (round-half-away correction for negatives)
@@ -178,52 +187,175 @@ __device__ __forceinline__ int32_t sat_s16(int64_t r) { int32_t o; asm("cvt.sat.
 __device__ __forceinline__ int32_t sat_s32(int64_t r) { int32_t o; asm("cvt.sat.s32.s64 %0, %1;" : "=r"(o) : "l"(r)); return o; }
 
 template <int OUT, bool SLOPE, bool ROWBIAS>
-__device__ __forceinline__ void epi_chunk(const uint32_t (&acc)[32], const EpiCtx &cx, void *optr, bool vec) {
-    int32_t o[32];
+__device__ __forceinline__ void epi_chunk(const uint32_t (&acc)[EC], const EpiCtx &cx, int32_t (&o)[EC]) {
 #pragma unroll
-    for (int q = 0; q < 32; ++q) {
-        const int2 bm = cx.chan[q];
+    for (int q = 0; q < EC; ++q) {
+        const int32_t bias = cx.chan4 ? cx.chan4[q].x : cx.chan[q].x;
+        const uint32_t mul = (uint32_t)(cx.chan4 ? cx.chan4[q].y : cx.chan[q].y);
         int32_t a32 = (int32_t)acc[q];
         if (ROWBIAS) a32 = (int32_t)((uint32_t)a32 + (uint32_t)__ldg(&cx.row_bias[q < cx.nvalid ? q : 0]));
-        int64_t v = (int64_t)a32 + (int64_t)bm.x;
+        int64_t v = (int64_t)a32 + (int64_t)bias;
         if (SLOPE) {  // Q6.25 PReLU on negatives, round half away (bias_prelu_requant.cu:17-22)
             int64_t t = v * (int64_t)cx.slope;
             t = (t + ((1ll << 24) - (int64_t)((uint64_t)t >> 63))) >> 25;
             v = v < 0 ? t : v;
         }
-        int64_t r = v * (int64_t)(uint32_t)bm.y + cx.zp;
+        int64_t r = v * (int64_t)mul + cx.zp;
         r = (r + (cx.half - (int64_t)(((uint64_t)r >> 63) & (uint64_t)cx.sgn))) >> cx.shift;
         o[q] = OUT == FPCC_OUT_I8 ? sat_s8(r) : (OUT == FPCC_OUT_I16 ? sat_s16(r) : sat_s32(r));
     }
-    if (OUT == FPCC_OUT_I32 && cx.residual) {
+}
+
+// ---- 32-bit fast path -------------------------------------------------------------------------------------
+// The same results as epi_chunk with ~11 (no PReLU) / ~15 (PReLU) 32-bit instructions per element.  It is taken
+// when the CTA-uniform preconditions checked at staging time hold (fast_ok below); a chunk whose values leave the
+// proven ranges falls back to epi_chunk.  Per channel, staged in shared memory:
+//   x bias   y mul (< 2^31)   z B   w -B,  thr[c]
+//   B:   |v| >= B  =>  the requantised value saturates the output type, so clamping v to [-B, B] first changes
+//        nothing and makes v*mul + zp fit comfortably in 64 bits with a quotient that fits 32 bits (I8 / I16);
+//   thr: v*mul + zp < 0  <=>  v < thr  (the "-1 for negatives" of round-half-away; thr == 0 when zp == 0).
+struct FastCtx {
+    uint32_t chan;   // shared-space addresses (explicit ld.shared: the compiler cannot prove the space of a struct member)
+    uint32_t thr;
+    int32_t slope, post;
+    uint32_t c0_lo, c0_hi;   // zp + 2^(shift-1)
+    int shift;
+    uint32_t ovf_add, ovf_lim;  // I32: result fits iff (hi + ovf_add) < ovf_lim (unsigned)
+};
+
+__device__ __forceinline__ int64_t mad_wide(int32_t a, int32_t b, int64_t c) {  // one IMAD.WIDE
+    int64_t d;
+    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ int4 lds128(uint32_t addr) {
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int32_t lds32(uint32_t addr) {
+    int32_t v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int32_t prelu_fast(int32_t v, int32_t slope) {  // 0 <= slope <= 2^25: |result| <= |v|
+    const int64_t p = mad_wide(v, slope, (int64_t)((1 << 24) - 1));  // v < 0 => product <= 0 => the -1 applies
+    const int32_t pv = (int32_t)__funnelshift_r((uint32_t)p, (uint32_t)((uint64_t)p >> 32), 25);
+    return v < 0 ? pv : v;
+}
+
+template <int OUT, bool SLOPE, bool ROWBIAS, bool ZP0>
+__device__ __forceinline__ bool epi_chunk_fast(const uint32_t (&acc)[EC], const FastCtx &fx, const int32_t *row_bias,
+                                               int nvalid, int32_t (&o)[EC]) {
+    bool bad = false;
 #pragma unroll
-        for (int q = 0; q < 32; ++q) {
-            int32_t rv = (int32_t)((uint32_t)o[q] + (uint32_t)__ldg(&cx.residual[q < cx.nvalid ? q : 0]));  // int32 add wraps
-            o[q] = cx.has_post ? sat_s32(prelu_q25((int64_t)rv, cx.post)) : rv;
+    for (int q = 0; q < EC; ++q) {
+        const int4 ch = lds128(fx.chan + q * 16);
+        int32_t v = (int32_t)acc[q];
+        if (ROWBIAS) {
+            v = (int32_t)((uint32_t)v + (uint32_t)__ldg(&row_bias[q < nvalid ? q : 0]));
+            bad |= (uint32_t)v + (1u << 30) > (1u << 31);  // keeps v + bias inside int32
         }
+        v += ch.x;
+        if (SLOPE) v = prelu_fast(v, fx.slope);
+        if (OUT != FPCC_OUT_I32) v = max(min(v, ch.z), ch.w);
+        const bool neg = ZP0 ? (v < 0) : (v < lds32(fx.thr + q * 4));
+        const int64_t c = (int64_t)(((uint64_t)fx.c0_hi << 32) | (uint64_t)(fx.c0_lo - (neg ? 1u : 0u)));  // c0_lo != 0
+        const int64_t t = mad_wide(v, ch.y, c);
+        const uint32_t lo = (uint32_t)t, hi = (uint32_t)((uint64_t)t >> 32);
+        int32_t r = (int32_t)__funnelshift_r(lo, hi, fx.shift);
+        if (OUT == FPCC_OUT_I8) r = max(min(r, 127), -128);
+        else if (OUT == FPCC_OUT_I16) r = max(min(r, 32767), -32768);
+        else bad |= hi + fx.ovf_add >= fx.ovf_lim;
+        o[q] = r;
     }
-    if (vec) {
-        if (OUT == FPCC_OUT_I8) {
-            uint4 *dst = reinterpret_cast<uint4 *>(optr);
+    return !bad;
+}
+
+// CTA-uniform part of the fast-path preconditions
+__device__ __forceinline__ bool fast_uniform_ok(const EpiParams &ep, int out_type, int64_t zp, int64_t kk) {
+    const int shift = ep.shift;
+    if (shift > 31 || shift < (out_type == FPCC_OUT_I32 ? 1 : 0) || kk > 65536) return false;
+    const int64_t c0 = zp + (shift > 0 ? (int64_t)1 << (shift - 1) : 0);
+    if ((uint32_t)c0 == 0u || zp > ((int64_t)1 << 60) || zp < -((int64_t)1 << 60)) return false;
+    if (ep.slope) { const int32_t sl = ep.slope[0]; if (sl < 0 || sl > (1 << 25)) return false; }
+    if (ep.post_slope) { const int32_t sl = ep.post_slope[0]; if (sl < 0 || sl > (1 << 25)) return false; }
+    return true;
+}
+
+// Per-channel constants of the fast path; returns false when this channel cannot take it.
+__device__ __forceinline__ bool fast_channel(int32_t bias, uint32_t mul, int64_t zp, int shift, int out_type, int4 *ch, int32_t *thr) {
+    bool ok = mul < (1u << 31) && bias <= (1 << 29) && bias >= -(1 << 29);
+    const int64_t azp = zp < 0 ? -zp : zp;
+    int64_t B = 0;
+    if (out_type != FPCC_OUT_I32) {
+        const int64_t hi_t = out_type == FPCC_OUT_I8 ? 127 : 32767;
+        const int64_t num = ((hi_t + 2) << shift) + azp;
+        B = mul ? (num + (int64_t)mul - 1) / (int64_t)mul : 0;
+        if (B > 2147483646ll) B = 2147483646ll;
+        // |v*mul + zp + half| <= num + mul + |zp| + half must shift down into 32 bits
+        ok = ok && ((num + (int64_t)mul + azp + ((int64_t)1 << 31)) >> shift) < 2147483647ll;
+    }
+    int64_t t;
+    if (mul == 0) t = zp < 0 ? 2147483647ll : -2147483648ll;
+    else { const int64_t nz = -zp, m = (int64_t)mul; t = nz >= 0 ? (nz + m - 1) / m : -((-nz) / m); }
+    t = t > 2147483647ll ? 2147483647ll : (t < -2147483648ll ? -2147483648ll : t);
+    *ch = make_int4(bias, (int32_t)mul, (int32_t)B, (int32_t)-B);
+    *thr = (int32_t)t;
+    return ok;
+}
+
+template <int OUT>
+__device__ __forceinline__ void epi_store_chunk(int32_t (&o)[EC], const EpiCtx &cx, void *optr, bool vec, bool fast_post) {
+    if (OUT == FPCC_OUT_I32 && cx.residual) {
+        if (vec) {
+            const int4 *rp = reinterpret_cast<const int4 *>(cx.residual);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                uint32_t w[4];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const int q = h * 16 + t * 4;
-                    w[t] = (uint32_t)(o[q] & 0xff) | ((uint32_t)(o[q + 1] & 0xff) << 8) | ((uint32_t)(o[q + 2] & 0xff) << 16) |
-                           ((uint32_t)(o[q + 3] & 0xff) << 24);
-                }
-                dst[h] = make_uint4(w[0], w[1], w[2], w[3]);
+            for (int t = 0; t < EC / 4; ++t) {
+                const int4 rv = 4 * t < cx.nvalid ? __ldg(rp + t) : make_int4(0, 0, 0, 0);
+                o[4 * t] = (int32_t)((uint32_t)o[4 * t] + (uint32_t)rv.x);  // int32 add wraps
+                o[4 * t + 1] = (int32_t)((uint32_t)o[4 * t + 1] + (uint32_t)rv.y);
+                o[4 * t + 2] = (int32_t)((uint32_t)o[4 * t + 2] + (uint32_t)rv.z);
+                o[4 * t + 3] = (int32_t)((uint32_t)o[4 * t + 3] + (uint32_t)rv.w);
             }
         } else {
-            int4 *dst = reinterpret_cast<int4 *>(optr);
 #pragma unroll
-            for (int t = 0; t < 8; ++t) dst[t] = make_int4(o[4 * t], o[4 * t + 1], o[4 * t + 2], o[4 * t + 3]);
+            for (int q = 0; q < EC; ++q) o[q] = (int32_t)((uint32_t)o[q] + (uint32_t)__ldg(&cx.residual[q < cx.nvalid ? q : 0]));
+        }
+        if (cx.has_post) {
+            if (fast_post) {
+#pragma unroll
+                for (int q = 0; q < EC; ++q) o[q] = prelu_fast(o[q], cx.post);
+            } else {
+#pragma unroll
+                for (int q = 0; q < EC; ++q) o[q] = sat_s32(prelu_q25((int64_t)o[q], cx.post));
+            }
+        }
+    }
+    if (vec) {  // nvalid == EC here (N is a multiple of 16)
+        if (OUT == FPCC_OUT_I8) {
+            uint32_t w[EC / 4];
+#pragma unroll
+            for (int t = 0; t < EC / 4; ++t) {
+                const int q = t * 4;
+                w[t] = (uint32_t)(o[q] & 0xff) | ((uint32_t)(o[q + 1] & 0xff) << 8) | ((uint32_t)(o[q + 2] & 0xff) << 16) |
+                       ((uint32_t)(o[q + 3] & 0xff) << 24);
+            }
+            store_words<EC / 4>((char *)optr, w, cx.nvalid);
+        } else if (OUT == FPCC_OUT_I16) {
+            uint32_t w[EC / 2];
+#pragma unroll
+            for (int t = 0; t < EC / 2; ++t) w[t] = (uint32_t)(o[2 * t] & 0xffff) | ((uint32_t)o[2 * t + 1] << 16);
+            store_words<EC / 2>((char *)optr, w, cx.nvalid * 2);
+        } else {
+            uint32_t w[EC];
+#pragma unroll
+            for (int t = 0; t < EC; ++t) w[t] = (uint32_t)o[t];
+            store_words<EC>((char *)optr, w, cx.nvalid * 4);
         }
     } else {
 #pragma unroll
-        for (int q = 0; q < 32; ++q) {
+        for (int q = 0; q < EC; ++q) {
             if (q < cx.nvalid) {
                 if (OUT == FPCC_OUT_I8) ((int8_t *)optr)[q] = (int8_t)o[q];
                 else if (OUT == FPCC_OUT_I16) ((int16_t *)optr)[q] = (int16_t)o[q];
@@ -233,10 +365,29 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&acc)[32], const EpiCt
     }
 }
 
+template <int OUT, bool SLOPE, bool ROWBIAS>
+__device__ __forceinline__ void epi_one(const uint32_t (&acc)[EC], const EpiCtx &cx, const FastCtx &fx, void *optr, bool vec,
+                                        bool fast, bool zp0) {
+    int32_t o[EC];
+    bool done = false;
+    if (fast) {
+        done = zp0 ? epi_chunk_fast<OUT, SLOPE, ROWBIAS, true>(acc, fx, cx.row_bias, cx.nvalid, o)
+                   : epi_chunk_fast<OUT, SLOPE, ROWBIAS, false>(acc, fx, cx.row_bias, cx.nvalid, o);
+    }
+    if (!done) epi_chunk<OUT, SLOPE, ROWBIAS>(acc, cx, o);
+    epi_store_chunk<OUT>(o, cx, optr, vec, fast);
+}
+
 template <int OUT>
-__device__ __forceinline__ void epi_dispatch(const uint32_t (&acc)[32], const EpiCtx &cx, void *optr, bool vec, bool slope, bool rb) {
-    if (slope) { if (rb) epi_chunk<OUT, true, true>(acc, cx, optr, vec); else epi_chunk<OUT, true, false>(acc, cx, optr, vec); }
-    else { if (rb) epi_chunk<OUT, false, true>(acc, cx, optr, vec); else epi_chunk<OUT, false, false>(acc, cx, optr, vec); }
+__device__ __forceinline__ void epi_dispatch(const uint32_t (&acc)[EC], const EpiCtx &cx, const FastCtx &fx, void *optr, bool vec,
+                                             bool slope, bool rb, bool fast, bool zp0) {
+    if (slope) {
+        if (rb) epi_one<OUT, true, true>(acc, cx, fx, optr, vec, fast, zp0);
+        else epi_one<OUT, true, false>(acc, cx, fx, optr, vec, fast, zp0);
+    } else {
+        if (rb) epi_one<OUT, false, true>(acc, cx, fx, optr, vec, fast, zp0);
+        else epi_one<OUT, false, false>(acc, cx, fx, optr, vec, fast, zp0);
+    }
 }
 
 // ---- floating-point epilogue (kind::f16 path): v = acc + bias; act; [+ residual; post act]; cast -------------
@@ -253,36 +404,32 @@ __device__ __forceinline__ float f_act(float v, int act, float slope) {
 __device__ __forceinline__ float f_load(const void *p, int64_t i, int t) {
     return t == 0 ? __half2float(((const __half *)p)[i]) : (t == 1 ? __bfloat162float(((const __nv_bfloat16 *)p)[i]) : ((const float *)p)[i]);
 }
-__device__ __forceinline__ void epi_chunk_f(const uint32_t (&acc)[32], const int2 *chan, const FEpi &fe, const void *res,
+__device__ __forceinline__ void epi_chunk_f(const uint32_t (&acc)[EC], const int2 *chan, const FEpi &fe, const void *res,
                                             void *optr, int nvalid, bool vec) {
-    float o[32];
+    float o[EC];
 #pragma unroll
-    for (int q = 0; q < 32; ++q) {
+    for (int q = 0; q < EC; ++q) {
         float v = __uint_as_float(acc[q]) + __int_as_float(chan[q].x);
         v = f_act(v, fe.act, fe.slope);
         if (res) v += f_load(res, q < nvalid ? q : 0, fe.out_type);
         o[q] = f_act(v, fe.post_act, fe.post_slope);
     }
-    if (vec && fe.out_type != 2) {
-        uint4 *dst = reinterpret_cast<uint4 *>(optr);
+    if (vec && fe.out_type != 2) {  // nvalid is a multiple of 8 here
+        uint32_t w[EC / 2];
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-            uint32_t w[4];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int q = h * 8 + t * 2;
-                if (fe.out_type == 0) { __half2 hv = __floats2half2_rn(o[q], o[q + 1]); w[t] = *reinterpret_cast<uint32_t *>(&hv); }
-                else { __nv_bfloat162 bv = __floats2bfloat162_rn(o[q], o[q + 1]); w[t] = *reinterpret_cast<uint32_t *>(&bv); }
-            }
-            dst[h] = make_uint4(w[0], w[1], w[2], w[3]);
+        for (int t = 0; t < EC / 2; ++t) {
+            if (fe.out_type == 0) { __half2 hv = __floats2half2_rn(o[2 * t], o[2 * t + 1]); w[t] = *reinterpret_cast<uint32_t *>(&hv); }
+            else { __nv_bfloat162 bv = __floats2bfloat162_rn(o[2 * t], o[2 * t + 1]); w[t] = *reinterpret_cast<uint32_t *>(&bv); }
         }
+        store_words<EC / 2>((char *)optr, w, nvalid * 2);
     } else if (vec) {
-        float4 *dst = reinterpret_cast<float4 *>(optr);
+        uint32_t w[EC];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) dst[t] = make_float4(o[4 * t], o[4 * t + 1], o[4 * t + 2], o[4 * t + 3]);
+        for (int t = 0; t < EC; ++t) w[t] = __float_as_uint(o[t]);
+        store_words<EC>((char *)optr, w, nvalid * 4);
     } else {
 #pragma unroll
-        for (int q = 0; q < 32; ++q) {
+        for (int q = 0; q < EC; ++q) {
             if (q < nvalid) {
                 if (fe.out_type == 0) ((__half *)optr)[q] = __float2half_rn(o[q]);
                 else if (fe.out_type == 1) ((__nv_bfloat16 *)optr)[q] = __float2bfloat16_rn(o[q]);
@@ -292,9 +439,11 @@ __device__ __forceinline__ void epi_chunk_f(const uint32_t (&acc)[32], const int
     }
 }
 
-constexpr int P_THREADS = 448;
-constexpr int P_EPI_WARPS = 8;
-constexpr int P_PROD_WARP0 = 8;
+constexpr int P_EPI_WARPS = 16;
+constexpr int P_PROD_WARP0 = P_EPI_WARPS;
+constexpr int P_TMA_WARP = P_PROD_WARP0 + 4;
+constexpr int P_MMA_WARP = P_TMA_WARP + 1;
+constexpr int P_THREADS = (P_MMA_WARP + 1) * 32;
 
 struct PMeta {  // per-tile metadata, double buffered
     uint32_t kmask;
@@ -305,7 +454,7 @@ template <int STAGES>
 struct PSmem {
     static size_t bytes(int n_tile, int rows_k) {
         return 1024 + (size_t)STAGES * (TC_M * TC_KB + (size_t)n_tile * TC_KB) + 2 * (size_t)rows_k * TC_M * 4 +
-               (size_t)n_tile * 8 + 512;
+               (size_t)n_tile * 20 + 512;
     }
 };
 
@@ -338,18 +487,21 @@ __global__ void __launch_bounds__(P_THREADS, 1) igemm_tc_persistent(TcArgs a, co
     uint8_t *sB = smem + STAGES * a_bytes;
     const int rows_k = MODE == 0 ? a.kvol : 2;
     int32_t *rows_s = (int32_t *)(sB + (size_t)STAGES * b_bytes);  // [2 slots][rows_k][128]
-    int2 *chan_s = (int2 *)(rows_s + 2 * rows_k * TC_M);          // [n_tile] (bias, mul) of the current channel block
-    uint64_t *bars = (uint64_t *)(chan_s + a.n_tile);
+    int4 *chan4_s = (int4 *)(rows_s + 2 * rows_k * TC_M);         // [n_tile] (bias, mul, B, -B) of the current channel block
+    int2 *chan_s = (int2 *)chan4_s;                               // float kinds: (bias bits, 0)
+    int32_t *thr_s = (int32_t *)(chan4_s + a.n_tile);             // [n_tile] sign threshold of the fast epilogue
+    uint64_t *bars = (uint64_t *)(thr_s + a.n_tile);
     uint64_t *full = bars, *empty = bars + STAGES;
     uint64_t *meta_full = bars + 2 * STAGES, *tmem_full = meta_full + 2, *tmem_empty = tmem_full + 2;
     PMeta *meta = (PMeta *)(tmem_empty + 2);
     uint32_t *tmem_ptr = (uint32_t *)(meta + 2);
+    uint32_t *fast_off = tmem_ptr + 1;  // set once a staged channel block fails the fast-epilogue preconditions
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_chunks = (a.K + TC_KB - 1) / TC_KB;
     const int total_tiles = tiles_m * tiles_n;
 
-    if (warp == 13 && lane == 0) {
+    if (warp == P_MMA_WARP && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full[s], TC_M + 1);
             mbar_init(&empty[s], 1);
@@ -361,17 +513,26 @@ __global__ void __launch_bounds__(P_THREADS, 1) igemm_tc_persistent(TcArgs a, co
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 12 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
-    if (warp == 13) {
+    if (warp == P_TMA_WARP && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+    if (warp == P_MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"((uint32_t)(2 * a.tmem_cols)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     // per-channel epilogue constants of a single channel block are staged once (grouped weights reload per tile)
     const bool chan_static = tiles_n == 1 && !(MODE == 1 && a.bias_per_group);
+    const int64_t zp_all = KIND == 0 ? ep.zp[0] : 0;
+    const bool fast_uni = KIND == 0 && !(a.dbg & 16) && fast_uniform_ok(ep, ep.out_type, zp_all, (int64_t)a.K * (MODE == 0 ? a.kvol : 1));
+    if (tid == 0) *fast_off = fast_uni ? 0u : 1u;
+    __syncthreads();
     if (chan_static)
         for (int c = tid; c < a.n_tile; c += P_THREADS) {
-            if (KIND == 0) chan_s[c] = c < a.N ? make_int2(ep.bias ? ep.bias[c] : 0, (int)ep.mul[ep.mul_is_scalar ? 0 : c]) : make_int2(0, 0);
-            else chan_s[c] = make_int2(c < a.N && fe.bias ? __float_as_int(fe.bias[c]) : 0, 0);
+            if (KIND == 0) {
+                const int32_t b = c < a.N && ep.bias ? ep.bias[c] : 0;
+                const uint32_t mu = c < a.N ? ep.mul[ep.mul_is_scalar ? 0 : c] : 0u;
+                if (!fast_channel(b, mu, zp_all, ep.shift, ep.out_type, &chan4_s[c], &thr_s[c]) && fast_uni) atomicOr(fast_off, 1u);
+            } else {
+                chan_s[c] = make_int2(c < a.N && fe.bias ? __float_as_int(fe.bias[c]) : 0, 0);
+            }
         }
     tc_fence_before();
     __syncthreads();
@@ -381,10 +542,20 @@ __global__ void __launch_bounds__(P_THREADS, 1) igemm_tc_persistent(TcArgs a, co
     if (warp >= P_PROD_WARP0 && warp < P_PROD_WARP0 + 4) {
         // ================= metadata + gather producers =================
         const int r = tid - P_PROD_WARP0 * 32;
-        const uint32_t row_smem = r * TC_KB, sw = r & 7;
         int it = 0;       // running pipeline step across tiles
-        int arrived = 0;  // steps [0, arrived) have been published on their full barrier
         int j = 0;        // local tile counter
+        // The neighbour rows of a tile are fetched one tile ahead into registers: the 27 dependent-latency loads
+        // overlap the previous tile's gathers instead of stalling the pipeline at every tile boundary.
+        constexpr int PRE = 27;
+        int32_t nv[PRE];
+        const bool pre = MODE == 0 && a.kvol <= PRE;
+        auto fetch = [&](int t) {
+            const int m = (t / tiles_n) * TC_M + r;
+            const bool ok = t < total_tiles && m < a.n_out;
+#pragma unroll
+            for (int u = 0; u < PRE; ++u) nv[u] = (ok && u < a.kvol) ? __ldg(&a.nbr[(int64_t)u * a.ld + m]) : 0;
+        };
+        if (pre) fetch(blockIdx.x);
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
             const int slot = j & 1;
             const int tile_m = tile / tiles_n;
@@ -395,10 +566,20 @@ __global__ void __launch_bounds__(P_THREADS, 1) igemm_tc_persistent(TcArgs a, co
             if (MODE == 0) {
                 const int m = tile_m * TC_M + r;
                 uint32_t mine = 0;
-                for (int k = 0; k < a.kvol; ++k) {
-                    int32_t v = m < a.n_out ? __ldg(&a.nbr[(int64_t)k * a.ld + m]) : 0;
-                    rows[k * TC_M + r] = v - 1;
-                    mine |= (uint32_t)(v != 0) << k;
+                if (pre) {
+#pragma unroll
+                    for (int u = 0; u < PRE; ++u)
+                        if (u < a.kvol) {
+                            rows[u * TC_M + r] = nv[u] - 1;
+                            mine |= (uint32_t)(nv[u] != 0) << u;
+                        }
+                    fetch(tile + gridDim.x);
+                } else {
+                    for (int k = 0; k < a.kvol; ++k) {
+                        int32_t v = m < a.n_out ? __ldg(&a.nbr[(int64_t)k * a.ld + m]) : 0;
+                        rows[k * TC_M + r] = v - 1;
+                        mine |= (uint32_t)(v != 0) << k;
+                    }
                 }
                 mine = __reduce_or_sync(0xffffffffu, mine);
                 if (lane == 0 && mine) atomicOr(&meta[slot].kmask, mine);
@@ -416,36 +597,37 @@ __global__ void __launch_bounds__(P_THREADS, 1) igemm_tc_persistent(TcArgs a, co
             mbar_wait(&meta_full[slot], (j >> 1) & 1);
             uint32_t rem = meta[slot].kmask;
             const int total = __popc(rem) * n_chunks;
-            int k = 0;
+            int k = 0, kc = n_chunks - 1;
             for (int i = 0; i < total; ++i, ++it) {
-                const int kc = i % n_chunks;
-                if (kc == 0) { k = __ffs(rem) - 1; rem &= rem - 1; }
+                if (++kc == n_chunks) { kc = 0; k = __ffs(rem) - 1; rem &= rem - 1; }
                 const int stage = it % STAGES;
                 mbar_wait(&empty[stage], ((it / STAGES) & 1) ^ 1);
-                const int32_t src = rows[(MODE == 0 ? k : 0) * TC_M + r];
-                const int8_t *gsrc = a.A + (src >= 0 ? (int64_t)src * a.K : 0) + kc * TC_KB;
-                const uint32_t dst = smem_u32(sA + stage * a_bytes) + row_smem;
+                // 8 consecutive lanes fetch the 8 16-byte pieces of ONE row (a full 128-byte line), 4 rows per
+                // instruction: 4 L1 wavefronts per LDGSTS instead of 32 with one row per lane.
+                // This lane serves rows base..base+7 (two 16-byte shared loads fetch their source rows).
+                const int base = (r & ~31) + (lane >> 3) * 8;
+                const uint32_t rk = smem_u32(rows + (MODE == 0 ? k : 0) * TC_M + base);
+                const int4 s0 = lds128(rk), s1 = lds128(rk + 16);
+                const int32_t srcs[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                const int piece = lane & 7;
+                const bool k_ok = kc * TC_KB + piece * 16 < a.K;
+                const uint32_t dst0 = smem_u32(sA + stage * a_bytes);
                 if (!(a.dbg & 1)) {
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const bool ok = src >= 0 && kc * TC_KB + c * 16 < a.K;
-                        cp_async16(dst + ((c ^ sw) << 4), ok ? (const void *)(gsrc + c * 16) : (const void *)a.A, ok ? 16u : 0u);
+                    for (int i = 0; i < 8; ++i) {
+                        const int32_t src = srcs[i];
+                        const int row = base + i;
+                        const bool ok = src >= 0 && k_ok;
+                        const int8_t *gsrc = a.A + (ok ? (int64_t)src * a.K + kc * TC_KB + piece * 16 : 0);
+                        cp_async16(dst0 + row * TC_KB + ((piece ^ (row & 7)) << 4), gsrc, ok ? 16u : 0u);
                     }
                 }
-                cp_async_commit();
-                if (it - arrived >= STAGES - 1) {  // keep at most STAGES-1 steps in flight per thread
-                    cp_async_wait<STAGES - 1>();
-                    fence_proxy_async();
-                    for (; arrived <= it - (STAGES - 1); ++arrived) mbar_arrive(&full[arrived % STAGES]);
-                }
+                // The stage's full barrier is signalled by the copy engine itself once this thread's copies have
+                // landed (no commit/wait lag in the producer): all STAGES stages can be in flight or queued.
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full[stage])) : "memory");
             }
-            // Publish the tail of this tile before blocking on the next tile's accumulator: the MMAs of this
-            // tile (and through them the epilogue that frees that accumulator) wait for these arrivals.
-            cp_async_wait<0>();
-            fence_proxy_async();
-            for (; arrived < it; ++arrived) mbar_arrive(&full[arrived % STAGES]);
         }
-    } else if (warp == 12) {
+    } else if (warp == P_TMA_WARP) {
         // ================= weight producer (TMA) =================
         if (lane == 0) {
             int it = 0, j = 0;
@@ -456,10 +638,9 @@ __global__ void __launch_bounds__(P_THREADS, 1) igemm_tc_persistent(TcArgs a, co
                 uint32_t rem = meta[slot].kmask;
                 const int total = __popc(rem) * n_chunks;
                 const int group = MODE == 1 ? meta[slot].group : 0;
-                int k = 0;
+                int k = 0, kc = n_chunks - 1;
                 for (int i = 0; i < total; ++i, ++it) {
-                    const int kc = i % n_chunks;
-                    if (kc == 0) { k = __ffs(rem) - 1; rem &= rem - 1; }
+                    if (++kc == n_chunks) { kc = 0; k = __ffs(rem) - 1; rem &= rem - 1; }
                     const int stage = it % STAGES;
                     mbar_wait(&empty[stage], ((it / STAGES) & 1) ^ 1);
                     if (a.dbg & 2) { mbar_arrive(&full[stage]); continue; }
@@ -469,7 +650,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) igemm_tc_persistent(TcArgs a, co
                 }
             }
         }
-    } else if (warp == 13) {
+    } else if (warp == P_MMA_WARP) {
         // ================= MMA issuer =================
         if (lane == 0) {
             const uint32_t idesc = KIND == 0 ? umma_idesc_i8(a.n_tile) : umma_idesc_f16(a.n_tile, KIND == 2);
@@ -484,6 +665,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) igemm_tc_persistent(TcArgs a, co
                 for (int i = 0; i < total; ++i, ++it) {
                     const int stage = it % STAGES;
                     mbar_wait(&full[stage], (it / STAGES) & 1);
+                    fence_proxy_async();  // the gathered rows were written through the generic proxy (cp.async)
                     tc_fence_after();
                     const uint64_t ad = umma_desc_sw128(smem_u32(sA + stage * a_bytes));
                     const uint64_t bd = umma_desc_sw128(smem_u32(sB + (size_t)stage * b_bytes));
@@ -502,14 +684,15 @@ __global__ void __launch_bounds__(P_THREADS, 1) igemm_tc_persistent(TcArgs a, co
         }
     } else if (warp < P_EPI_WARPS) {
         // ================= epilogue =================
-        const int quarter = warp & 3, half = warp >> 2;
+        const int quarter = warp & 3, group = warp >> 2;  // TMEM lane quarter, column group (4 groups of 4 warps)
         const int r = quarter * 32 + lane;  // tile row == TMEM lane
         const bool has_slope = KIND == 0 && ep.slope != nullptr, has_post = KIND == 0 && ep.post_slope != nullptr;
         const int32_t slope = has_slope ? ep.slope[0] : 0, post = has_post ? ep.post_slope[0] : 0;
         const int64_t zp = KIND == 0 ? ep.zp[0] : 0;
         const int shift = ep.shift;
-        const int cols_half = ((a.n_tile / 2 + 31) / 32) * 32;  // columns per half, multiple of 32
-        const int c_begin = half * cols_half, c_end = min(a.n_tile, c_begin + cols_half);
+        const int cols_grp = ((a.n_tile / (P_EPI_WARPS / 4) + EC - 1) / EC) * EC;  // columns per group, multiple of EC
+        const int c_begin = min(a.n_tile, group * cols_grp), c_end = min(a.n_tile, c_begin + cols_grp);
+        const bool out_al = ((uintptr_t)out & 15) == 0;
         int j = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
             const int slot = j & 1;
@@ -518,54 +701,65 @@ __global__ void __launch_bounds__(P_THREADS, 1) igemm_tc_persistent(TcArgs a, co
             const bool have_acc = meta[slot].kmask != 0;
             const int pbase = (MODE == 1 && a.bias_per_group) ? meta[slot].group * a.N : 0;
             if (!chan_static) {  // grouped weights / several channel blocks: restage (bias, mul) of this tile's block
-                asm volatile("bar.sync 2, 256;" ::: "memory");  // every epilogue warp is done with the previous tile's values
+                asm volatile("bar.sync 2, 512;" ::: "memory");  // every epilogue warp is done with the previous tile's values
                 const int t = warp * 32 + lane;
                 if (t < a.n_tile) {
                     const int pc = pbase + min(n0 + t, a.N - 1);
-                    if (KIND == 0) chan_s[t] = make_int2(ep.bias ? __ldg(&ep.bias[pc]) : 0, (int)__ldg(&ep.mul[ep.mul_is_scalar ? 0 : pc]));
-                    else chan_s[t] = make_int2(fe.bias ? __float_as_int(__ldg(&fe.bias[pc])) : 0, 0);
+                    if (KIND == 0) {
+                        const int32_t b = ep.bias ? __ldg(&ep.bias[pc]) : 0;
+                        const uint32_t mu = __ldg(&ep.mul[ep.mul_is_scalar ? 0 : pc]);
+                        if (!fast_channel(b, mu, zp_all, ep.shift, ep.out_type, &chan4_s[t], &thr_s[t]) && fast_uni) atomicOr(fast_off, 1u);
+                    } else {
+                        chan_s[t] = make_int2(fe.bias ? __float_as_int(__ldg(&fe.bias[pc])) : 0, 0);
+                    }
                 }
-                asm volatile("bar.sync 2, 256;" ::: "memory");
+                asm volatile("bar.sync 2, 512;" ::: "memory");
             }
+            const bool fast = KIND == 0 && *(volatile uint32_t *)fast_off == 0u;
             const int32_t *rows = rows_s + slot * rows_k * TC_M;
             const int64_t m = MODE == 0 ? (int64_t)tile_m * TC_M + r : (int64_t)rows[TC_M + r];
             const bool row_ok = MODE == 0 ? (m < a.n_out) : (m >= 0);
             mbar_wait(&tmem_full[slot], (j >> 1) & 1);
             tc_fence_after();
             const uint32_t tacc = tmem_base + (uint32_t)(slot * a.tmem_cols) + ((uint32_t)(quarter * 32) << 16);
-            for (int c0 = c_begin; c0 < c_end; c0 += 32) {
-                uint32_t acc[32];
+            for (int c0 = c_begin; c0 < c_end; c0 += EC) {
+                uint32_t acc[EC];
                 if (have_acc) {
-                    tmem_ld32(tacc + (uint32_t)c0, acc);
+                    tmem_ld16(tacc + (uint32_t)c0, acc);
                 } else {
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) acc[q] = 0;
+                    for (int q = 0; q < EC; ++q) acc[q] = 0;
                 }
                 const int nb = n0 + c0;
                 if (!row_ok || nb >= a.N) continue;
                 if (a.dbg & 4) { if (c0 == 0) ((int32_t *)out)[m] = (int32_t)acc[0]; continue; }
                 if (KIND != 0) {
                     const int esz = fe.out_type == 2 ? 4 : 2;
-                    const int nvalid = min(32, a.N - nb);
+                    const int nvalid = min(EC, a.N - nb);
                     const void *res = fe.residual ? (const char *)fe.residual + (m * a.N + nb) * esz : nullptr;
                     epi_chunk_f(acc, chan_s + c0, fe, res, (char *)out + (m * a.N + nb) * esz, nvalid,
-                                nvalid == 32 && (a.N & 7) == 0);
+                                out_al && (a.N & 7) == 0);
                     continue;
                 }
                 EpiCtx cx;
-                cx.chan = chan_s + c0;
+                cx.chan = nullptr; cx.chan4 = chan4_s + c0;
                 cx.slope = slope; cx.post = post; cx.zp = zp; cx.shift = shift;
                 cx.half = shift > 0 ? (int64_t)1 << (shift - 1) : 0; cx.sgn = shift > 0;
                 cx.row_bias = ep.row_bias ? ep.row_bias + (int64_t)__ldg(&ep.row_idx[m]) * a.N + nb : nullptr;
                 cx.residual = ep.residual ? ep.residual + m * a.N + nb : nullptr;
                 cx.has_post = has_post;
-                cx.nvalid = min(32, a.N - nb);
+                cx.nvalid = min(EC, a.N - nb);
+                FastCtx fx;
+                fx.chan = smem_u32(chan4_s + c0); fx.thr = smem_u32(thr_s + c0); fx.slope = slope; fx.post = post; fx.shift = shift;
+                const int64_t c0v = zp + cx.half;
+                fx.c0_lo = (uint32_t)c0v; fx.c0_hi = (uint32_t)((uint64_t)c0v >> 32);
+                fx.ovf_add = shift > 0 ? 1u << (shift - 1) : 0u; fx.ovf_lim = 1u << (shift & 31);
                 void *optr = (char *)out + (m * a.N + nb) * (ep.out_type == FPCC_OUT_I8 ? 1 : (ep.out_type == FPCC_OUT_I16 ? 2 : 4));
-                const bool vec = cx.nvalid == 32 && (a.N & 15) == 0;
+                const bool vec = out_al && (a.N & 15) == 0;
                 const bool rb = ep.row_bias != nullptr;
-                if (ep.out_type == FPCC_OUT_I8) epi_dispatch<FPCC_OUT_I8>(acc, cx, optr, vec, has_slope, rb);
-                else if (ep.out_type == FPCC_OUT_I32) epi_dispatch<FPCC_OUT_I32>(acc, cx, optr, vec, has_slope, rb);
-                else epi_dispatch<FPCC_OUT_I16>(acc, cx, optr, false, has_slope, rb);
+                if (ep.out_type == FPCC_OUT_I8) epi_dispatch<FPCC_OUT_I8>(acc, cx, fx, optr, vec, has_slope, rb, fast, zp == 0);
+                else if (ep.out_type == FPCC_OUT_I32) epi_dispatch<FPCC_OUT_I32>(acc, cx, fx, optr, vec, has_slope, rb, fast, zp == 0);
+                else epi_dispatch<FPCC_OUT_I16>(acc, cx, fx, optr, vec, has_slope, rb, fast, zp == 0);
             }
             tc_fence_before();
             __syncwarp();
@@ -574,7 +768,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) igemm_tc_persistent(TcArgs a, co
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 13) {
+    if (warp == P_MMA_WARP) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * a.tmem_cols)) : "memory");
     }
 }
@@ -685,6 +879,23 @@ static int pick_tile(int N, int *n_tile, int *tmem_cols) {
     return (N + nt - 1) / nt;
 }
 
+constexpr size_t TC_SMEM_MAX = 227 * 1024;
+template <int MODE, int STAGES, int KIND>
+static int launch_stages(const TcArgs &a, const CUtensorMap &tmap, const EpiParams &ep, const FEpi &fe, void *out, int tiles_m,
+                         int n_blocks_n, int grid, int rows_k, cudaStream_t s) {
+    size_t smem = PSmem<STAGES>::bytes(a.n_tile, rows_k);
+    FPCC_REQUIRE(smem <= TC_SMEM_MAX, "igemm_tc: %zu bytes of shared memory exceed the 227 KB limit", smem);
+    auto kern = igemm_tc_persistent<MODE, STAGES, KIND>;
+    static bool configured = false;
+    if (!configured) {
+        FPCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX));
+        configured = true;
+    }
+    kern<<<grid, P_THREADS, smem, s>>>(a, tmap, ep, fe, out, tiles_m, n_blocks_n);
+    FPCC_LAUNCH_CHECK();
+    return FPCC_OK;
+}
+
 template <int MODE, int KIND>
 static int launch_tc(TcArgs &a, const void *W, int64_t w_rows, int tiles_m, const EpiParams &ep, const FEpi &fe, void *out,
                      cudaStream_t s) {
@@ -693,22 +904,13 @@ static int launch_tc(TcArgs &a, const void *W, int64_t w_rows, int tiles_m, cons
     CUtensorMap tmap;
     int rc = weight_tensor_map((const int8_t *)W, w_rows, a.K, a.n_tile, &tmap);
     if (rc) return rc;
-    constexpr int STAGES = 4;
     const int rows_k = MODE == 0 ? a.kvol : 2;
-    size_t smem = PSmem<STAGES>::bytes(a.n_tile, rows_k);
-    FPCC_REQUIRE(smem <= 227 * 1024, "igemm_tc: %zu bytes of shared memory exceed the 227 KB limit", smem);
-    auto kern = igemm_tc_persistent<MODE, STAGES, KIND>;
-    static bool configured = false;
-    if (!configured) {
-        FPCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = true;
-    }
     int total = tiles_m * n_blocks_n;
     int sms = g_sm_budget > 0 && g_sm_budget < sm_count() ? g_sm_budget : sm_count();
     int grid = total < sms ? total : sms;
-    kern<<<grid, P_THREADS, smem, s>>>(a, tmap, ep, fe, out, tiles_m, n_blocks_n);
-    FPCC_LAUNCH_CHECK();
-    return FPCC_OK;
+    if (PSmem<4>::bytes(a.n_tile, rows_k) <= TC_SMEM_MAX)
+        return launch_stages<MODE, 4, KIND>(a, tmap, ep, fe, out, tiles_m, n_blocks_n, grid, rows_k, s);
+    return launch_stages<MODE, 3, KIND>(a, tmap, ep, fe, out, tiles_m, n_blocks_n, grid, rows_k, s);
 }
 
 int launch_conv_tc(const int8_t *feats, int n_in, int c_in, const int8_t *weight, int kvol, int c_out, const int32_t *nbr,

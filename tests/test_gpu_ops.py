@@ -163,6 +163,61 @@ def test_linear_and_gemm(ops, m, k, n):
     assert (d.cpu().numpy() == K.gemm_int8(a, w, None)).all()
 
 
+def test_epilogue_ranges_fast_and_wide_paths(ops):
+    """The tcgen05 epilogue has a 32-bit fast path guarded by range preconditions and a 64-bit general path: sweep
+    shifts, multipliers up to 2^32, large biases, huge zero points, slopes outside [0, 1] and every output type so
+    that both paths and the per-chunk fall-back are compared with the oracle (bias_prelu_requant.cu:6-37)."""
+    rng = np.random.default_rng(7)
+    m, k, n = 300, 64, 96
+    a = rng.integers(-128, 128, (m, k)).astype(np.int8)
+    w = rng.integers(-127, 128, (n, k)).astype(np.int8)
+    acc0 = K.gemm_int8(a, w, None)
+    assert ops.gemm_engine(k, n) == 'tc'
+    cases = 0
+    for trial in range(72):
+        out_t, np_t = [(ops.OUT_I8, np.int8), (ops.OUT_I16, np.int16), (ops.OUT_I32, np.int32)][trial % 3]
+        shift = int(rng.integers(0, 32))
+        mul_hi = [1 << 8, 1 << 20, (1 << 31) - 1, (1 << 32) - 1][int(rng.integers(0, 4))]
+        mul = rng.integers(0, mul_hi, n, endpoint=True).astype(np.uint32)
+        if trial % 5 == 0:
+            mul[::7] = 0
+        bias_hi = [1000, 1 << 20, 1 << 29, (1 << 31) - 1][int(rng.integers(0, 4))]
+        bias = rng.integers(-bias_hi, bias_hi, n, endpoint=True).astype(np.int32)
+        zp = np.array([[0, 0, 1, -1, 3 << shift, -(5 << shift), (1 << 40) + 12345, -(1 << 45)][int(rng.integers(0, 8))]], np.int64)
+        slope = [None, None, 0, 1 << 25, int(0.2 * (1 << 25)), -(1 << 23), 3 << 25][int(rng.integers(0, 7))]
+        slope = None if slope is None else np.array([slope], np.int32)
+        want = K.requant(acc0, mul, zp, shift, np_t, bias=bias, slope=slope)
+        ep = ops.make_epilogue(dev(mul), dev(zp), shift, out_t, bias=dev(bias), slope=None if slope is None else dev(slope))
+        got = ops.linear(dev(a), dev(w), ep).cpu().numpy()
+        assert got.dtype == np_t and (got == want).all(), (trial, shift, mul_hi, bias_hi, int(zp[0]), slope)
+        cases += 1
+    # occupancy row bias with entries large enough to leave the proven range (per-chunk fall-back) + residual / post PReLU
+    table = rng.integers(-(1 << 31), (1 << 31) - 1, (256, n), endpoint=True).astype(np.int32)
+    table[:128] >>= 9
+    idx = rng.integers(0, 256, m).astype(np.uint8)
+    mul = rng.integers(1 << 10, 1 << 22, n).astype(np.uint32)
+    bias = rng.integers(-(1 << 28), 1 << 28, n).astype(np.int32)
+    for out_t, np_t, shift in [(ops.OUT_I8, np.int8, 20), (ops.OUT_I32, np.int32, 9)]:
+        for zpv in (0, 77777):
+            zp = np.array([zpv], np.int64)
+            slope = np.array([int(0.3 * (1 << 25))], np.int32)
+            accb = (acc0.astype(np.int64) + table[idx].astype(np.int64)).astype(np.int32)  # int32 add wraps
+            want = K.requant(accb, mul, zp, shift, np_t, bias=bias, slope=slope)
+            ep = ops.make_epilogue(dev(mul), dev(zp), shift, out_t, bias=dev(bias), slope=dev(slope), row_bias=(dev(table), dev(idx)))
+            got = ops.linear(dev(a), dev(w), ep).cpu().numpy()
+            assert (got == want).all(), (out_t, zpv)
+    res = rng.integers(-(1 << 31), (1 << 31) - 1, (m, n), endpoint=True).astype(np.int32)
+    for post_v in (int(0.25 * (1 << 25)), -(1 << 24), 5 << 25):
+        post = np.array([post_v], np.int32)
+        zp = np.zeros(1, np.int64)
+        y = K.requant(acc0, mul, zp, 3, np.int32, bias=bias)
+        want = K.prelu((y.astype(np.int64) + res.astype(np.int64)).astype(np.int32), post)
+        ep = ops.make_epilogue(dev(mul), dev(zp), 3, ops.OUT_I32, bias=dev(bias), residual=dev(res), post_slope=dev(post))
+        got = ops.linear(dev(a), dev(w), ep).cpu().numpy()
+        assert (got == want).all(), post_v
+    assert cases == 72
+
+
 def test_selected_linear_equals_masked_dense(ops):
     """Linear(C->8C) + child mask (model.py:64-66) == occupied-children-only evaluation."""
     rng = np.random.default_rng(4)

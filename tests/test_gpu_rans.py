@@ -72,3 +72,37 @@ def test_truncated_stream_is_reported():
     out = np.zeros_like(sym)
     with pytest.raises(RuntimeError):
         dec.decode(cdf, out)
+
+
+def test_lossy_heads_match_oracle_and_roundtrip():
+    """geo_lossl_em.py:59-114: sigmoid -> 16-bit P(1) -> binary rANS; histogram-CDF residual stream layout."""
+    import io
+    from fastpcc_b200 import lossy_heads as H
+    g = torch.Generator(device='cuda').manual_seed(0)
+    logit = (torch.randn((50000, 1), generator=g, device='cuda') * 4).half()
+    x = (torch.rand(50000, generator=g, device='cuda') < logit.float().sigmoid().reshape(-1))
+    prob = np.clip(np.round(logit.sigmoid().cpu().numpy().astype(np.float64) * 65536).astype(np.uint32), 1, 65535).reshape(1, -1)
+    assert (H.init_prob(logit).cpu().numpy().astype(np.uint32) == prob.reshape(-1)).all()
+    want = orans.BinaryRansCoder(1).encode(x.cpu().numpy().reshape(1, -1), prob)[0]
+    data = H.binary_encode(logit, x)
+    assert data == want
+    assert torch.equal(H.binary_decode(logit, data), x)
+    rng = np.random.default_rng(1)
+    t = np.round(np.clip(rng.normal(0, 3, (4000, 2)), -20, 20)).astype(np.int32)
+    bs = io.BytesIO()
+    H.rans_encode_with_cdf(t, bs)
+    ref = io.BytesIO()
+    # the same layout through the oracle coder
+    ref.write((4000).to_bytes(3, 'little')); off = int(t.min()); ref.write((-off).to_bytes(1, 'little'))
+    oc = orans.IndexedRansCoder(False, 1)
+    oc.init_with_pmfs(np.bincount((t - off).reshape(-1)).astype(np.float64)[None], np.array([off], np.int32))
+    cdf = oc.get_cdfs()[0]
+    ref.write((len(cdf) - 2).to_bytes(1, 'little'))
+    for cd in cdf[1:-1]:
+        ref.write(int(cd).to_bytes(2, 'little'))
+    payload = oc.encode(t.reshape(1, -1))[0]
+    ref.write(len(payload).to_bytes(3, 'little')); ref.write(payload)
+    assert bs.getvalue() == ref.getvalue()
+    bs.seek(0)
+    back, cdf2 = H.rans_decode_with_cdf(bs, channels=2)
+    assert (back == t).all() and cdf2 == cdf
