@@ -49,8 +49,8 @@ SIGNATURES = {
     'fpcc_mma_i8_peak': (_i, [_i, _i, _vp, _vp]),
     'fpcc_gemm_engine': (_i, [_i, _i, _i, _i]),
     'fpcc_softmax_i32': (_i, [_vp, _i64, _i, _vp, _vp]),
-    'fpcc_quantize_cdf': (_i, [_vp, _i64, _i, _vp, _i, _vp]),
-    'fpcc_cdf_symbol_ranges': (_i, [_vp, _i64, _i, _vp, _vp, _vp]),
+    'fpcc_quantize_cdf': (_i, [_vp, _i64, _i64, _i, _vp, _i, _vp]),
+    'fpcc_cdf_symbol_ranges': (_i, [_vp, _i64, _i64, _i, _vp, _vp, _vp]),
     'fpcc_table_symbol_ranges': (_i, [_vp, _i64, _i, _vp, _i64, _vp, _vp]),
     'fpcc_rans_encode': (_i, [_vp, _vp, _vp, _i, _i64, _vp, _i64, _vp, _vp, _i, _vp, _sz, _vp]),
     'fpcc_rans_dec_init': (_i, [_vp, _vp, _vp, _vp, _i, _vp]),

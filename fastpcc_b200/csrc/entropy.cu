@@ -59,12 +59,12 @@ __global__ void __launch_bounds__(256) softmax_kernel(const int32_t *__restrict_
 // MODE 0: write the inclusive uint16 CDF (pitch ld, pad entries = 0xFFFF);  MODE 1: write the packed
 // range start | (freq-1)<<16 of symbols[r].
 template <int MODE>
-__global__ void __launch_bounds__(256) cdf_kernel(const int32_t *__restrict__ logits, int64_t rows, int S,
+__global__ void __launch_bounds__(256) cdf_kernel(const int32_t *__restrict__ logits, int64_t logits_ld, int64_t rows, int S,
                                                   uint16_t *__restrict__ cdf, int ld, const int32_t *__restrict__ symbols,
                                                   uint32_t *__restrict__ ranges) {
     int lane = threadIdx.x & 31;
     for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * 8) {
-        const int32_t *row = logits + r * S;
+        const int32_t *row = logits + r * logits_ld;
         RowStat st = row_stat(row, S, 7, lane);
         uint32_t running = 0;
         int sym = MODE == 1 ? symbols[r] : 0;
@@ -128,19 +128,21 @@ extern "C" int fpcc_softmax_i32(const int32_t *in, int64_t rows, int c, uint32_t
     return FPCC_OK;
 }
 
-extern "C" int fpcc_quantize_cdf(const int32_t *logits, int64_t rows, int s, uint16_t *cdf, int ld, void *stream) {
+extern "C" int fpcc_quantize_cdf(const int32_t *logits, int64_t logits_ld, int64_t rows, int s, uint16_t *cdf, int ld, void *stream) {
     FPCC_REQUIRE(logits && cdf, "quantize_cdf: NULL pointer");
+    FPCC_REQUIRE(logits_ld >= s, "quantize_cdf: logits pitch %lld < s = %d", (long long)logits_ld, s);
     FPCC_REQUIRE(rows > 0 && s > 1 && s < 65536 && ld >= s, "quantize_cdf: bad sizes");
-    cdf_kernel<0><<<row_grid(rows), 256, 0, (cudaStream_t)stream>>>(logits, rows, s, cdf, ld, nullptr, nullptr);
+    cdf_kernel<0><<<row_grid(rows), 256, 0, (cudaStream_t)stream>>>(logits, logits_ld, rows, s, cdf, ld, nullptr, nullptr);
     FPCC_LAUNCH_CHECK();
     return FPCC_OK;
 }
 
-extern "C" int fpcc_cdf_symbol_ranges(const int32_t *logits, int64_t rows, int s, const int32_t *symbols,
+extern "C" int fpcc_cdf_symbol_ranges(const int32_t *logits, int64_t logits_ld, int64_t rows, int s, const int32_t *symbols,
                                       uint32_t *ranges, void *stream) {
     FPCC_REQUIRE(logits && symbols && ranges, "cdf_symbol_ranges: NULL pointer");
+    FPCC_REQUIRE(logits_ld >= s, "cdf_symbol_ranges: logits pitch %lld < s = %d", (long long)logits_ld, s);
     FPCC_REQUIRE(rows > 0 && s > 1 && s < 65536, "cdf_symbol_ranges: bad sizes");
-    cdf_kernel<1><<<row_grid(rows), 256, 0, (cudaStream_t)stream>>>(logits, rows, s, nullptr, 0, symbols, ranges);
+    cdf_kernel<1><<<row_grid(rows), 256, 0, (cudaStream_t)stream>>>(logits, logits_ld, rows, s, nullptr, 0, symbols, ranges);
     FPCC_LAUNCH_CHECK();
     return FPCC_OK;
 }

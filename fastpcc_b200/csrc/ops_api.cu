@@ -58,6 +58,61 @@ __global__ void __launch_bounds__(256) requant_vec4_kernel(const int4 *__restric
     }
 }
 
+// RequantFxpToScaledInt8 between layers: ONE multiplier, no bias, no PReLU, int8 out.  16 elements per thread per
+// step (four 16-byte loads in flight, one 16-byte store) and, when the ranges allow it, exact 32-bit arithmetic:
+// v is first clamped to [-B, B] with B the smallest magnitude that already saturates int8, so v*mul + zp fits a
+// 64-bit accumulator whose shifted value fits 32 bits; "t < 0" is decided as v < thr = ceil(-zp / mul).
+__global__ void __launch_bounds__(256) requant_scalar_i8_kernel(const int4 *__restrict__ in, int64_t total16, EpiParams ep,
+                                                                uint4 *__restrict__ out) {
+    const int64_t zp = ep.zp[0];
+    const uint32_t mul = ep.mul[0];
+    const int shift = ep.shift;
+    const int64_t half = shift > 0 ? (int64_t)1 << (shift - 1) : 0;
+    const int64_t c0 = zp + half;
+    const int64_t azp = zp < 0 ? -zp : zp;
+    bool fast = shift <= 31 && mul < (1u << 31) && (uint32_t)c0 != 0u && azp < ((int64_t)1 << 60);
+    int32_t B = 0, thr = 0;
+    if (fast) {
+        const int64_t num = ((int64_t)129 << shift) + azp;
+        int64_t b = mul ? (num + (int64_t)mul - 1) / (int64_t)mul : 0;
+        fast = b <= 2147483646ll;  // inputs span all of int32 here: the clamp must not bind below saturation
+        fast = fast && ((num + (int64_t)mul + azp + ((int64_t)1 << 31)) >> shift) < 2147483647ll;
+        int64_t t;
+        if (mul == 0) t = zp < 0 ? 2147483647ll : -2147483648ll;
+        else { const int64_t nz = -zp, m = (int64_t)mul; t = nz >= 0 ? (nz + m - 1) / m : -((-nz) / m); }
+        t = t > 2147483647ll ? 2147483647ll : (t < -2147483648ll ? -2147483648ll : t);
+        B = (int32_t)b; thr = (int32_t)t;
+    }
+    const uint32_t c_lo = (uint32_t)c0, c_hi = (uint32_t)((uint64_t)c0 >> 32);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total16; i += (int64_t)gridDim.x * blockDim.x) {
+        int4 v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = __ldg(&in[4 * i + q]);
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int32_t a[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+            int32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (fast) {
+                    const int32_t x = max(min(a[e], B), -B);
+                    const int64_t c = (int64_t)(((uint64_t)c_hi << 32) | (uint64_t)(c_lo - (x < thr ? 1u : 0u)));
+                    int64_t t;
+                    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(t) : "r"(x), "r"((int32_t)mul), "l"(c));
+                    const int32_t r = (int32_t)__funnelshift_r((uint32_t)t, (uint32_t)((uint64_t)t >> 32), shift);
+                    o[e] = max(min(r, 127), -128);
+                } else {
+                    const int64_t r = epi_value(a[e], 0, false, 0, mul, zp, shift);
+                    o[e] = (int32_t)(r < -128 ? -128 : (r > 127 ? 127 : r));
+                }
+            }
+            w[q] = (uint32_t)(o[0] & 0xff) | ((uint32_t)(o[1] & 0xff) << 8) | ((uint32_t)(o[2] & 0xff) << 16) | ((uint32_t)(o[3] & 0xff) << 24);
+        }
+        out[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
 __global__ void __launch_bounds__(256) prelu_kernel(const int32_t *__restrict__ in, int64_t total, const int32_t *__restrict__ slope,
                                                     int32_t *__restrict__ out) {
     const int32_t sl = slope[0];
@@ -83,7 +138,10 @@ extern "C" int fpcc_requant(const int32_t *in, int64_t rows, int ch, const fpcc_
     int64_t total = rows * ch;
     cudaStream_t s = (cudaStream_t)stream;
     EpiParams ep = to_params(e);
-    if (ch % 4 == 0 && (((uintptr_t)in | (uintptr_t)out) & 15) == 0) {
+    if (e->out_type == FPCC_OUT_I8 && e->mul_is_scalar && !e->bias && !e->slope && total % 16 == 0 &&
+        (((uintptr_t)in | (uintptr_t)out) & 15) == 0) {
+        requant_scalar_i8_kernel<<<ew_grid(total / 16), 256, 0, s>>>((const int4 *)in, total / 16, ep, (uint4 *)out);
+    } else if (ch % 4 == 0 && (((uintptr_t)in | (uintptr_t)out) & 15) == 0) {
         int64_t t4 = total / 4;
         if (e->out_type == FPCC_OUT_I8) requant_vec4_kernel<FPCC_OUT_I8><<<ew_grid(t4), 256, 0, s>>>((const int4 *)in, t4, ch / 4, ep, out);
         else if (e->out_type == FPCC_OUT_I16) requant_vec4_kernel<FPCC_OUT_I16><<<ew_grid(t4), 256, 0, s>>>((const int4 *)in, t4, ch / 4, ep, out);

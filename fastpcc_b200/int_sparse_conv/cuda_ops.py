@@ -440,7 +440,35 @@ class LinearIn8W8(_AffineIn8):
     def forward(self, input: torch.Tensor, sel=None, n_out_rows=None) -> torch.Tensor:
         """GEMM + bias + [PReLU] + requant in one kernel.  `sel` (from ops.slot_pairs) evaluates only the
         occupied (row, child) blocks of a C -> 8C linear: identical values, 4-8x less work."""
+        if sel is None and getattr(self, 'padded_output', False) and self.out_ch % 16 != 0 and self.in_ch % 16 == 0 and self.in_ch >= 32:
+            # opt-in (the consumer must accept a row pitch), e.g. the 255 logits feeding the CDF kernels: run the
+            # kernel on 256 zero-padded channels so that its rows are 16-byte aligned
+            # vector stores, and hand back the [m, out_ch] column slice (row pitch 256) of that buffer.
+            w, ep = self._padded_channels()
+            return ops.linear(input, w, ep)[:, :self.out_ch]
         return ops.linear(input, self.weight, self.epilogue(True), sel=sel, n_out_rows=n_out_rows)
+
+    def _padded_channels(self):
+        key = (self.weight._version, self.bias._version, self.requant_mul._version, self.int_zero_point_out._version,
+               self.weight.data_ptr())
+        cache = getattr(self, '_pad_cache', None)
+        if cache is None or cache[0] != key:
+            n_pad = (self.out_ch + 15) // 16 * 16
+            pad = n_pad - self.out_ch
+            w = torch.nn.functional.pad(self.weight, (0, 0, 0, pad)).contiguous()
+            bias = torch.nn.functional.pad(self.bias, (0, pad)).contiguous()
+            mul = self.requant_mul
+            if mul.numel() > 1:
+                mul = torch.nn.functional.pad(mul.view(torch.int32), (0, pad)).contiguous().view(torch.uint32)
+            shift = _shift_of(self)
+            out_type = ops.OUT_I8 if self.out_scaled_int else ops.OUT_I32
+            if not self.out_scaled_int:
+                shift -= SharedFxpShift
+            ep = ops.make_epilogue(mul, self.int_zero_point_out, shift, out_type, bias=bias,
+                                   slope=self.slope if self.with_prelu else None)
+            cache = (key, w, ep)
+            self._pad_cache = cache
+        return cache[1], cache[2]
 
     def forward_with_bits(self, input: torch.Tensor, occ: torch.Tensor, q0: int, q1: int) -> torch.Tensor:
         """Linear over cat(input, bits) where `bits` are the 8 occupancy channels of `occ` (channel k = bit 7-k)

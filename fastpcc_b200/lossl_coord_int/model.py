@@ -137,6 +137,7 @@ class OneScalePredictor(nn.Module):
         self.dec = SparseResBlockIn32W8Out32(channels)
         self.pred = SparseSequential(
             RequantFxpToScaledInt8(), SparseConvPReLUIn8W8Out8(channels, channels), LinearIn8W8Out32(channels, 255))
+        self.pred[-1].padded_output = True  # logits are only read by the CDF kernels, which take a row pitch
         self.if_upsample = if_upsample
         if if_upsample:
             self.upsample = SparseSequential(
@@ -199,6 +200,7 @@ class OneScaleMultiStepPredictor(nn.Module):
             else:
                 self.pred.append(SparseSequential(
                     RequantFxpToScaledInt8(), SparseConvPReLUIn8W8Out8(channels, channels), LinearIn8W8Out32(channels, 255)))
+                self.pred[-1][-1].padded_output = True
 
     def run(self, cur: SparseTensor, levels: List[Level]):
         """levels[j] = nodes of stride fea_stride / 2^j for j = 0 .. pred_steps-1 (coarse -> fine); all of

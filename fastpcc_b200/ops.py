@@ -64,7 +64,8 @@ def profile_summary(prof):
         d['ms'] += e0.elapsed_time(e1)
         d['launches'] += 1
         for k, v in work.items():
-            d[k] = d.get(k, 0.0) + v
+            if not isinstance(v, str):
+                d[k] = d.get(k, 0.0) + v
     return out
 
 
@@ -262,7 +263,9 @@ def requant(inp, ep, out=None):
     if inp.shape[0] <= 0 or inp.shape[1] <= 0:
         raise RuntimeError('requant: N > 0 && Ch > 0')
     out = torch.empty(inp.shape, dtype=_OUT_DTYPE[ep.out_type], device=inp.device) if out is None else out
-    _call('fpcc_requant', _p(inp), inp.shape[0], inp.shape[1], C.byref(ep), _p(out), _s())
+    _call('fpcc_requant', _p(inp), inp.shape[0], inp.shape[1], C.byref(ep), _p(out), _s(),
+          work={'bytes': float(inp.numel() * 4 + out.numel() * out.element_size()), 'desc': f'{inp.shape[0]}x{inp.shape[1]} out{ep.out_type}'}
+          if _prof is not None else None)
     return out
 
 
@@ -307,7 +310,8 @@ def linear(a, weight, ep, sel=None, n_out_rows=None, out=None):
         n = weight.shape[0]
         out = torch.empty((m, n), dtype=_OUT_DTYPE[ep.out_type], device=a.device) if out is None else out
         _call('fpcc_linear_i8', _p(a), m, k, _p(weight), n, None, None, None, 1, 0, C.byref(ep), _p(out), _s(),
-              tag='linear_' + gemm_engine(k, n) if _prof is not None else None, work={'ops': 2.0 * m * k * n})
+              tag='linear_' + gemm_engine(k, n) if _prof is not None else None,
+              work={'ops': 2.0 * m * k * n, 'desc': f'{m}x{k}->{n} out{ep.out_type} rb{int(bool(ep.row_bias))}'})
     else:
         sel_row, sel_out, offsets = sel
         groups = offsets.numel() - 1
@@ -315,7 +319,7 @@ def linear(a, weight, ep, sel=None, n_out_rows=None, out=None):
         out = torch.empty((n_out_rows, n), dtype=_OUT_DTYPE[ep.out_type], device=a.device) if out is None else out
         _call('fpcc_linear_i8', _p(a), m, k, _p(weight), n, _p(sel_row), _p(sel_out), _p(offsets), groups, n_out_rows,
               C.byref(ep), _p(out), _s(), tag='linear_sel_' + gemm_engine(k, n) if _prof is not None else None,
-              work={'ops': 2.0 * n_out_rows * k * n})
+              work={'ops': 2.0 * n_out_rows * k * n, 'desc': f'{m}x{k}->{groups}x{n} rows{n_out_rows} out{ep.out_type}'})
     return out
 
 
@@ -366,21 +370,30 @@ def softmax_i32(x):
     return out
 
 
+def _logits_pitch(logits):
+    """logits may be a column slice of a padded linear output: [n, s] with unit column stride and any row pitch"""
+    if logits.dtype != torch.int32 or not logits.is_cuda or logits.dim() != 2:
+        raise RuntimeError('logits: expected a 2-D int32 CUDA tensor')
+    if logits.shape[0] > 1 and (logits.stride(1) != 1 or logits.stride(0) < logits.shape[1]):
+        logits = logits.contiguous()
+    return logits, (logits.stride(0) if logits.shape[0] > 1 else logits.shape[1])
+
+
 def quantize_cdf(logits, ld=CDF_LD):
-    _need(logits, torch.int32, 'logits', 2)
+    logits, pitch = _logits_pitch(logits)
     n, s = logits.shape
     ld = max(ld, s)
     out = torch.empty((n, ld), dtype=torch.uint16, device=logits.device)
-    _call('fpcc_quantize_cdf', _p(logits), n, s, _p(out), ld, _s())
+    _call('fpcc_quantize_cdf', _p(logits), pitch, n, s, _p(out), ld, _s())
     return out
 
 
 def cdf_symbol_ranges(logits, symbols, out=None):
-    _need(logits, torch.int32, 'logits', 2)
+    logits, pitch = _logits_pitch(logits)
     _need(symbols, torch.int32, 'symbols', 1)
     n, s = logits.shape
     out = torch.empty(n, dtype=torch.int32, device=logits.device) if out is None else out
-    _call('fpcc_cdf_symbol_ranges', _p(logits), n, s, _p(symbols), _p(out), _s())
+    _call('fpcc_cdf_symbol_ranges', _p(logits), pitch, n, s, _p(symbols), _p(out), _s())
     return out
 
 

@@ -216,14 +216,15 @@ int fpcc_gemm_engine(int k, int n, int kvol, int has_zp_comp);
 int fpcc_softmax_i32(const int32_t *in, int64_t rows, int c, uint32_t *out, void *stream);
 
 /* replaces Model.batch_quantize_pmf_torch (model.py:344-353) without the D2H copy:
- * logits Q8.23 [rows,s] -> inclusive uint16 CDF rows (entry s-1 = 65535) with a row pitch of `ld` >= s
- * entries; pad entries are 0xFFFF.  ld = 256 with 16-byte aligned rows selects the decoder's fast path. */
-int fpcc_quantize_cdf(const int32_t *logits, int64_t rows, int s, uint16_t *cdf, int ld, void *stream);
+ * logits Q8.23 [rows,s] (row pitch `logits_ld` >= s elements, so a padded linear output is read in place)
+ * -> inclusive uint16 CDF rows (entry s-1 = 65535) with a row pitch of `ld` >= s entries; pad entries are
+ * 0xFFFF.  ld = 256 with 16-byte aligned rows selects the decoder's fast path. */
+int fpcc_quantize_cdf(const int32_t *logits, int64_t logits_ld, int64_t rows, int s, uint16_t *cdf, int ld, void *stream);
 
 /* Encoder-side fusion of the above with the symbol lookup of RansEncoder::encode
  * (simple_rans_wrapper.cpp:86-90): ranges[i] = start | (freq-1)<<16 of symbols[i] under row i.
  * Device-side symbol arrays are int32 throughout this ABI (values 0..s-1). */
-int fpcc_cdf_symbol_ranges(const int32_t *logits, int64_t rows, int s, const int32_t *symbols,
+int fpcc_cdf_symbol_ranges(const int32_t *logits, int64_t logits_ld, int64_t rows, int s, const int32_t *symbols,
                            uint32_t *ranges, void *stream);
 /* same lookup for an explicit uint16 CDF table ([n_cdf,s], n_cdf == rows or 1) */
 int fpcc_table_symbol_ranges(const uint16_t *cdf, int64_t n_cdf, int s, const int32_t *symbols, int64_t rows,

@@ -216,6 +216,16 @@ def test_epilogue_ranges_fast_and_wide_paths(ops):
         got = ops.linear(dev(a), dev(w), ep).cpu().numpy()
         assert (got == want).all(), post_v
     assert cases == 72
+    # stand-alone requant with one multiplier (RequantFxpToScaledInt8, cuda_ops.py:478-507): full int32 inputs
+    x = rng.integers(-(1 << 31), (1 << 31) - 1, (513, 64), endpoint=True).astype(np.int32)
+    x[0, :8] = [-(1 << 31), (1 << 31) - 1, 0, -1, 1, -(1 << 31) + 1, 1 << 30, -(1 << 30)]
+    for shift in (0, 1, 7, 23, 31, 36):
+        for mulv in (0, 1, 3, 12345, (1 << 22) + 5, (1 << 31) - 1, (1 << 31) + 7):
+            for zpv in (0, -1, 5 << shift, -(1 << 40)):
+                mul1, zp = np.array([mulv], np.uint32), np.array([zpv], np.int64)
+                want = K.requant(x, np.full(64, mulv, np.uint32), zp, shift, np.int8)
+                got = ops.requant(dev(x), ops.make_epilogue(dev(mul1), dev(zp), shift, ops.OUT_I8)).cpu().numpy()
+                assert (got == want).all(), (shift, mulv, zpv)
 
 
 def test_selected_linear_equals_masked_dense(ops):
