@@ -42,10 +42,10 @@ __device__ __forceinline__ EncSym make_enc_sym(uint32_t start, uint32_t freq, ui
 }
 
 // Encoding is two kernels.  (1) enc_prepare_kernel, fully parallel: every entry gets its exact-division
-// constants {x_max, rcp, bias, cmpl | rcp_shift << 16}.  (2) rans_encode_kernel, one warp per stream, all lanes
-// uniform: entries of stream b are [rng_off[b], rng_off[b+1]) in DECODE order and are consumed back to front
-// (rANS is LIFO) with 8 records prefetched ahead of the state recurrence; bytes are written backwards from the
-// end of the stream's slot, collected in a register and stored as aligned 32-bit words.
+// constants {x_max, rcp, bias, cmpl | rcp_shift << 16}.  (2) rans_encode_kernel, one warp per stream: entries
+// of stream b are [rng_off[b], rng_off[b+1]) in DECODE order and are consumed back to front (rANS is LIFO);
+// bytes are written backwards from the end of the stream's slot, collected in a register and stored as
+// aligned 32-bit words.
 __global__ void __launch_bounds__(256) enc_prepare_kernel(const uint32_t *__restrict__ ranges, const uint8_t *__restrict__ bits,
                                                           int64_t total, uint4 *__restrict__ recs) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -55,34 +55,43 @@ __global__ void __launch_bounds__(256) enc_prepare_kernel(const uint32_t *__rest
     recs[i] = make_uint4(es.x_max, es.rcp, es.bias, (uint32_t)es.cmpl | ((uint32_t)es.rcp_shift << 16));
 }
 
-// predicated 32-bit store (keeps the serial loop free of branches)
-__device__ __forceinline__ void st_u32_if(void *p, uint32_t v, bool pred) {
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.u32 [%0], %1;\n\t}" ::"l"(p), "r"(v), "r"((uint32_t)pred) : "memory");
+// One rANS step on record r, branch-free.  The state recurrence is all that stays serial: the bytes that leave
+// (0..2, low byte first) are handed to the packer warp as one word, low 16 bits of the old state | count << 16.
+__device__ __forceinline__ int enc_step(uint32_t &x, const uint4 r, uint32_t &emit) {
+    // RansEncRenorm, rans_byte.h:77-89: x < 2^31 and x_max >= 2^15, so at most two bytes leave.  The three possible
+    // renormalised states and their quotients are formed side by side and selected afterwards: the serial
+    // dependency per symbol is shift -> multiply-high -> select -> shift -> multiply-add.
+    const uint32_t x1 = x >> 8, x2 = x >> 16;
+    const bool c1 = x >= r.x, c2 = x1 >= r.x;
+    const uint32_t q0 = __umulhi(x, r.y), q1 = __umulhi(x1, r.y), q2 = __umulhi(x2, r.y);  // exact x / freq (rans_byte.h:201-259)
+    const uint32_t xs = c2 ? x2 : (c1 ? x1 : x);
+    const uint32_t qs = c2 ? q2 : (c1 ? q1 : q0);
+    const int nb = (int)c1 + (int)c2;
+    emit = (x & 0xFFFFu) | ((uint32_t)nb << 16);
+    x = (xs + r.z) + (qs >> (r.w >> 16)) * (r.w & 0xFFFFu);
+    return nb;
 }
 
-// One rANS step on record r: branch-free.  Emitted bytes collect in `acc` (oldest byte most significant) and
-// leave as aligned 32-bit words written backwards.
-__device__ __forceinline__ void enc_step(uint32_t &x, const uint4 r, uint64_t &acc, int &nacc, uint8_t *&ptr) {
-    // RansEncRenorm, rans_byte.h:77-89: x < 2^31 and x_max >= 2^15, so at most two bytes leave
-    const int nb = (int)(x >= r.x) + (int)((x >> 8) >= r.x);
-    const uint32_t two = ((x & 0xffu) << 8) | ((x >> 8) & 0xffu);  // first emitted byte (higher address) on top
-    acc = (acc << (8 * nb)) | (uint64_t)(two >> (16 - 8 * nb));
-    nacc += nb;
-    x >>= 8 * nb;
-    const bool fl = nacc >= 4;
-    st_u32_if(ptr - 4, (uint32_t)(acc >> ((8 * (nacc - 4)) & 63)), fl);
-    ptr -= fl ? 4 : 0;
-    nacc -= fl ? 4 : 0;
-    const uint32_t q = __umulhi(x, r.y) >> (r.w >> 16);  // exact x / freq (rans_byte.h:201-259)
-    x = x + r.z + q * (r.w & 0xFFFFu);
+// Two warps per stream.  Warp 0: all lanes stream the records of the stream, back to front, through a
+// shared-memory ring with cp.async (ENC_RING-1 chunks of ENC_CH records in flight); lane 0 runs the serial
+// recurrence on them at shared-memory latency.  Warp 1 packs: per chunk it turns the per-symbol byte counts into
+// positions with a warp scan and stores the bytes (backwards from the end of the stream's slot), off the critical
+// path of the recurrence.  The two warps hand chunks over through named barriers (double-buffered).
+constexpr int ENC_CH = 256, ENC_RING = 4;
+__device__ __forceinline__ void nbar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void nbar_arrive(int id) {
+    __threadfence_block();
+    asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory");
 }
 
-// One thread per stream (the recurrence is serial; a lone thread needs no divergence bookkeeping).
-__global__ void __launch_bounds__(32) rans_encode_kernel(const uint4 *__restrict__ recs, const int64_t *__restrict__ rng_off,
+__global__ void __launch_bounds__(64) rans_encode_kernel(const uint4 *__restrict__ recs, const int64_t *__restrict__ rng_off,
                                                          uint8_t *__restrict__ out, int64_t out_stride,
                                                          int32_t *__restrict__ out_len, uint32_t *__restrict__ state_io,
                                                          int do_flush) {
-    if (threadIdx.x != 0) return;
+    __shared__ uint4 ring[ENC_RING][ENC_CH];
+    __shared__ __align__(16) uint32_t emit[2][ENC_CH];
+    __shared__ int emit_n[2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x;
     const int64_t lo = rng_off[b], hi = rng_off[b + 1];
     uint8_t *const base = out + (int64_t)b * out_stride;
@@ -94,22 +103,98 @@ __global__ void __launch_bounds__(32) rans_encode_kernel(const uint4 *__restrict
         uint32_t written = state_io[2 * b + 1];
         if (written == 0xFFFFFFFFu) overflow = true; else ptr -= written;
     }
-    int64_t top = hi;
-    if (!overflow && ((uintptr_t)ptr & 3) == 0) {
-        // fast path: aligned write position, eight records prefetched ahead of the recurrence
-        uint64_t acc = 0;
-        int nacc = 0;
-        constexpr int U = 8;
-        while (top - lo >= U && ptr - base >= 4 * U + 16) {
-            uint4 r[U];
+    // named barriers: 1 + buf = "emit[buf] filled", 3 + buf = "emit[buf] drained", 5 = join
+    if (warp == 1) {  // ---- packer ----
+        for (int64_t c = 0;; ++c) {
+            const int buf = (int)(c & 1);
+            nbar_sync(1 + buf);
+            if (emit_n[buf] == 0) break;
+            const uint4 w0 = reinterpret_cast<const uint4 *>(emit[buf])[2 * lane], w1 = reinterpret_cast<const uint4 *>(emit[buf])[2 * lane + 1];
+            const uint32_t w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+            int local = 0;
 #pragma unroll
-            for (int u = 0; u < U; ++u) r[u] = __ldg(&recs[top - 1 - u]);
+            for (int k = 0; k < 8; ++k) local += (int)(w[k] >> 16);
+            int incl = local;
 #pragma unroll
-            for (int u = 0; u < U; ++u) enc_step(x, r[u], acc, nacc, ptr);
-            top -= U;
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            uint8_t *q = ptr - (incl - local);  // first byte of this lane's first symbol goes to q[-1]
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int nb = (int)(w[k] >> 16);
+                if (nb >= 1) q[-1] = (uint8_t)(w[k] & 0xffu);
+                if (nb >= 2) q[-2] = (uint8_t)((w[k] >> 8) & 0xffu);
+                q -= nb;
+            }
+            ptr -= __shfl_sync(0xffffffffu, incl, 31);
+            nbar_arrive(3 + buf);
         }
-        for (int t = nacc - 1; t >= 0; --t) *--ptr = (uint8_t)(acc >> (8 * t));  // bytes still held in the register
+        nbar_sync(5);
+        return;
     }
+    int64_t top = hi;
+    {
+        // Chunk c holds records [hi - (c+1)*ENC_CH, hi - c*ENC_CH).
+        const int64_t n_chunks = overflow ? 0 : (hi - lo) / ENC_CH;
+        auto issue = [&](int64_t c) {
+            if (c < n_chunks) {
+                const uint4 *src = recs + (hi - (c + 1) * ENC_CH);
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&ring[c % ENC_RING][0]);
+#pragma unroll
+                for (int t = 0; t < ENC_CH / 32; ++t)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)((t * 32 + lane) * 16)), "l"(src + t * 32 + lane) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        for (int c = 0; c < ENC_RING - 1; ++c) issue(c);
+        int64_t room = ptr - base;  // bytes still free in front of the write position (lane 0 keeps it exact)
+        int64_t c = 0;
+        for (; c < n_chunks; ++c) {
+            const int buf = (int)(c & 1);
+            issue(c + ENC_RING - 1);
+            asm volatile("cp.async.wait_group %0;" ::"n"(ENC_RING - 1) : "memory");
+            __syncwarp();
+            if (c >= 2) nbar_sync(3 + buf);  // packer has drained this buffer (chunk c-2)
+            int go = 1;
+            if (lane == 0) {
+                go = room >= 2 * ENC_CH + 16;  // worst case two bytes per record; the flush needs 4 more
+                if (go) {
+                    const uint4 *rb = ring[c % ENC_RING];
+                    uint32_t *em = emit[buf];
+                    int total = 0;
+                    constexpr int U = 8;
+#pragma unroll 1
+                    for (int i = ENC_CH - U; i >= 0; i -= U) {
+                        uint4 r[U];
+#pragma unroll
+                        for (int u = 0; u < U; ++u) r[u] = rb[i + U - 1 - u];
+#pragma unroll
+                        for (int u = 0; u < U; ++u) total += enc_step(x, r[u], em[ENC_CH - U - i + u]);
+                    }
+                    room -= total;
+                }
+                emit_n[buf] = go ? ENC_CH : 0;
+            }
+            go = __shfl_sync(0xffffffffu, go, 0);
+            nbar_arrive(1 + buf);
+            if (!go) break;
+            top -= ENC_CH;
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (c == n_chunks) {  // normal end: post the terminating empty chunk
+            const int buf = (int)(c & 1);
+            if (c >= 2) nbar_sync(3 + buf);
+            if (lane == 0) emit_n[buf] = 0;
+            __syncwarp();
+            nbar_arrive(1 + buf);
+        }
+        nbar_sync(5);  // every byte of the chunks above is in place
+        room = __shfl_sync(0xffffffffu, (int)room, 0);
+        ptr = base + room;
+    }
+    if (lane != 0) return;
     // tail (and unaligned resume points): plain loop with byte stores
     uint8_t *const guard = base + 8;
     for (; top > lo; --top) {
@@ -172,6 +257,12 @@ __device__ __forceinline__ uint32_t dec_advance(uint32_t x, ByteReader &br, uint
 
 // Big-endian window over the byte stream (next byte on top), refilled with aligned 32-bit loads that are
 // issued one refill ahead of their use.  Reads at most 3 bytes before / 7 bytes past the stream.
+__device__ __forceinline__ int32_t le_mask(uint32_t e, int32_t cf_plus_1) {  // -1 if e <= cf else 0 (e, cf < 2^16)
+    int32_t m;
+    asm("{\n\t.reg .s32 d;\n\tsub.s32 d, %1, %2;\n\tshr.s32 %0, d, 31;\n\t}" : "=r"(m) : "r"((int32_t)e), "r"(cf_plus_1));
+    return m;
+}
+
 struct ByteWindow {
     const uint32_t *wp;
     uint64_t win;
@@ -196,6 +287,11 @@ struct ByteWindow {
             nextw = *wp++;
             if (((uintptr_t)wp & 127) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(wp + 64));  // two lines ahead
         }
+    }
+    __device__ __forceinline__ void consume(int n) {  // drops n (0..2) bytes from the front of the window
+        win <<= 8 * n;
+        avail -= n;
+        refill();
     }
     // Shifts the next n (0..2) bytes of the stream into x from the right: x = (x << 8n) | bytes.
     __device__ __forceinline__ uint32_t shift_in(uint32_t x, int n) {
@@ -264,33 +360,43 @@ __global__ void __launch_bounds__(64) rans_decode_rows_kernel(fpcc_rans_dec_stat
     uint32_t x = s.x, pos = s.pos;
     ByteWindow bw;
     bw.init(p + pos);
-    const int cidx = lane * 8 + 7;
-    const bool cvalid = cidx < S - 1;
+    // Lane l owns entries 8l .. 8l+7 of the current row (one 16-byte shared load, issued one symbol ahead: rows do
+    // not depend on the coder state).  With the state known, every lane counts its entries <= cf (the CDF is
+    // non-decreasing, so they form a prefix), one warp reduction gives the symbol, and two broadcast loads fetch
+    // its range: compare -> redux -> load -> multiply-add is the whole serial dependency.
+    const int nv = min(8, max(0, S - 1 - 8 * lane));  // entries j >= S-1 never count (simple_rans_wrapper.cpp:225-228)
     for (int64_t sl = 0; sl < nslots; ++sl) {
         const int slot = (int)(sl % DEC_SLOTS);
         bar_wait(&full[slot], (uint32_t)((sl / DEC_SLOTS) & 1));
         const int rows = (int)min((int64_t)DEC_SLOT_ROWS, n - sl * DEC_SLOT_ROWS);
         const int64_t i0 = lo + sl * DEC_SLOT_ROWS;
-        uint32_t cv = cvalid ? (uint32_t)ring[slot][0][cidx] : 0x10000u;
+        uint4 ev = reinterpret_cast<const uint4 *>(ring[slot][0])[lane];
         for (int r = 0; r < rows; ++r) {
             const uint16_t *row = ring[slot][r];
-            const uint32_t cv_next = (cvalid && r + 1 < rows) ? (uint32_t)ring[slot][r + 1][cidx] : 0x10000u;
+            const uint32_t e0 = ev.x & 0xFFFFu, e1 = ev.x >> 16, e2 = ev.y & 0xFFFFu, e3 = ev.y >> 16;
+            const uint32_t e4 = ev.z & 0xFFFFu, e5 = ev.z >> 16, e6 = ev.w & 0xFFFFu, e7 = ev.w >> 16;
+            if (r + 1 < rows) ev = reinterpret_cast<const uint4 *>(ring[slot][r + 1])[lane];
             const uint32_t cf = x & 0xFFFFu;
-            // symbol = #{j < S-1 : cdf[j] <= cf}  (== upper_bound clamped to S-1, simple_rans_wrapper.cpp:225-228)
-            const int g = __popc(__ballot_sync(0xffffffffu, cv <= cf));  // groups of 8 entries entirely <= cf
-            const int idx = 8 * g - 1 + lane;                             // lanes 0..8: entries 8g-1 .. 8g+7
-            const uint32_t w = row[min(max(idx, 0), 255)];                // always in the row: no divergent load
-            uint32_t v = idx < 0 ? 0u : w;
-            v = (lane > 8 || idx >= S - 1) ? 0x10000u : v;
-            const int c = __popc(__ballot_sync(0xffffffffu, v <= cf));    // >= 1: lane 0 is always <= cf
-            const uint32_t start = __shfl_sync(0xffffffffu, v, c - 1);
-            const uint32_t end = __shfl_sync(0xffffffffu, v, c);
+            // entries < 2^16: (e - cf - 1) >> 31 is -1 exactly when e <= cf; eight independent subtract/shift pairs and
+            // a three-input add tree instead of a chain of compare-and-select
+            const int32_t t1 = (int32_t)cf + 1;
+            const int cnt8 = -((le_mask(e0, t1) + le_mask(e1, t1) + le_mask(e2, t1)) + (le_mask(e3, t1) + le_mask(e4, t1) + le_mask(e5, t1)) +
+                               (le_mask(e6, t1) + le_mask(e7, t1)));
+            const int cnt = min(cnt8, nv);
+            const int sym = __reduce_add_sync(0xffffffffu, cnt);  // #{j < S-1 : cdf[j] <= cf}
+            const uint32_t start = sym > 0 ? (uint32_t)row[sym - 1] : 0u;
+            const uint32_t end = sym == S - 1 ? 0x10000u : (uint32_t)row[sym];
             x = (end - start) * (x >> 16) + cf - start;                   // RansDecAdvance, rans_byte.h:149-165
-            const int nb = (int)(x < RANS_L) + (int)(x < (1u << 15));     // renormalisation: 0..2 bytes
-            x = bw.shift_in(x, nb);
+            // renormalisation, 0..2 bytes: both refilled candidates are formed from the window before the compares
+            // resolve, then selected
+            const uint32_t whi = (uint32_t)(bw.win >> 32);
+            const uint32_t c1 = __funnelshift_l(whi, x, 8), c2 = __funnelshift_l(whi, x, 16);
+            const bool p0 = x >= RANS_L, p1 = x >= (1u << 15);
+            const int nb = (int)!p0 + (int)!p1;
+            x = p0 ? x : (p1 ? c1 : c2);
+            bw.consume(nb);
             pos += nb;
-            if (lane == 0) symbols[i0 + r] = 8 * g + c - 1;
-            cv = cv_next;
+            if (lane == 0) symbols[i0 + r] = sym;
         }
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&empty[slot])) : "memory");
@@ -543,7 +649,7 @@ extern "C" int fpcc_rans_encode(const uint32_t *ranges, const uint8_t *bits, con
         enc_prepare_kernel<<<ceil_div(total_entries, 256), 256, 0, s>>>(ranges, bits, total_entries, recs);
         FPCC_LAUNCH_CHECK();
     }
-    rans_encode_kernel<<<n_streams, 32, 0, s>>>(recs, rng_off, out, out_stride, out_len, state_io, do_flush);
+    rans_encode_kernel<<<n_streams, 64, 0, s>>>(recs, rng_off, out, out_stride, out_len, state_io, do_flush);
     FPCC_LAUNCH_CHECK();
     return FPCC_OK;
 }
