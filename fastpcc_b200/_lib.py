@@ -29,6 +29,8 @@ SIGNATURES = {
     'fpcc_kmap_lookup': (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i64, _vp]),
     'fpcc_kmap_compact_workspace': (_sz, [_i, _i]),
     'fpcc_kmap_compact': (_i, [_vp, _i, _i, _i64, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'fpcc_kmap_row_masks': (_i, [_vp, _i, _i, _i64, _vp, _vp]),
+    'fpcc_kmap_permute': (_i, [_vp, _i, _i, _i64, _vp, _vp, _i64, _vp]),
     'fpcc_scan_workspace': (_sz, [_i]),
     'fpcc_downsample': (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'fpcc_upsample': (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -40,9 +42,9 @@ SIGNATURES = {
     'fpcc_gather_gemm_scatter_i8': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'fpcc_requant': (_i, [_vp, _i64, _i, _EP, _vp, _vp]),
     'fpcc_prelu_i32': (_i, [_vp, _i64, _vp, _vp, _vp]),
-    'fpcc_spconv_i8': (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _i64, _i, _vp, _EP, _vp, _vp]),
+    'fpcc_spconv_i8': (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _i64, _i, _vp, _vp, _EP, _vp, _vp]),
     'fpcc_linear_i8': (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _EP, _vp, _vp]),
-    'fpcc_spconv_f16': (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp, _i64, _i, _vp, _i, C.c_float, _vp, _i, C.c_float, _vp, _i, _vp]),
+    'fpcc_spconv_f16': (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp, _i64, _i, _vp, _vp, _i, C.c_float, _vp, _i, C.c_float, _vp, _i, _vp]),
     'fpcc_linear_f16': (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _i, C.c_float, _vp, _i, C.c_float, _vp, _i, _vp]),
     'fpcc_set_tc_mode': (_i, [_i]),
     'fpcc_set_sm_budget': (_i, [_i]),

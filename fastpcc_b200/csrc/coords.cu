@@ -106,6 +106,25 @@ __global__ void __launch_bounds__(256) kmap_lookup_kernel(const unsigned long lo
     else table[(int64_t)o * g.kvol + k] = v;
 }
 
+// Row grouping for the tensor-core conv: the kernel skips an offset for a whole 128-row tile only when NO row of
+// the tile has that neighbour, so rows with equal neighbour patterns should share tiles.  row_masks gives the
+// sort key (bit k = neighbour k present); permute_table rewrites the table in the sorted row order.
+__global__ void __launch_bounds__(256) kmap_row_masks_kernel(const int32_t *__restrict__ table, int kvol, int n_out, int64_t ld,
+                                                             int32_t *__restrict__ masks) {
+    int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n_out) return;
+    uint32_t m = 0;
+    for (int k = 0; k < kvol; ++k) m |= (uint32_t)(table[(int64_t)k * ld + o] != 0) << (k < 31 ? k : 31);
+    masks[o] = (int32_t)(m & 0x7FFFFFFFu);  // non-negative: any signed sort groups equal patterns
+}
+__global__ void __launch_bounds__(256) kmap_permute_kernel(const int32_t *__restrict__ table, int n_out, int64_t ld,
+                                                           const int32_t *__restrict__ perm, int32_t *__restrict__ out, int64_t ld_out) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int k = blockIdx.y;
+    if (j >= n_out) return;
+    out[(int64_t)k * ld_out + j] = table[(int64_t)k * ld + perm[j]];
+}
+
 // ---------------------------------------------------------------------------------------------
 // compaction: k-major table -> offset-major (in,out) pair lists, output index ascending
 // ---------------------------------------------------------------------------------------------
@@ -299,6 +318,25 @@ extern "C" int fpcc_kmap_lookup(const int64_t *keys, const int32_t *vals, int ca
     dim3 grid(ceil_div(n_out, 256), g.kvol);
     kmap_lookup_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const unsigned long long *)keys, vals, (uint32_t)capacity,
                                                                out_coords, n_out, layout, g, table, k_major, ld);
+    FPCC_LAUNCH_CHECK();
+    return FPCC_OK;
+}
+
+extern "C" int fpcc_kmap_row_masks(const int32_t *table, int kvol, int n_out, int64_t ld, int32_t *masks, void *stream) {
+    FPCC_REQUIRE(table && masks, "kmap_row_masks: NULL pointer");
+    FPCC_REQUIRE(kvol > 0 && n_out >= 0 && ld >= n_out, "kmap_row_masks: bad sizes");
+    if (n_out == 0) return FPCC_OK;
+    kmap_row_masks_kernel<<<ceil_div(n_out, 256), 256, 0, (cudaStream_t)stream>>>(table, kvol, n_out, ld, masks);
+    FPCC_LAUNCH_CHECK();
+    return FPCC_OK;
+}
+
+extern "C" int fpcc_kmap_permute(const int32_t *table, int kvol, int n_out, int64_t ld, const int32_t *perm, int32_t *out,
+                                 int64_t ld_out, void *stream) {
+    FPCC_REQUIRE(table && perm && out, "kmap_permute: NULL pointer");
+    FPCC_REQUIRE(kvol > 0 && kvol <= 65535 && n_out >= 0 && ld >= n_out && ld_out >= n_out, "kmap_permute: bad sizes");
+    if (n_out == 0) return FPCC_OK;
+    kmap_permute_kernel<<<dim3(ceil_div(n_out, 256), kvol), 256, 0, (cudaStream_t)stream>>>(table, n_out, ld, perm, out, ld_out);
     FPCC_LAUNCH_CHECK();
     return FPCC_OK;
 }

@@ -141,6 +141,7 @@ struct TcArgs {
     const int32_t *nbr;
     int64_t ld;
     int n_out, kvol;
+    const int32_t *row_perm;  // optional: column j of nbr describes output row row_perm[j] (rows grouped by pattern)
     // MODE_PAIRS
     const int32_t *in_idx, *out_idx, *offsets;
     int n_groups, n_pairs, bias_per_group;
@@ -723,8 +724,9 @@ __global__ void __launch_bounds__(P_THREADS, 1) igemm_tc_persistent(TcArgs a, co
             }
             const bool fast = KIND == 0 && *(volatile uint32_t *)fast_off == 0u;
             const int32_t *rows = rows_s + slot * rows_k * TC_M;
-            const int64_t m = MODE == 0 ? (int64_t)tile_m * TC_M + r : (int64_t)rows[TC_M + r];
-            const bool row_ok = MODE == 0 ? (m < a.n_out) : (m >= 0);
+            const int64_t mt = (int64_t)tile_m * TC_M + r;  // MODE 0: column of the neighbour table
+            const bool row_ok = MODE == 0 ? (mt < a.n_out) : (rows[TC_M + r] >= 0);
+            const int64_t m = MODE == 0 ? ((a.row_perm && row_ok) ? (int64_t)__ldg(&a.row_perm[mt]) : mt) : (int64_t)rows[TC_M + r];
             mbar_wait(&tmem_full[slot], (j >> 1) & 1);
             tc_fence_after();
             const uint32_t tacc = tmem_base + (uint32_t)(slot * a.tmem_cols) + ((uint32_t)(quarter * 32) << 16);
@@ -920,12 +922,12 @@ static int launch_tc(TcArgs &a, const void *W, int64_t w_rows, int tiles_m, cons
 }
 
 int launch_conv_tc(const int8_t *feats, int n_in, int c_in, const int8_t *weight, int kvol, int c_out, const int32_t *nbr,
-                   int64_t ld, int n_out, const EpiParams &ep, void *out, cudaStream_t s) {
+                   int64_t ld, int n_out, const int32_t *row_perm, const EpiParams &ep, void *out, cudaStream_t s) {
     (void)n_in;
     if (!tc_shape_ok(feats, weight, c_in, c_out) || kvol > TC_MAX_KVOL) return FPCC_ERR_UNSUPPORTED;
     TcArgs a = {};
     a.A = feats; a.K = c_in; a.N = c_out;
-    a.nbr = nbr; a.ld = ld; a.n_out = n_out; a.kvol = kvol;
+    a.nbr = nbr; a.ld = ld; a.n_out = n_out; a.kvol = kvol; a.row_perm = row_perm;
     FEpi fe = {};
     return launch_tc<0, 0>(a, weight, (int64_t)kvol * c_out, ceil_div(n_out, TC_M), ep, fe, out, s);
 }
@@ -955,7 +957,7 @@ static int f16_common(int dtype, int out_type, int act, int post_act, int c_in, 
 }
 
 extern "C" int fpcc_spconv_f16(const void *feats, int dtype, int n_in, int c_in, const void *weight, int kvol, int c_out,
-                               const int32_t *nbr_table, int64_t ld, int n_out, const float *bias, int act, float slope,
+                               const int32_t *nbr_table, int64_t ld, int n_out, const int32_t *row_perm, const float *bias, int act, float slope,
                                const void *residual, int post_act, float post_slope, void *out, int out_type, void *stream) {
     using namespace fpcc;
     FPCC_REQUIRE(feats && weight && nbr_table && out, "spconv_f16: NULL pointer");
@@ -964,7 +966,7 @@ extern "C" int fpcc_spconv_f16(const void *feats, int dtype, int n_in, int c_in,
     if (rc) return rc;
     TcArgs a = {};
     a.A = (const int8_t *)feats; a.K = 2 * c_in; a.N = c_out;
-    a.nbr = nbr_table; a.ld = ld; a.n_out = n_out; a.kvol = kvol;
+    a.nbr = nbr_table; a.ld = ld; a.n_out = n_out; a.kvol = kvol; a.row_perm = row_perm;
     FEpi fe = {bias, residual, slope, post_slope, act, post_act, out_type};
     EpiParams ep = {};
     if (dtype == 0) return launch_tc<0, 1>(a, weight, (int64_t)kvol * c_out, ceil_div(n_out, TC_M), ep, fe, out, (cudaStream_t)stream);

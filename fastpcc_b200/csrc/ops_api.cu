@@ -8,7 +8,7 @@ int launch_conv_simt(const int8_t *feats, int c_in, const int8_t *weight, int kv
                      int64_t ld, int n_out, const int32_t *zp_comp, const EpiParams &ep, void *out, cudaStream_t s);
 // tensor-core (tcgen05) paths, igemm_tc.cu; return FPCC_ERR_UNSUPPORTED when the shape is not covered
 int launch_conv_tc(const int8_t *feats, int n_in, int c_in, const int8_t *weight, int kvol, int c_out, const int32_t *nbr,
-                   int64_t ld, int n_out, const EpiParams &ep, void *out, cudaStream_t s);
+                   int64_t ld, int n_out, const int32_t *row_perm, const EpiParams &ep, void *out, cudaStream_t s);
 int launch_pairs_tc(const PairArgs &a, const EpiParams &ep, void *out, int max_tiles, cudaStream_t s);
 bool tc_enabled();
 
@@ -180,8 +180,8 @@ extern "C" int fpcc_gather_gemm_scatter_i8(const int8_t *A, const int8_t *B, int
 }
 
 extern "C" int fpcc_spconv_i8(const int8_t *in_feats, int n_in, int c_in, const int8_t *weight, int kvol, int c_out,
-                              const int32_t *nbr_table, int64_t ld, int n_out, const int32_t *zp_comp,
-                              const fpcc_epilogue *e, void *out, void *stream) {
+                              const int32_t *nbr_table, int64_t ld, int n_out, const int32_t *row_perm,
+                              const int32_t *zp_comp, const fpcc_epilogue *e, void *out, void *stream) {
     FPCC_REQUIRE(in_feats && weight && nbr_table && out, "spconv_i8: NULL pointer");
     FPCC_REQUIRE(n_in > 0 && n_out > 0 && c_in > 0 && c_out > 0 && kvol > 0 && ld >= n_out, "spconv_i8: bad sizes");
     int rc = check_epilogue(e, true);
@@ -189,9 +189,10 @@ extern "C" int fpcc_spconv_i8(const int8_t *in_feats, int n_in, int c_in, const 
     FPCC_REQUIRE(e->row_bias == nullptr, "spconv_i8: row_bias belongs to the linear kernels");
     EpiParams ep = to_params(e);
     if (tc_enabled() && !zp_comp) {
-        rc = launch_conv_tc(in_feats, n_in, c_in, weight, kvol, c_out, nbr_table, ld, n_out, ep, out, (cudaStream_t)stream);
+        rc = launch_conv_tc(in_feats, n_in, c_in, weight, kvol, c_out, nbr_table, ld, n_out, row_perm, ep, out, (cudaStream_t)stream);
         if (rc != FPCC_ERR_UNSUPPORTED) return rc;
     }
+    FPCC_REQUIRE(!row_perm, "spconv_i8: a grouped (row_perm) table needs the tensor-core path (see fpcc_gemm_engine)");
     return launch_conv_simt(in_feats, c_in, weight, kvol, c_out, nbr_table, ld, n_out, zp_comp, ep, out, (cudaStream_t)stream);
 }
 

@@ -22,6 +22,9 @@ WeightRange = (1 << 7) - 1
 ActRange = (1 << 7) - 1
 
 
+GROUP_ROWS_MIN = 4096  # below this a conv is launch-bound and the sort does not pay
+
+
 class KernelMap:
     """Neighbour table [kernel_volume, n_out] int32: input row + 1, 0 = none (k-major, device)."""
 
@@ -29,6 +32,13 @@ class KernelMap:
         self.table = table
         self.idx_omit_map = idx_omit_map
         self._pairs = None
+        self._grouped = None
+
+    def grouped(self):
+        """(table regrouped by neighbour pattern, row permutation) for the tensor-core conv, built once per map"""
+        if self._grouped is None:
+            self._grouped = ops.group_rows(self.table)
+        return self._grouped
 
     @classmethod
     def from_pair_lists(cls, in_out_maps, n_out, kernel_volume, n_in_equals_out_centre=-1, device=None):
@@ -99,7 +109,13 @@ def sparse_conv_in8w8out32(
     else:
         kmap = _as_kernel_map(in_out_maps, out_coords.shape[0], kernel_volume, idx_omit_map, in_feats.device)
     ep = _epilogue if _epilogue is not None else ops.identity_epilogue(in_feats.device)
-    out = ops.spconv(in_feats, weight, kmap.table, ep, zp_comp=zero_point_comp)
+    kv, c_out, c_in = weight.shape
+    if (zero_point_comp is None and kv > 1 and kmap.table.shape[1] >= GROUP_ROWS_MIN
+            and ops.gemm_engine(c_in, c_out, kv) == 'tc'):
+        table_p, perm = kmap.grouped()
+        out = ops.spconv(in_feats, weight, table_p, ep, row_perm=perm)
+    else:
+        out = ops.spconv(in_feats, weight, kmap.table, ep, zp_comp=zero_point_comp)
     return out, hashmap_kv, kmap
 
 

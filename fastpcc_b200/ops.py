@@ -277,8 +277,25 @@ def prelu_i32(inp, slope):
     return out
 
 
-def spconv(in_feats, weight, table, ep, zp_comp=None, out=None):
-    """Fused output-stationary sparse conv from a k-major neighbour table [kvol, n_out]."""
+def group_rows(table):
+    """Regroups the columns (output rows) of a k-major neighbour table by neighbour pattern.
+
+    -> (table_p, perm): table_p[:, j] = table[:, perm[j]], perm int32 [n_out] sorted by the pattern bit mask.
+    `spconv(..., table_p, ..., row_perm=perm)` gives the results of `spconv(..., table, ...)` while the kernel,
+    which can only skip an offset for a whole 128-row tile, meets tiles whose rows share their offsets."""
+    _need(table, torch.int32, 'table', 2)
+    kv, n_out = table.shape
+    masks = torch.empty(n_out, dtype=torch.int32, device=table.device)
+    _call('fpcc_kmap_row_masks', _p(table), kv, n_out, n_out, _p(masks), _s())
+    perm = torch.sort(masks, stable=True)[1].to(torch.int32)  # stable: neighbouring rows stay neighbours within a pattern
+    table_p = torch.empty_like(table)
+    _call('fpcc_kmap_permute', _p(table), kv, n_out, n_out, _p(perm), _p(table_p), n_out, _s())
+    return table_p, perm
+
+
+def spconv(in_feats, weight, table, ep, zp_comp=None, out=None, row_perm=None):
+    """Fused output-stationary sparse conv from a k-major neighbour table [kvol, n_out] (optionally regrouped
+    by `group_rows`: pass its permutation as row_perm)."""
     _need(in_feats, torch.int8, 'in_feats', 2)
     _need(weight, torch.int8, 'weight', 3)
     _need(table, torch.int32, 'table', 2)
@@ -293,8 +310,12 @@ def spconv(in_feats, weight, table, ep, zp_comp=None, out=None):
         pairs = _pairs_of(table)
         work = {'ops': 2.0 * pairs * c_in * c_out, 'mma_ops': 2.0 * ((n_out + 127) // 128 * 128) * kv * c_in * c_out,
                 'bytes': float(in_feats.numel() + weight.numel() + out.numel() * out.element_size() + 4 * table.numel())}
+    if row_perm is not None:
+        _need(row_perm, torch.int32, 'row_perm', 1)
+        if row_perm.numel() != n_out:
+            raise RuntimeError('spconv: row_perm must have one entry per output row')
     _call('fpcc_spconv_i8', _p(in_feats), in_feats.shape[0], c_in, _p(weight), kv, c_out, _p(table), n_out, n_out,
-          _p(zp_comp), C.byref(ep), _p(out), _s(), tag=tag, work=work)
+          _p(row_perm), _p(zp_comp), C.byref(ep), _p(out), _s(), tag=tag, work=work)
     return out
 
 
@@ -467,7 +488,7 @@ def _fargs(bias, residual, out_dtype):
 
 
 def spconv_f16(feats, weight_t, table, bias=None, act=ACT_NONE, slope=0.0, residual=None, post_act=ACT_NONE,
-               post_slope=0.0, out_dtype=None):
+               post_slope=0.0, out_dtype=None, row_perm=None):
     """Fused fp16/bf16 sparse conv: feats [n_in, c_in], weight_t [kvol, c_out, c_in] (same dtype), k-major table."""
     if feats.dtype not in _F_DT or weight_t.dtype != feats.dtype:
         raise RuntimeError(f'spconv_f16: fp16/bf16 features and weights of one dtype expected, got {feats.dtype}/{weight_t.dtype}')
@@ -483,8 +504,10 @@ def spconv_f16(feats, weight_t, table, bias=None, act=ACT_NONE, slope=0.0, resid
     work = None
     if _prof is not None:
         work = {'ops': 2.0 * _pairs_of(table) * c_in * c_out, 'mma_ops': 2.0 * ((n_out + 127) // 128 * 128) * kv * c_in * c_out}
+    if row_perm is not None:
+        _need(row_perm, torch.int32, 'row_perm', 1)
     _call('fpcc_spconv_f16', _p(feats), _F_DT[feats.dtype], feats.shape[0], c_in, _p(weight_t), kv, c_out, _p(table), n_out,
-          n_out, pb, act, float(slope), pr, post_act, float(post_slope), _p(out), _F_OUT[out_dtype], _s(),
+          n_out, _p(row_perm), pb, act, float(slope), pr, post_act, float(post_slope), _p(out), _F_OUT[out_dtype], _s(),
           tag='spconv_f16_tc', work=work)
     return out
 

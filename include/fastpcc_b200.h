@@ -81,6 +81,14 @@ int fpcc_kmap_compact(const int32_t *table, int kvol, int n_out, int64_t ld, int
                       int32_t *in_map, int32_t *out_map, int32_t *offsets /* [kvol+1] */,
                       void *workspace, size_t workspace_bytes, void *stream);
 
+/* Row grouping for fpcc_spconv_*: masks[o] = OR_k (table[k*ld+o] != 0) << min(k,31) (non-negative int32, the sort
+ * key), and out[k*ld_out + j] = table[k*ld + perm[j]] for a permutation `perm` of the output rows (e.g. the
+ * argsort of the masks).  No reference counterpart: the reference runs one GEMM per offset on pair lists
+ * (cuda_ops.py:132-169); this is the equivalent compaction for the output-stationary kernel. */
+int fpcc_kmap_row_masks(const int32_t *table, int kvol, int n_out, int64_t ld, int32_t *masks, void *stream);
+int fpcc_kmap_permute(const int32_t *table, int kvol, int n_out, int64_t ld, const int32_t *perm, int32_t *out,
+                      int64_t ld_out, void *stream);
+
 /* replaces Model.get_bin (lossl_coord_int/model.py:261-295): coords must be sorted so that the 8
  * children of a parent are contiguous (x-major Morton order, batch-major).  Writes parent coords
  * (coords>>1, unique_consecutive), the 8-bit child occupancy of each parent
@@ -153,10 +161,13 @@ int fpcc_prelu_i32(const int32_t *in, int64_t numel, const int32_t *slope, int32
  * (cuda_ops.py:383-403) in one output-stationary kernel, driven by the k-major neighbour table of
  * fpcc_kmap_lookup (no pair lists, no atomics, no int32 round trip through HBM).
  * in_feats [n_in,c_in] int8, weight [kvol,c_out,c_in] int8, out [n_out,c_out] (ep->out_type).
- * zp_comp: optional int32 [kvol,c_out] zero-point compensation rows (cuda_ops.py:157-162). */
+ * zp_comp: optional int32 [kvol,c_out] zero-point compensation rows (cuda_ops.py:157-162).
+ * row_perm: NULL, or int32 [n_out] when the table's columns were regrouped with fpcc_kmap_row_masks /
+ * fpcc_kmap_permute: column j then describes output row row_perm[j] (results are identical; the kernel skips an
+ * offset per 128-row tile, so tiles of equal neighbour patterns do ~2x less work on LiDAR levels). */
 int fpcc_spconv_i8(const int8_t *in_feats, int n_in, int c_in,
                    const int8_t *weight, int kvol, int c_out,
-                   const int32_t *nbr_table, int64_t ld, int n_out,
+                   const int32_t *nbr_table, int64_t ld, int n_out, const int32_t *row_perm,
                    const int32_t *zp_comp, const fpcc_epilogue *ep, void *out, void *stream);
 
 /* Fused LinearIn8W8.forward (cuda_ops.py:609-635): out = epilogue(A*W^T), bias inside the epilogue.
@@ -195,7 +206,7 @@ int fpcc_set_sm_budget(int sms);
  * act codes: 0 none, 1 ReLU, 2 LeakyReLU / single-slope PReLU.  Accumulation order is fixed (offset-major, K
  * ascending), so encoder and decoder of a float codec see identical bits run to run.  c_in % 8 == 0, >= 16. */
 int fpcc_spconv_f16(const void *feats, int dtype, int n_in, int c_in, const void *weight, int kvol, int c_out,
-                    const int32_t *nbr_table, int64_t ld, int n_out, const float *bias, int act, float slope,
+                    const int32_t *nbr_table, int64_t ld, int n_out, const int32_t *row_perm, const float *bias, int act, float slope,
                     const void *residual, int post_act, float post_slope, void *out, int out_type, void *stream);
 int fpcc_linear_f16(const void *A, int dtype, int m, int k, const void *W, int n, const int32_t *sel_row,
                     const int32_t *sel_out, const int32_t *sel_offsets, int n_groups, int n_sel, const float *bias,

@@ -50,6 +50,11 @@ for dbg in (sys.argv[4].split(',') if len(sys.argv) > 4 else ['0']):
     ms = t(lambda: ops.linear(f, w2, ep))
     print(f'[dbg {dbg}] linear n={n} {ch}->{ch}: {ms:.3f} ms  {2.0 * n * ch * ch / ms / 1e9:.1f} TOP/s')
 os.environ['FPCC_TC_DEBUG'] = '0'
+ms = t(lambda: ops.group_rows(table))
+tp, perm = ops.group_rows(table)
+print(f'group_rows n={n}: {ms:.3f} ms')
+ms = t(lambda: ops.spconv(f, w, tp, ep, row_perm=perm))
+print(f'conv on grouped rows: {ms:.3f} ms  algorithmic {alg / ms / 1e9:.1f} TOP/s   equal={bool((ops.spconv(f, w, tp, ep, row_perm=perm) == ops.spconv(f, w, table, ep)).all())}')
 ms = t(lambda: ops.kmap_lookup(keys, vals, C, (3, 3, 3), (1, 1, 1)))
 print(f'kmap lookup n={n}: {ms:.3f} ms  {(16 * n + 8 * 27 * n + 4 * 27 * n) / ms / 1e6:.1f} GB/s (algorithmic bytes)')
 ms = t(lambda: ops.hash_build(C))

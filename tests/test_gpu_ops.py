@@ -115,6 +115,15 @@ def test_fused_sparse_conv(ops, cin, cout, prelu, out8):
                            slope=dev(slope) if prelu else None)
     got = ops.spconv(dev(f), dev(w), table, ep)
     assert (got.cpu().numpy() == want).all()
+    if ops.gemm_engine(cin, cout, 27) == 'tc':
+        # rows regrouped by neighbour pattern (tile-level offset skipping): same values, original row order
+        tp, perm = ops.group_rows(table)
+        pn = perm.cpu().numpy()
+        assert (np.sort(pn) == np.arange(n)).all() and (tp.cpu().numpy() == table.cpu().numpy()[:, pn]).all()
+        masks = ((table.cpu().numpy()[:, pn] != 0).astype(np.int64) << np.arange(27)[:, None]).sum(0)
+        assert (np.diff(masks) >= 0).all()
+        got = ops.spconv(dev(f), dev(w), tp, ep, row_perm=perm)
+        assert (got.cpu().numpy() == want).all()
     # raw accumulator + mirror API of the reference (per-offset gather-GEMM-scatter, dense centre GEMM)
     raw = ops.spconv(dev(f), dev(w), table, ops.identity_epilogue(torch.device('cuda', 0)))
     assert (raw.cpu().numpy() == acc).all()
