@@ -312,3 +312,10 @@ def test_softmax_and_cdf_head(ops, S):
     lo = np.where(sym == 0, 0, w64[np.arange(n), np.maximum(sym - 1, 0)])
     hi = np.where(sym == S - 1, 65536, w64[np.arange(n), sym])
     assert ((rngs & 0xFFFF) == lo).all() and ((rngs >> 16) + 1 == hi - lo).all()
+    # the same rows as a column slice of a wider (padded) buffer: the kernels take the row pitch
+    pitch = (S + 15) // 16 * 16 + 16
+    wide = torch.full((n, pitch), 12345, dtype=torch.int32, device='cuda')
+    wide[:, :S] = dev(logits)
+    cdf2 = ops.quantize_cdf(wide[:, :S], ld=max(256, S)).cpu().numpy().view(np.uint16)
+    assert (cdf2 == cdf).all()
+    assert (ops.cdf_symbol_ranges(wide[:, :S], dev(sym)).cpu().numpy().view(np.uint32) == rngs).all()
