@@ -121,8 +121,8 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--frames', type=int, default=32, help='frames per step per GPU (coded together, one stream each)')
-    ap.add_argument('--groups', type=int, default=1, help='slices of the batch coded concurrently (CUDA streams)')
+    ap.add_argument('--frames', type=int, default=64, help='frames per step per GPU (coded together, one stream each)')
+    ap.add_argument('--groups', type=int, default=2, help='slices of the batch coded concurrently (CUDA streams)')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--cpu-stride', type=int, default=8, help='subsampling of the CPU baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -221,13 +221,19 @@ def main():
     int8_probe = ops.mma_i8_peak(20000, 256)  # back-to-back tcgen05.mma.kind::i8 on resident tiles, this GPU, now
     int8_peak = int8_probe
     conv = stats.get('spconv_tc', {'ms': 0.0, 'ops': 0.0, 'launches': 0, 'mma_ops': 0.0})
-    roof = {'bound': 'tensor', 'kernel': 'igemm_tc_kernel<conv> (tcgen05.mma.kind::i8)',
+    traffic = None
+    tpath = osp.join(osp.dirname(osp.abspath(__file__)), 'profiles', 'r01_conv_traffic.json')
+    if osp.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum of one captured launch (ncu --set full), committed
+        with open(tpath) as f:
+            traffic = json.load(f)
+    roof = {'bound': 'tensor', 'kernel': 'igemm_tc_persistent<CONV> (tcgen05.mma.kind::i8)',
             'achieved': (conv['ops'] / (conv['ms'] * 1e-3) / 1e12) if conv['ms'] else 0.0,
-            'peak': int8_peak, 'unit': 'TOP/s', 'traffic': None,
+            'peak': int8_peak, 'unit': 'TOP/s', 'traffic': traffic['dram_bytes'] if traffic else None,
+            'traffic_note': traffic.get('note') if traffic else None,
             'peak_source': 'measured in this run: fpcc_mma_i8_peak (tcgen05.mma.kind::i8 M128 N256 K32 back to back on all SMs); '
                            f'for scale, 2 x bf16_tflops of MEASURED_PEAKS.json ({peak_kind}) = {2.0 * peaks["bf16_tflops"]:.1f}',
             'launches': conv['launches'], 'ms_per_step': conv['ms'],
-            'executed_mma_tops': (conv['mma_ops'] / (conv['ms'] * 1e-3) / 1e12) if conv['ms'] else 0.0,
+            'executed_mma_tops': (conv.get('exec_ops', 0.0) / (conv['ms'] * 1e-3) / 1e12) if conv['ms'] else 0.0,
             'share_of_step': conv['ms'] / ms_dev if ms_dev else 0.0}
     roof['frac'] = roof['achieved'] / roof['peak'] if roof['peak'] else 0.0
     launches = sum(v['launches'] for v in stats.values())

@@ -277,6 +277,16 @@ def prelu_i32(inp, slope):
     return out
 
 
+def _tile_offsets_of(table):
+    """profiling only: sum over 128-row tiles of the number of offsets with a neighbour in the tile (= MMA steps run)"""
+    kv, n = table.shape
+    any_k = (table != 0)
+    pad = (-n) % 128
+    if pad:
+        any_k = torch.nn.functional.pad(any_k, (0, pad))
+    return float(any_k.view(kv, -1, 128).any(dim=2).sum().item())
+
+
 def group_rows(table):
     """Regroups the columns (output rows) of a k-major neighbour table by neighbour pattern.
 
@@ -309,6 +319,7 @@ def spconv(in_feats, weight, table, ep, zp_comp=None, out=None, row_perm=None):
         tag = 'spconv_' + gemm_engine(c_in, c_out, kv, zp_comp is not None)
         pairs = _pairs_of(table)
         work = {'ops': 2.0 * pairs * c_in * c_out, 'mma_ops': 2.0 * ((n_out + 127) // 128 * 128) * kv * c_in * c_out,
+                'exec_ops': 2.0 * 128 * _tile_offsets_of(table) * c_in * c_out,
                 'bytes': float(in_feats.numel() + weight.numel() + out.numel() * out.element_size() + 4 * table.numel())}
     if row_perm is not None:
         _need(row_perm, torch.int32, 'row_perm', 1)
