@@ -67,10 +67,13 @@ __global__ void __launch_bounds__(256) requant_scalar_i8_kernel(const int4 *__re
     const int64_t zp = ep.zp[0];
     const uint32_t mul = ep.mul[0];
     const int shift = ep.shift;
+    const bool has_slope = ep.slope != nullptr;  // optional Q6.25 PReLU in front (PReLUIn32Out32 -> Requant chains)
+    const int32_t slope = has_slope ? ep.slope[0] : 0;
     const int64_t half = shift > 0 ? (int64_t)1 << (shift - 1) : 0;
     const int64_t c0 = zp + half;
     const int64_t azp = zp < 0 ? -zp : zp;
-    bool fast = shift <= 31 && mul < (1u << 31) && (uint32_t)c0 != 0u && azp < ((int64_t)1 << 60);
+    bool fast = shift <= 31 && mul < (1u << 31) && (uint32_t)c0 != 0u && azp < ((int64_t)1 << 60) &&
+                (!has_slope || (slope >= 0 && slope <= (1 << 25)));
     int32_t B = 0, thr = 0;
     if (fast) {
         const int64_t num = ((int64_t)129 << shift) + azp;
@@ -96,14 +99,21 @@ __global__ void __launch_bounds__(256) requant_scalar_i8_kernel(const int4 *__re
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 if (fast) {
-                    const int32_t x = max(min(a[e], B), -B);
+                    int32_t x = a[e];
+                    if (has_slope) {  // 0 <= slope <= 2^25: |result| <= |x|, the product is <= 0 for x < 0 so the -1 applies
+                        int64_t p;
+                        asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(p) : "r"(x), "r"(slope), "l"((int64_t)((1 << 24) - 1)));
+                        const int32_t pv = (int32_t)__funnelshift_r((uint32_t)p, (uint32_t)((uint64_t)p >> 32), 25);
+                        x = x < 0 ? pv : x;
+                    }
+                    x = max(min(x, B), -B);
                     const int64_t c = (int64_t)(((uint64_t)c_hi << 32) | (uint64_t)(c_lo - (x < thr ? 1u : 0u)));
                     int64_t t;
                     asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(t) : "r"(x), "r"((int32_t)mul), "l"(c));
                     const int32_t r = (int32_t)__funnelshift_r((uint32_t)t, (uint32_t)((uint64_t)t >> 32), shift);
                     o[e] = max(min(r, 127), -128);
                 } else {
-                    const int64_t r = epi_value(a[e], 0, false, 0, mul, zp, shift);
+                    const int64_t r = epi_value(a[e], 0, has_slope, slope, mul, zp, shift);
                     o[e] = (int32_t)(r < -128 ? -128 : (r > 127 ? 127 : r));
                 }
             }
@@ -138,7 +148,7 @@ extern "C" int fpcc_requant(const int32_t *in, int64_t rows, int ch, const fpcc_
     int64_t total = rows * ch;
     cudaStream_t s = (cudaStream_t)stream;
     EpiParams ep = to_params(e);
-    if (e->out_type == FPCC_OUT_I8 && e->mul_is_scalar && !e->bias && !e->slope && total % 16 == 0 &&
+    if (e->out_type == FPCC_OUT_I8 && e->mul_is_scalar && !e->bias && total % 16 == 0 &&
         (((uintptr_t)in | (uintptr_t)out) & 15) == 0) {
         requant_scalar_i8_kernel<<<ew_grid(total / 16), 256, 0, s>>>((const int4 *)in, total / 16, ep, (uint4 *)out);
     } else if (ch % 4 == 0 && (((uintptr_t)in | (uintptr_t)out) & 15) == 0) {

@@ -376,6 +376,16 @@ class PReLUIn32Out32(nn.Module):
     def forward(self, input: torch.Tensor):
         return ops.prelu_i32(input, self.slope)
 
+    def slope_in_unit_range(self) -> bool:
+        """0 <= slope <= 1.0 (Q6.25), read back once per parameter version"""
+        key = self.slope._version
+        cache = getattr(self, '_unit_range', None)
+        if cache is None or cache[0] != key:
+            v = int(self.slope.item())
+            cache = (key, 0 <= v <= (1 << 25))
+            self._unit_range = cache
+        return cache[1]
+
 
 class RequantFxpToScaledInt8(LoadSaveUint32RequantMul):
     def __init__(self, eps=None, requant_mul_guard_bits=None):
@@ -403,9 +413,17 @@ class RequantFxpToScaledInt8(LoadSaveUint32RequantMul):
         self.int_zero_point_out[:] = (zero_point_out * (2 ** (SharedFxpShift + self.requant_shift.to(torch.float)))) \
             .round().to(torch.int64)
 
-    def forward(self, input: torch.Tensor) -> torch.Tensor:
-        # (Q8.23 x Qx.xx) >> (23 + xx) -> scaled int8; the single multiplier is broadcast by the kernel
-        ep = ops.make_epilogue(self.requant_mul, self.int_zero_point_out, SharedFxpShift + _shift_of(self), ops.OUT_I8)
+    def forward(self, input: torch.Tensor, prelu: Optional['PReLUIn32Out32'] = None) -> torch.Tensor:
+        """(Q8.23 x Qx.xx) >> (23 + xx) -> scaled int8; the single multiplier is broadcast by the kernel.
+        `prelu`: a PReLUIn32Out32 that precedes this requant; its pass is folded into this kernel when its slope
+        lies in [0, 1] (then the int32 saturation of the stand-alone PReLU cannot trigger, so the integers agree)."""
+        slope = None
+        if prelu is not None:
+            if prelu.slope_in_unit_range():
+                slope = prelu.slope
+            else:
+                input = prelu(input)
+        ep = ops.make_epilogue(self.requant_mul, self.int_zero_point_out, SharedFxpShift + _shift_of(self), ops.OUT_I8, slope=slope)
         return ops.requant(input, ep)
 
     def bit_levels(self):

@@ -27,6 +27,7 @@ keys, vals = ops.hash_build(C)
 table = ops.kmap_lookup(keys, vals, C, (3, 3, 3), (1, 1, 1))
 pairs = int(torch.count_nonzero(table).item())
 ep = ops.make_epilogue(mul, zp, 24, ops.OUT_I8, bias=bias, slope=slope)
+ep32 = ops.make_epilogue(mul, zp, 6, ops.OUT_I32, bias=bias, slope=slope)
 
 
 def t(fn, reps=5):
@@ -49,6 +50,8 @@ for dbg in (sys.argv[4].split(',') if len(sys.argv) > 4 else ['0']):
     print(f'[dbg {dbg}] conv  stride 2^{lvl} n={n} C={ch} pairs/pt={pairs / n:.2f}: {ms:.3f} ms  algorithmic {alg / ms / 1e9:.1f} TOP/s  executed {mma / ms / 1e9:.1f} TOP/s')
     ms = t(lambda: ops.linear(f, w2, ep))
     print(f'[dbg {dbg}] linear n={n} {ch}->{ch}: {ms:.3f} ms  {2.0 * n * ch * ch / ms / 1e9:.1f} TOP/s')
+    ms = t(lambda: ops.linear(f, w2, ep32))
+    print(f'[dbg {dbg}] linear int32 out n={n} {ch}->{ch}: {ms:.3f} ms  {2.0 * n * ch * ch / ms / 1e9:.1f} TOP/s  {n * ch * 5 / ms / 1e6:.0f} GB/s')
 os.environ['FPCC_TC_DEBUG'] = '0'
 ms = t(lambda: ops.group_rows(table))
 tp, perm = ops.group_rows(table)

@@ -235,6 +235,13 @@ def test_epilogue_ranges_fast_and_wide_paths(ops):
                 want = K.requant(x, np.full(64, mulv, np.uint32), zp, shift, np.int8)
                 got = ops.requant(dev(x), ops.make_epilogue(dev(mul1), dev(zp), shift, ops.OUT_I8)).cpu().numpy()
                 assert (got == want).all(), (shift, mulv, zpv)
+    # ... and with the PReLU in front (prelu_requant_to_int8, bias_prelu_requant.cu:6-37): slopes inside and outside [0, 1]
+    for slope_v in (0, 1 << 25, int(0.3 * (1 << 25)), -(1 << 22), 3 << 25):
+        for shift, mulv, zpv in ((7, 12345, 0), (23, (1 << 22) + 5, -77), (31, 3, 5 << 31), (36, (1 << 31) + 7, 0)):
+            mul1, zp, sl = np.array([mulv], np.uint32), np.array([zpv], np.int64), np.array([slope_v], np.int32)
+            want = K.requant(x, np.full(64, mulv, np.uint32), zp, shift, np.int8, slope=sl)
+            got = ops.requant(dev(x), ops.make_epilogue(dev(mul1), dev(zp), shift, ops.OUT_I8, slope=dev(sl))).cpu().numpy()
+            assert (got == want).all(), (slope_v, shift, mulv, zpv)
 
 
 def test_selected_linear_equals_masked_dense(ops):
