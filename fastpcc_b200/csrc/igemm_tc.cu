@@ -58,11 +58,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "{\n\t"
         ".reg .pred p;\n\t"
         "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"  // suspend-time hint: sleep in hardware, not in a spin loop
         "@p bra.uni WAIT_DONE;\n\t"
         "bra.uni WAIT_LOOP;\n\t"
         "WAIT_DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -145,6 +145,7 @@ struct TcArgs {
     // MODE_PAIRS
     const int32_t *in_idx, *out_idx, *offsets;
     int n_groups, n_pairs, bias_per_group;
+    int k24;  // (1 << 24) - 1, see FastCtx
     int dbg;  // FPCC_TC_DEBUG bitmask (experiments only): 1 skip A loads, 2 skip B loads, 4 skip epilogue math, 8 skip MMA,
               // 16 force the 64-bit epilogue
 };
@@ -221,6 +222,8 @@ struct FastCtx {
     uint32_t thr;
     int32_t slope, post;
     uint32_t c0_lo, c0_hi;   // zp + 2^(shift-1)
+    int64_t c_pos, c_neg;    // the same constant and constant - 1 as ready-made 64-bit addends of IMAD.WIDE
+    int64_t k24;             // 2^24 - 1 (kernel argument, so that it stays a register-pair addend)
     int shift;
     uint32_t ovf_add, ovf_lim;  // I32: result fits iff (hi + ovf_add) < ovf_lim (unsigned)
 };
@@ -240,8 +243,8 @@ __device__ __forceinline__ int32_t lds32(uint32_t addr) {
     asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ int32_t prelu_fast(int32_t v, int32_t slope) {  // 0 <= slope <= 2^25: |result| <= |v|
-    const int64_t p = mad_wide(v, slope, (int64_t)((1 << 24) - 1));  // v < 0 => product <= 0 => the -1 applies
+__device__ __forceinline__ int32_t prelu_fast(int32_t v, int32_t slope, int64_t k24 = (1 << 24) - 1) {  // 0 <= slope <= 2^25: |result| <= |v|
+    const int64_t p = mad_wide(v, slope, k24);  // v < 0 => product <= 0 => the -1 applies
     const int32_t pv = (int32_t)__funnelshift_r((uint32_t)p, (uint32_t)((uint64_t)p >> 32), 25);
     return v < 0 ? pv : v;
 }
@@ -259,17 +262,16 @@ __device__ __forceinline__ bool epi_chunk_fast(const uint32_t (&acc)[EC], const 
             bad |= (uint32_t)v + (1u << 30) > (1u << 31);  // keeps v + bias inside int32
         }
         v += ch.x;
-        if (SLOPE) v = prelu_fast(v, fx.slope);
+        if (SLOPE) v = prelu_fast(v, fx.slope, fx.k24);
         if (OUT != FPCC_OUT_I32) v = max(min(v, ch.z), ch.w);
-        const bool neg = ZP0 ? (v < 0) : (v < lds32(fx.thr + q * 4));
-        const int64_t c = (int64_t)(((uint64_t)fx.c0_hi << 32) | (uint64_t)(fx.c0_lo - (neg ? 1u : 0u)));  // c0_lo != 0
-        const int64_t t = mad_wide(v, ch.y, c);
+        // t = v*mul + zp + half - [v*mul + zp < 0]: one of two predicated IMAD.WIDE with the addend already formed
+        const int32_t thr = ZP0 ? 0 : lds32(fx.thr + q * 4);
+        const int64_t t = mad_wide(v, ch.y, v < thr ? fx.c_neg : fx.c_pos);
         const uint32_t lo = (uint32_t)t, hi = (uint32_t)((uint64_t)t >> 32);
         int32_t r = (int32_t)__funnelshift_r(lo, hi, fx.shift);
-        if (OUT == FPCC_OUT_I8) r = max(min(r, 127), -128);
-        else if (OUT == FPCC_OUT_I16) r = max(min(r, 32767), -32768);
-        else bad |= hi + fx.ovf_add >= fx.ovf_lim;
-        o[q] = r;
+        if (OUT == FPCC_OUT_I16) r = max(min(r, 32767), -32768);
+        if (OUT == FPCC_OUT_I32) bad |= hi + fx.ovf_add >= fx.ovf_lim;
+        o[q] = r;  // I8: saturated by the packing conversion (or the scalar store path)
     }
     return !bad;
 }
@@ -341,8 +343,9 @@ __device__ __forceinline__ void epi_store_chunk(int32_t (&o)[EC], const EpiCtx &
 #pragma unroll
             for (int t = 0; t < EC / 4; ++t) {
                 const int q = t * 4;
-                w[t] = (uint32_t)(o[q] & 0xff) | ((uint32_t)(o[q + 1] & 0xff) << 8) | ((uint32_t)(o[q + 2] & 0xff) << 16) |
-                       ((uint32_t)(o[q + 3] & 0xff) << 24);
+                uint32_t up;  // saturating pack: d = c[15:0] << 16 | sat8(a) << 8 | sat8(b)
+                asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(up) : "r"(o[q + 3]), "r"(o[q + 2]), "r"(0));
+                asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(w[t]) : "r"(o[q + 1]), "r"(o[q]), "r"(up));
             }
             store_words<EC / 4>((char *)optr, w, cx.nvalid);
         } else if (OUT == FPCC_OUT_I16) {
@@ -360,7 +363,7 @@ __device__ __forceinline__ void epi_store_chunk(int32_t (&o)[EC], const EpiCtx &
 #pragma unroll
         for (int q = 0; q < EC; ++q) {
             if (q < cx.nvalid) {
-                if (OUT == FPCC_OUT_I8) ((int8_t *)optr)[q] = (int8_t)o[q];
+                if (OUT == FPCC_OUT_I8) ((int8_t *)optr)[q] = (int8_t)max(min(o[q], 127), -128);
                 else if (OUT == FPCC_OUT_I16) ((int16_t *)optr)[q] = (int16_t)o[q];
                 else ((int32_t *)optr)[q] = o[q];
             }
@@ -761,6 +764,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) igemm_tc_persistent(TcArgs a, co
                 fx.chan = smem_u32(chan4_s + c0); fx.thr = smem_u32(thr_s + c0); fx.slope = slope; fx.post = post; fx.shift = shift;
                 const int64_t c0v = zp + cx.half;
                 fx.c0_lo = (uint32_t)c0v; fx.c0_hi = (uint32_t)((uint64_t)c0v >> 32);
+                fx.c_pos = c0v; fx.c_neg = c0v - 1; fx.k24 = (int64_t)a.k24;
                 fx.ovf_add = shift > 0 ? 1u << (shift - 1) : 0u; fx.ovf_lim = 1u << (shift & 31);
                 void *optr = (char *)out + (m * a.N + nb) * (ep.out_type == FPCC_OUT_I8 ? 1 : (ep.out_type == FPCC_OUT_I16 ? 2 : 4));
                 const bool vec = out_al && (a.N & 15) == 0;
@@ -909,6 +913,7 @@ static int launch_tc(TcArgs &a, const void *W, int64_t w_rows, int tiles_m, cons
                      cudaStream_t s) {
     int n_blocks_n = pick_tile(a.N, &a.n_tile, &a.tmem_cols);
     { const char *e = getenv("FPCC_TC_DEBUG"); a.dbg = e ? atoi(e) : 0; }
+    a.k24 = (1 << 24) - 1;
     CUtensorMap tmap;
     int rc = weight_tensor_map((const int8_t *)W, w_rows, a.K, a.n_tile, &tmap);
     if (rc) return rc;

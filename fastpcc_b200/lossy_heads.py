@@ -93,3 +93,41 @@ def rans_decode_with_cdf(bs: io.BytesIO, channels: int, offset: Optional[int] = 
     target = np.empty((1, shape_sum * channels), np.int32)
     coder.decode([payload], target)
     return target.reshape(shape_sum, channels), cdf
+
+
+@torch.no_grad()
+def get_keep(pred_f: torch.Tensor, coords: torch.Tensor, tensor_stride, max_stride, target_points_num=None) -> torch.Tensor:
+    """Top-k pruning mask of the lossy decoder (lossy_coord_v2/layers.py:151-180), device side.
+
+    pred_f [n] or [n,1]: occupancy logits of the candidate voxels `coords` [n,4] = (batch, x, y, z) of stride
+    `tensor_stride`; candidates are grouped by their ancestor voxel of stride `max_stride` (MinkowskiMaxPooling +
+    MinkowskiPoolingTranspose with kernel = stride = max_stride / tensor_stride): the best candidate of every group
+    is always kept; among the others, sample b keeps those above its (n_b - target_b)-th smallest logit
+    (`torch.kthvalue`), or above 0 when no target counts are given."""
+    f = pred_f.reshape(-1)
+    n = f.shape[0]
+    ts = torch.as_tensor(tensor_stride, device=coords.device, dtype=torch.int64)
+    ms = torch.as_tensor(max_stride, device=coords.device, dtype=torch.int64)
+    assert bool((ms % ts == 0).all())
+    c = coords.long()
+    anc = torch.div(c[:, 1:], ms, rounding_mode='floor')  # ancestor voxel index (coordinates are multiples of tensor_stride)
+    lo = anc.amin(0)
+    span = (anc.amax(0) - lo + 1)
+    key = ((c[:, 0] * span[0] + (anc[:, 0] - lo[0])) * span[1] + (anc[:, 1] - lo[1])) * span[2] + (anc[:, 2] - lo[2])
+    _, inv = torch.unique(key, return_inverse=True)
+    gmax = torch.full((int(inv.max().item()) + 1,), float('-inf'), dtype=f.dtype, device=f.device)
+    gmax.scatter_reduce_(0, inv, f, reduce='amax')
+    not_max = (f - gmax[inv]) != 0
+    if target_points_num is not None:
+        thr = torch.empty(len(target_points_num), dtype=f.dtype, device=f.device)
+        for b, tgt in enumerate(target_points_num):
+            rows = c[:, 0] == b
+            nb = int(rows.sum().item())
+            assert nb > tgt
+            thr[b] = torch.kthvalue(f[rows & not_max], nb - tgt, dim=0).values
+        threshold = thr[c[:, 0]]
+    else:
+        threshold = 0
+    keep = f > threshold
+    keep |= ~not_max
+    return keep

@@ -142,6 +142,14 @@ class CoordinateManager:
             self._kmaps[tag] = ops.kmap_lookup(keys, vals, self._coords[out_key], _triple(kernel_size), _triple(scale), convention=1)
         return self._kmaps[tag]
 
+    def grouped_kernel_table(self, in_key, out_key, kernel_size, scale):
+        """(table with its columns regrouped by neighbour pattern, row permutation) for the conv kernel, cached;
+        skipped (all-empty) offsets contribute exact zeros, so the fp32 sums are bit-identical to the plain table's."""
+        tag = ('kmap_grouped', in_key, out_key, _triple(kernel_size), _triple(scale))
+        if tag not in self._kmaps:
+            self._kmaps[tag] = ops.group_rows(self.kernel_table(in_key, out_key, kernel_size, scale))
+        return self._kmaps[tag]
+
     def kernel_map(self, in_key, out_key, stride=1, kernel_size=3, region_type=None, **_):
         """ME's dict {kernel index: [2, n] (in rows, out rows)} (used with kernel_size=1 by get_coord_mask,
         geo_lossl_em.py:306-317)."""
@@ -150,6 +158,9 @@ class CoordinateManager:
         off = offsets.tolist()
         return {k: torch.stack([in_map[off[k]: off[k + 1]], out_map[off[k]: off[k + 1]]]).long()
                 for k in range(table.shape[0]) if off[k + 1] > off[k]}
+
+
+GROUP_ROWS_MIN = 4096  # below this a conv is launch-bound and sorting the rows does not pay
 
 
 class SparseTensor:
@@ -272,7 +283,7 @@ class _ConvBase(nn.Module):
             self._cache = (key, w, b, cin_p, cout_p)
         return self._cache[1:]
 
-    def _run(self, f, table, act, slope, residual=None):
+    def _run(self, f, table, act, slope, residual=None, row_perm=None):
         w, b, cin_p, cout_p = self._weights()
         f = _pad_cols(_as_compute(f), cin_p).contiguous()
         if residual is not None:
@@ -281,7 +292,7 @@ class _ConvBase(nn.Module):
         if kv == 1:
             out = ops.linear_f16(f, w[0], bias=b, act=act, slope=slope, residual=residual)
         else:
-            out = ops.spconv_f16(f, w, table, bias=b, act=act, slope=slope, residual=residual)
+            out = ops.spconv_f16(f, w, table, bias=b, act=act, slope=slope, residual=residual, row_perm=row_perm)
         return out[:, :self.out_channels] if cout_p != self.out_channels else out
 
 
@@ -294,10 +305,14 @@ class MinkowskiConvolution(_ConvBase):
             out_key = x.coordinate_map_key if coordinates is None else coordinates
         else:
             out_key = cm.stride(x.coordinate_map_key, kg.kernel_stride) if coordinates is None else coordinates
-        table = None
+        table = perm = None
         if kg.kernel_volume > 1:
-            table = cm.kernel_table(x.coordinate_map_key, out_key, kg.kernel_size, x.coordinate_map_key.tensor_stride)
-        f = self._run(x.F, table, code, slope)
+            args = (x.coordinate_map_key, out_key, kg.kernel_size, x.coordinate_map_key.tensor_stride)
+            if cm.get_coordinates(out_key).shape[0] >= GROUP_ROWS_MIN:
+                table, perm = cm.grouped_kernel_table(*args)
+            else:
+                table = cm.kernel_table(*args)
+        f = self._run(x.F, table, code, slope, row_perm=perm)
         return SparseTensor(f, coordinate_map_key=out_key, coordinate_manager=cm)
 
 

@@ -57,6 +57,11 @@ def test_spconv_f16_matches_fp32_reference(dtype, cin, cout, ks):
     # determinism: the same launch twice gives identical bits (encoder/decoder of a float codec rely on it)
     again = ops.spconv_f16(f.cuda(), w.permute(0, 2, 1).contiguous().cuda(), table, bias=torch.from_numpy(b).cuda(), act=ops.ACT_RELU)
     assert torch.equal(got, again)
+    # rows regrouped by neighbour pattern: skipped offsets only ever contributed exact zeros, so the bits are the same
+    tp, perm = ops.group_rows(table)
+    grouped = ops.spconv_f16(f.cuda(), w.permute(0, 2, 1).contiguous().cuda(), tp, bias=torch.from_numpy(b).cuda(),
+                             residual=res.cuda(), post_act=ops.ACT_LEAKY, post_slope=0.2, out_dtype=torch.float32, row_perm=perm)
+    assert torch.equal(grouped, got2)
 
 
 @pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16])

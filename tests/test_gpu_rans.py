@@ -106,3 +106,34 @@ def test_lossy_heads_match_oracle_and_roundtrip():
     bs.seek(0)
     back, cdf2 = H.rans_decode_with_cdf(bs, channels=2)
     assert (back == t).all() and cdf2 == cdf
+
+
+def test_lossy_topk_keep_mask():
+    """lossy_coord_v2/layers.py:151-180 restated with numpy loops: group max always kept, k-th value threshold."""
+    from fastpcc_b200 import lossy_heads as H
+    rng = np.random.default_rng(5)
+    coords, tgt = [], []
+    for b in range(2):
+        xyz = np.unique(rng.integers(0, 13, (1500, 3)), axis=0) * 2          # stride-2 candidates, ~40 per stride-8 group
+        coords.append(np.concatenate([np.full((len(xyz), 1), b), xyz], 1))
+        tgt.append(len(xyz) // 3)
+    C = np.concatenate(coords).astype(np.int32)
+    f = rng.normal(size=len(C)).astype(np.float32)
+    keep = H.get_keep(torch.from_numpy(f).cuda(), torch.from_numpy(C).cuda(), [2, 2, 2], [8, 8, 8], list(tgt)).cpu().numpy()
+    groups = {}
+    for i, (b, x, y, z) in enumerate(C):
+        groups.setdefault((b, x // 8, y // 8, z // 8), []).append(i)
+    is_max = np.zeros(len(C), bool)
+    for idx in groups.values():
+        m = f[idx].max()
+        for i in idx:
+            is_max[i] = f[i] == m
+    want = is_max.copy()
+    for b in range(2):
+        rows = C[:, 0] == b
+        cand = np.sort(f[rows & ~is_max])
+        thr = cand[rows.sum() - tgt[b] - 1]
+        want |= rows & (f > thr)
+    assert (keep == want).all()
+    keep0 = H.get_keep(torch.from_numpy(f).cuda(), torch.from_numpy(C).cuda(), [2, 2, 2], [8, 8, 8]).cpu().numpy()
+    assert (keep0 == (is_max | (f > 0))).all()
