@@ -449,11 +449,11 @@ __device__ __forceinline__ void epi_chunk_f(const uint32_t (&acc)[EC], const int
     }
 }
 
-constexpr int P_EPI_WARPS = 16;
-constexpr int P_PROD_WARP0 = P_EPI_WARPS;
-constexpr int P_TMA_WARP = P_PROD_WARP0 + 4;
-constexpr int P_MMA_WARP = P_TMA_WARP + 1;
-constexpr int P_THREADS = (P_MMA_WARP + 1) * 32;
+// Warp roles of a CTA with EW epilogue warps (EW in {8, 12, 16}: 2, 3 or 4 column groups x 4 TMEM lane quarters):
+// warps [0, EW) epilogue, [EW, EW+4) gather producers, EW+4 weight producer (TMA), EW+5 TMEM owner + MMA issuer.
+// Fewer epilogue warps leave more issue slots (and registers: 128 / 96 / 80 per thread) to everyone else; the
+// gather-heavy conv prefers 12, the epilogue-bound linears 16.
+constexpr int EPI_WARPS_CONV = 12, EPI_WARPS_PAIRS = 16;
 
 struct PMeta {  // per-tile metadata, double buffered
     uint32_t kmask;
@@ -485,10 +485,11 @@ __device__ __forceinline__ void pairs_tile_lookup(const TcArgs &a, int tile_m, P
 
 // KIND: 0 = int8 x int8 -> int32 (kind::i8, integer requant epilogue), 1 = fp16, 2 = bf16 (kind::f16, fp32
 // accumulation, floating-point epilogue).  a.K is the contraction length in BYTES in every case.
-template <int MODE, int STAGES, int KIND>
-__global__ void __launch_bounds__(P_THREADS, 1) igemm_tc_persistent(TcArgs a, const __grid_constant__ CUtensorMap tmap_w,
+template <int MODE, int STAGES, int KIND, int EW>
+__global__ void __launch_bounds__((EW + 6) * 32, 1) igemm_tc_persistent(TcArgs a, const __grid_constant__ CUtensorMap tmap_w,
                                                                     EpiParams ep, FEpi fe, void *__restrict__ out, int tiles_m,
                                                                     int tiles_n) {
+    constexpr int P_EPI_WARPS = EW, P_PROD_WARP0 = EW, P_TMA_WARP = EW + 4, P_MMA_WARP = EW + 5, P_THREADS = (EW + 6) * 32;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int b_bytes = a.n_tile * TC_KB;
@@ -700,7 +701,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) igemm_tc_persistent(TcArgs a, co
         const int32_t slope = has_slope ? ep.slope[0] : 0, post = has_post ? ep.post_slope[0] : 0;
         const int64_t zp = KIND == 0 ? ep.zp[0] : 0;
         const int shift = ep.shift;
-        const int cols_grp = ((a.n_tile / (P_EPI_WARPS / 4) + EC - 1) / EC) * EC;  // columns per group, multiple of EC
+        const int cols_grp = (((a.n_tile + P_EPI_WARPS / 4 - 1) / (P_EPI_WARPS / 4) + EC - 1) / EC) * EC;  // columns per group, multiple of EC
         const int c_begin = min(a.n_tile, group * cols_grp), c_end = min(a.n_tile, c_begin + cols_grp);
         const bool out_al = ((uintptr_t)out & 15) == 0;
         int j = 0;
@@ -711,7 +712,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) igemm_tc_persistent(TcArgs a, co
             const bool have_acc = meta[slot].kmask != 0;
             const int pbase = (MODE == 1 && a.bias_per_group) ? meta[slot].group * a.N : 0;
             if (!chan_static) {  // grouped weights / several channel blocks: restage (bias, mul) of this tile's block
-                asm volatile("bar.sync 2, 512;" ::: "memory");  // every epilogue warp is done with the previous tile's values
+                asm volatile("bar.sync 2, %0;" ::"n"(P_EPI_WARPS * 32) : "memory");  // every epilogue warp is done with the previous tile's values
                 const int t = warp * 32 + lane;
                 if (t < a.n_tile) {
                     const int pc = pbase + min(n0 + t, a.N - 1);
@@ -723,7 +724,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) igemm_tc_persistent(TcArgs a, co
                         chan_s[t] = make_int2(fe.bias ? __float_as_int(__ldg(&fe.bias[pc])) : 0, 0);
                     }
                 }
-                asm volatile("bar.sync 2, 512;" ::: "memory");
+                asm volatile("bar.sync 2, %0;" ::"n"(P_EPI_WARPS * 32) : "memory");
             }
             const bool fast = KIND == 0 && *(volatile uint32_t *)fast_off == 0u;
             const int32_t *rows = rows_s + slot * rows_k * TC_M;
@@ -897,13 +898,14 @@ static int launch_stages(const TcArgs &a, const CUtensorMap &tmap, const EpiPara
                          int n_blocks_n, int grid, int rows_k, cudaStream_t s) {
     size_t smem = PSmem<STAGES>::bytes(a.n_tile, rows_k);
     FPCC_REQUIRE(smem <= TC_SMEM_MAX, "igemm_tc: %zu bytes of shared memory exceed the 227 KB limit", smem);
-    auto kern = igemm_tc_persistent<MODE, STAGES, KIND>;
+    constexpr int EW = MODE == 0 ? EPI_WARPS_CONV : EPI_WARPS_PAIRS;
+    auto kern = igemm_tc_persistent<MODE, STAGES, KIND, EW>;
     static bool configured = false;
     if (!configured) {
         FPCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX));
         configured = true;
     }
-    kern<<<grid, P_THREADS, smem, s>>>(a, tmap, ep, fe, out, tiles_m, n_blocks_n);
+    kern<<<grid, (EW + 6) * 32, smem, s>>>(a, tmap, ep, fe, out, tiles_m, n_blocks_n);
     FPCC_LAUNCH_CHECK();
     return FPCC_OK;
 }
