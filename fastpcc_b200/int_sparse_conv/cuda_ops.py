@@ -74,6 +74,12 @@ class KernelMap:
         return self.as_pair_lists()[i]
 
 
+def _publish_ready():
+    """Derived parameter tensors are cached on the module and may be picked up by another thread on another CUDA stream:
+    finish the kernels that fill them before the cache entry becomes visible (once per parameter version)."""
+    torch.cuda.current_stream().synchronize()
+
+
 def _as_kernel_map(in_out_maps, n_out, kernel_volume, idx_omit_map, device):
     if isinstance(in_out_maps, KernelMap):
         return in_out_maps
@@ -319,6 +325,7 @@ class SparseConvIn8Out8(_AffineIn8):
                 wf = torch.zeros((self.out_ch, kp), dtype=torch.int8, device=self.weight.device)
                 wf[:, :kv * self.in_ch] = self.weight.permute(1, 0, 2).reshape(self.out_ch, kv * self.in_ch)
                 cache = (key, wf)
+                _publish_ready()  # other CUDA streams (concurrent coding groups) may read the cached tensors next
                 self._patch_weight = cache
             patches = ops.gather_patches(in_feats, kmap.table, kp)
             return ops.linear(patches, cache[1], ep), hashmap_kv, kmap
@@ -501,6 +508,7 @@ class LinearIn8W8(_AffineIn8):
             ep = ops.make_epilogue(mul, self.int_zero_point_out, shift, out_type, bias=bias,
                                    slope=self.slope if self.with_prelu else None)
             cache = (key, w, ep)
+            _publish_ready()  # other CUDA streams (concurrent coding groups) may read the cached tensors next
             self._pad_cache = cache
         return cache[1], cache[2]
 
@@ -518,6 +526,7 @@ class LinearIn8W8(_AffineIn8):
             q = pat * float(q1) + (1.0 - pat) * float(q0)                       # [256, 8]
             table = (q @ w[:, C:].double().T).round().to(torch.int32).contiguous()  # exact: |values| < 2^53
             cache = (key, w[:, :C].contiguous(), table)
+            _publish_ready()  # other CUDA streams (concurrent coding groups) may read the cached tensors next
             self._bits_cache = cache
         _, w_main, table = cache
         return ops.linear(input, w_main, self.epilogue(True, row_bias=(table, occ)))

@@ -280,6 +280,7 @@ class _ConvBase(nn.Module):
             if self.bias is not None:
                 b = torch.zeros(cout_p, dtype=torch.float32, device=k.device)
                 b[:k.shape[2]] = self.bias.detach().reshape(-1).float()
+            torch.cuda.current_stream().synchronize()  # the cache may be read from another stream next
             self._cache = (key, w, b, cin_p, cout_p)
         return self._cache[1:]
 
@@ -392,6 +393,7 @@ class MinkowskiLinear(nn.Module):
             if lin.bias is not None:
                 b = torch.zeros(cout_p, dtype=torch.float32, device=w.device)
                 b[:lin.out_features] = lin.bias.detach().float()
+            torch.cuda.current_stream().synchronize()  # the cache may be read from another stream next
             self._cache = (key, w, b, cin_p, cout_p)
         _, w, b, cin_p, cout_p = self._cache
         f = _pad_cols(_as_compute(x.F), cin_p).contiguous()

@@ -70,3 +70,25 @@ def test_batched_frames_equal_single_frame_streams():
     blob = m.compress_partitions([None] + [torch.from_numpy(synth.with_batch(f)).cuda() for f in frames])
     assert blob == b''.join(len(s).to_bytes(3, 'little') + s for s in want)
     assert m.decompress_partitions(blob).shape[0] == sum(f.shape[0] for f in frames)
+
+
+def test_concurrent_groups_on_a_fresh_model():
+    """Groups run in threads on their own CUDA streams.  Derived parameter tensors (padded logits weights, occupancy
+    bias tables, im2col weights) are built lazily on first use: a FRESH model coded with several groups at once must
+    not let one stream read such a tensor before the stream that builds it has finished (they are published only
+    after a stream synchronisation).  Bytes must equal the single-group result, repeatedly."""
+    cfg = dict(channels=64, max_stride_wo_recurrent=32, max_stride=128, fea_stride=16)
+    rng = np.random.default_rng(11)
+    frames = []
+    for i in range(9):
+        xyz = synth.surface_cloud(30 + i, bits=9, n_target=3000 + 150 * i) + rng.integers(0, 50, 3).astype(np.int32)
+        frames.append(torch.from_numpy(synth.with_batch(xyz)).cuda())
+    ref_model, _ = _make(cfg)
+    want = ref_model.compress_batch(frames)
+    for trial in range(3):
+        m, _ = _make(cfg)                      # fresh caches every trial
+        got = m.compress_batch(frames, n_groups=3)
+        assert got == want, trial
+        rec = m.decompress_batch(got, n_groups=3)
+        rec1 = ref_model.decompress_batch(want)
+        assert all(torch.equal(a, b) for a, b in zip(rec, rec1))
