@@ -79,8 +79,10 @@ class ClockSampler:
 
 
 def make_frames(n, rank):
+    from concurrent.futures import ThreadPoolExecutor
     from fastpcc_b200 import synth
-    return [synth.with_batch(synth.lidar_frame(1000 + rank * 1000 + i)) for i in range(n)]
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:  # numpy releases the GIL in the heavy parts
+        return list(pool.map(lambda i: synth.with_batch(synth.lidar_frame(1000 + rank * 1000 + i)), range(n)))
 
 
 def run_reference(args, rank, world):
