@@ -91,13 +91,16 @@ class CoordinateManager:
         self._hash: Dict[CoordinateMapKey, Tuple[torch.Tensor, torch.Tensor]] = {}
         self._kmaps: Dict[tuple, torch.Tensor] = {}
         self._n_tags = 0
+        self._manager = self  # ME exposes the C++ manager as `_manager` (lossy_coord_v2/layers.py:153)
 
     # -- coordinate sets ----------------------------------------------------------------------------------
-    def _new_key(self, tensor_stride, coords) -> CoordinateMapKey:
-        key = CoordinateMapKey(tensor_stride, '')
+    def _new_key(self, tensor_stride, coords, string_id: str = '') -> CoordinateMapKey:
+        """ME names a coordinate map (tensor stride, string id): '' for inserted / strided maps, 'pruned' for the
+        outputs of MinkowskiPruning and the maps derived from them; a taken name gets a numeric suffix."""
+        key = CoordinateMapKey(tensor_stride, string_id)
         if key in self._coords:
             self._n_tags += 1
-            key = CoordinateMapKey(tensor_stride, f'#{self._n_tags}')
+            key = CoordinateMapKey(tensor_stride, f'{string_id}#{self._n_tags}')
         self._coords[key] = coords.contiguous()
         return key
 
@@ -130,9 +133,35 @@ class CoordinateManager:
             c[:, a + 1] = torch.div(c[:, a + 1], out_ts[a], rounding_mode='floor') * out_ts[a]
         c = c[morton_order(c, out_ts[0])]
         c = torch.unique_consecutive(c, dim=0)
-        key = self._new_key(out_ts, c)
+        key = self._new_key(out_ts, c, in_key.tag.split('#')[0])
         self._kmaps[tag] = key
         return key
+
+    def origin_map(self, key: CoordinateMapKey):
+        """ME: (origin key, list of row-index tensors, one per batch sample) of the global (origin) pooling map."""
+        tag = ('origin', key)
+        if tag not in self._kmaps:
+            b = self._coords[key][:, 0].long()
+            n_batch = int(b.max().item()) + 1 if b.numel() else 0
+            order = torch.argsort(b, stable=True)
+            counts = torch.bincount(b, minlength=n_batch).tolist()
+            self._kmaps[tag] = list(torch.split(order, counts))
+        return CoordinateMapKey(tuple(0 for _ in key.tensor_stride), 'origin'), self._kmaps[tag]
+
+    def get_coordinate_map_keys(self, tensor_stride):
+        ts = _triple(tensor_stride)
+        return [k for k in self._coords if tuple(k.tensor_stride) == ts]
+
+    def parent_rows(self, in_key: CoordinateMapKey, out_key: CoordinateMapKey) -> torch.Tensor:
+        """row of `out_key` (coarser) that contains each voxel of `in_key`, -1 if absent; cached"""
+        tag = ('parent', in_key, out_key)
+        if tag not in self._kmaps:
+            ots = torch.tensor(out_key.tensor_stride, device=self._coords[in_key].device, dtype=torch.int32)
+            par = self._coords[in_key].clone()
+            par[:, 1:] = torch.div(par[:, 1:], ots, rounding_mode='floor') * ots
+            keys, vals = self.hash_of(out_key)
+            self._kmaps[tag] = (ops.kmap_lookup(keys, vals, par.contiguous(), (1, 1, 1), (1, 1, 1), convention=1)[0] - 1).long()
+        return self._kmaps[tag]
 
     def kernel_table(self, in_key, out_key, kernel_size, scale) -> torch.Tensor:
         """k-major neighbour table [K, N_out] (input row + 1 | 0), ME offset convention, cached."""
@@ -203,6 +232,28 @@ class SparseTensor:
 
     def _like(self, f):
         return SparseTensor(f, coordinate_map_key=self.coordinate_map_key, coordinate_manager=self.coordinate_manager)
+
+    # -- per-sample views (ME: SparseTensor.decomposition_permutations / decomposed_coordinates / decomposed_features)
+    @property
+    def _batchwise_row_indices(self):
+        return self.coordinate_manager.origin_map(self.coordinate_map_key)[1]
+
+    @property
+    def decomposition_permutations(self):
+        return self._batchwise_row_indices
+
+    @property
+    def decomposed_coordinates(self):
+        c = self.C
+        return [c[rows, 1:] for rows in self._batchwise_row_indices]
+
+    @property
+    def decomposed_features(self):
+        return [self._F[rows] for rows in self._batchwise_row_indices]
+
+    @property
+    def decomposed_coordinates_and_features(self):
+        return self.decomposed_coordinates, self.decomposed_features
 
     def __add__(self, o):
         if isinstance(o, SparseTensor):
@@ -446,9 +497,46 @@ class MinkowskiBatchNorm(nn.Module):
         return x._like(self.bn(x.F.float()).to(x.F.dtype))
 
 
+class MinkowskiMaxPooling(nn.Module):
+    """kernel_size == stride (non-overlapping cells), as used by the top-k pruning (lossy_coord_v2/layers.py:159):
+    max of the features of every coarse cell.  forward(x, coordinates=key) pools onto an existing coarser key."""
+
+    def __init__(self, kernel_size, stride=1, dilation=1, kernel_generator=None, dimension=3):
+        super().__init__()
+        self.kernel_size, self.stride = _triple(kernel_size), _triple(stride)
+        assert self.kernel_size == self.stride, 'only non-overlapping pooling (kernel_size == stride) is used by the codecs'
+
+    def forward(self, x: SparseTensor, coordinates: Optional[CoordinateMapKey] = None) -> SparseTensor:
+        cm = x.coordinate_manager
+        out_key = cm.stride(x.coordinate_map_key, self.stride) if coordinates is None else coordinates
+        par = cm.parent_rows(x.coordinate_map_key, out_key)
+        assert bool((par >= 0).all()), 'max pooling: a voxel has no cell in the target coordinate set'
+        n_out = cm.get_coordinates(out_key).shape[0]
+        f = x.F
+        out = torch.full((n_out, f.shape[1]), float('-inf'), dtype=f.dtype, device=f.device)
+        out.scatter_reduce_(0, par[:, None].expand(-1, f.shape[1]), f, reduce='amax')
+        return SparseTensor(out, coordinate_map_key=out_key, coordinate_manager=cm)
+
+
+class MinkowskiPoolingTranspose(nn.Module):
+    """kernel_size == stride un-pooling onto an existing finer key: every fine voxel receives its cell's feature."""
+
+    def __init__(self, kernel_size, stride, dilation=1, kernel_generator=None, expand_coordinates=False, dimension=3):
+        super().__init__()
+        self.kernel_size, self.stride = _triple(kernel_size), _triple(stride)
+        assert self.kernel_size == self.stride
+
+    def forward(self, x: SparseTensor, coordinates: CoordinateMapKey) -> SparseTensor:
+        cm = x.coordinate_manager
+        par = cm.parent_rows(coordinates, x.coordinate_map_key)
+        f = x.F[par.clamp(min=0)]
+        f = torch.where((par >= 0)[:, None], f, torch.zeros_like(f))
+        return SparseTensor(f, coordinate_map_key=coordinates, coordinate_manager=cm)
+
+
 class MinkowskiPruning(nn.Module):
     def forward(self, x: SparseTensor, mask: torch.Tensor) -> SparseTensor:
         assert mask.dtype == torch.bool and mask.shape[0] == x.F.shape[0]
         cm = x.coordinate_manager
-        key = cm._new_key(x.coordinate_map_key.tensor_stride, x.C[mask])
+        key = cm._new_key(x.coordinate_map_key.tensor_stride, x.C[mask], 'pruned')
         return SparseTensor(x.F[mask], coordinate_map_key=key, coordinate_manager=cm)

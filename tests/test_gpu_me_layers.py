@@ -109,3 +109,46 @@ def test_blocks_match_fp32_reference():
     km = y4.coordinate_manager.kernel_map(y5.coordinate_map_key, y4.coordinate_map_key, kernel_size=1)
     assert list(km) == [0] and km[0].shape == (2, n)
     assert (km[0][1].cpu() == torch.nonzero(mask.cpu())[:, 0]).all()
+
+
+def test_max_pool_unpool_and_per_sample_views_drive_topk_pruning():
+    """The lossy decoder's top-k pruning (lossy_coord_v2/layers.py:151-180) written against the ME surface --
+    MinkowskiMaxPooling / MinkowskiPoolingTranspose onto the coarse key, decomposition_permutations, kthvalue --
+    must select the same voxels as lossy_heads.get_keep (scatter-reduce formulation) and as a numpy loop."""
+    import numpy as np
+    from fastpcc_b200 import me as ME, lossy_heads as H
+    rng = np.random.default_rng(3)
+    cs = []
+    for b in range(2):
+        xyz = np.unique(rng.integers(0, 13, (1500, 3)), axis=0) * 2
+        cs.append(np.concatenate([np.full((len(xyz), 1), b), xyz], 1))
+    C = torch.from_numpy(np.concatenate(cs).astype(np.int32)).cuda()
+    C = C[ME.morton_order(C, 2)].contiguous()
+    f = torch.from_numpy(rng.normal(size=(C.shape[0], 1)).astype(np.float32)).cuda()
+    pred = ME.SparseTensor(f, C, tensor_stride=2)
+    cm = pred.coordinate_manager
+    coarse = cm.stride(pred.coordinate_map_key, 4)                       # stride 8 cells
+    assert len(cm._manager.get_coordinate_map_keys([8, 8, 8])) == 1
+    pool, unpool = ME.MinkowskiMaxPooling(4, 4, dimension=3), ME.MinkowskiPoolingTranspose(4, 4, dimension=3)
+    local_max = unpool(pool(pred, coarse), pred.coordinate_map_key)
+    not_max = (pred.F - local_max.F).squeeze(1) != 0
+    targets = [int(r.shape[0]) // 3 for r in pred.decomposition_permutations]
+    assert [c.shape[0] for c in pred.decomposed_coordinates] == [int((C[:, 0] == b).sum()) for b in range(2)]
+    thr = []
+    for tgt, rows in zip(targets, pred.decomposition_permutations):
+        sample = pred.F[rows]
+        thr.append(torch.kthvalue(sample[not_max[rows]], sample.shape[0] - tgt, dim=0).values)
+    thr = torch.cat(thr)[pred.C[:, 0].long()]
+    keep = (pred.F.squeeze(1) > thr) | ~not_max
+    assert torch.equal(keep, H.get_keep(pred.F, pred.C, [2, 2, 2], [8, 8, 8], targets))
+    # numpy restatement of the cell maximum
+    Cn, fn = C.cpu().numpy(), f.cpu().numpy()[:, 0]
+    cell = {}
+    for i, (b, x, y, z) in enumerate(Cn):
+        cell.setdefault((b, x // 8, y // 8, z // 8), []).append(i)
+    want = np.zeros(len(Cn), bool)
+    for idx in cell.values():
+        want[idx] = fn[idx] != fn[idx].max()
+    assert (not_max.cpu().numpy() == want).all()
+    pruned = ME.MinkowskiPruning()(pred, keep)
+    assert pruned.coordinate_map_key.tag == 'pruned' and pruned.F.shape[0] == int(keep.sum())
