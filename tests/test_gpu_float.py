@@ -85,3 +85,40 @@ def test_linear_f16_and_selected_children(dtype):
     dense = (a.float().numpy() @ w8.float().numpy().T).reshape(m, 8, n)
     bits = ((occ[:, None] >> np.arange(7, -1, -1)[None]) & 1).astype(bool)
     assert _rel(got, dense[bits]) < TOL[dtype]
+
+
+def test_torchsparse_style_layers_match_fp32_reference():
+    """fastpcc_b200.torchsparse_nn (Conv3d / functional conv3d / Block of lossl_coord/model.py:34-46,356-374,645-660)
+    against the fp32 oracle on the reference's own kernel-map convention (hashmap_cuda.cuh:221-275), incl. the strided
+    2x2x2 `get_bin` convolution with an explicit weight."""
+    from fastpcc_b200 import synth, torchsparse_nn as TS
+    from fastpcc_b200.sparse_tensor import SparseTensor
+    from oracle import int_ops as K
+    rng = np.random.default_rng(21)
+    xyz = synth.surface_cloud(4, bits=7, n_target=6000)
+    C = synth.with_batch(xyz)
+    C = C[np.lexsort((C[:, 3], C[:, 2], C[:, 1], C[:, 0]))]
+    ch = 32
+    f = rng.normal(0, 1, (C.shape[0], ch)).astype(np.float32)
+    x = SparseTensor(torch.from_numpy(f).cuda().half(), torch.from_numpy(C).cuda(), 1)
+    blk = TS.Block(ch).cuda()
+    with torch.no_grad():
+        blk.act.weight.fill_(0.2)
+        blk.act2.weight.fill_(0.1)
+    got = blk(x).F.float().cpu().numpy()
+    table = K.lookup_coords(C, C, (3, 3, 3), (1, 1, 1))                        # [K, n], input row + 1, 0 = none
+    f16 = x.F.float().cpu().numpy()
+    w1, w2 = (m.kernel.detach().half().float().cpu().numpy() for m in (blk.conv, blk.conv2))
+    b1, b2 = (m.bias.detach().float().cpu().numpy() for m in (blk.conv, blk.conv2))
+    h = FO.act(FO.sparse_conv_f32(f16, w1, table, b1), 'leaky_relu', 0.2).astype(np.float16).astype(np.float32)
+    want = FO.act(FO.sparse_conv_f32(h, w2, table, b2) + f16, 'leaky_relu', 0.1)
+    assert _rel(got, want) < TOL[torch.float16]
+    # get_bin: ones features, fold kernel 2x2x2 stride 2 with an explicit [8, 1, 1] weight of powers of two
+    ones = SparseTensor(torch.ones((C.shape[0], 1), device='cuda'), torch.from_numpy(C).cuda(), 1)
+    fold = torch.tensor([128., 64., 32., 16., 8., 4., 2., 1.], device='cuda').reshape(8, 1, 1)
+    ret = TS.conv3d(ones, weight=fold, kernel_size=(2, 2, 2), bias=None, stride=(2, 2, 2), out_dtype=torch.float32)
+    Cp = np.unique(np.concatenate([C[:, :1], C[:, 1:] >> 1], 1), axis=0)
+    assert (ret.C.cpu().numpy() == Cp).all() and ret.stride == (2, 2, 2)
+    tb = K.lookup_coords(C, Cp, (2, 2, 2), (2, 2, 2))
+    occ = ((tb != 0) * fold.reshape(8, 1).cpu().numpy()).sum(0)
+    assert (ret.F.cpu().numpy()[:, 0] == occ).all()                            # exact: small integers in fp16 / fp32
