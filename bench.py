@@ -214,6 +214,12 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()) / steps, clocks
 
+    # size-independent property at the full workload: the codec is lossless -- every decoded frame is the input's voxel
+    # set (checked once, outside the timed region, on the concurrent-group path that is timed)
+    rec = step_device()
+    lossless = all(torch.equal(torch.unique(r, dim=0), torch.unique(x[:, 1:], dim=0)) for r, x in zip(rec, frames_dev))
+    assert lossless, 'decoded frames differ from the input: the measured path is not a valid codec run'
+    del rec
     ms_dev, clocks = timed(step_device, args.steps, args.warmup, sample_clocks=True)
     ms_e2e, _ = timed(step_e2e, args.steps, max(1, args.warmup - 1))
     pts_all = torch.tensor([n_pts], dtype=torch.float64, device=dev)
@@ -266,7 +272,8 @@ def main():
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_dev,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int8', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'frames_per_step_per_gpu': args.frames, 'concurrent_groups': G, 'points_per_step': pts_all,
-                       'l2': 'flushed between timed iterations (256 MB write)', 'weights': 'seeded random int8 (seed 7)'},
+                       'l2': 'flushed between timed iterations (256 MB write)', 'weights': 'seeded random int8 (seed 7)',
+                       'roundtrip_lossless': bool(lossless)},
             'clocks': clocks,
             'e2e': {'value': pts_all / (ms_e2e * 1e-3) / 1e6, 'unit': 'Mpts/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': ms_e2e},
