@@ -45,6 +45,18 @@ def _out_coords(x: SparseTensor, stride: Tuple[int, int, int]):
     return out_stride, torch.unique(c, dim=0)
 
 
+def _kernel_map(input: SparseTensor, out_c: torch.Tensor, ks, st) -> KernelMap:
+    caches = input._caches
+    tag = (input.stride, ks, st)
+    entry = caches.kmaps.get(tag)
+    kmap = entry.get('in_out_maps') if entry is not None else None
+    if not isinstance(kmap, KernelMap):
+        kmap, hk = build_kernel_map(input.C, out_c, ks, st, caches.hashmaps.get(input.stride))
+        caches.hashmaps.setdefault(input.stride, hk)
+        caches.kmaps.setdefault(tag, {})['in_out_maps'] = kmap
+    return kmap
+
+
 def conv3d(input: SparseTensor, weight: torch.Tensor, kernel_size=3, bias: Optional[torch.Tensor] = None, stride=1,
            padding=0, dilation=1, transposed: bool = False, generative: bool = False, config=None, training: bool = False,
            fused_act: int = ops.ACT_NONE, slope: float = 0.0, residual: Optional[torch.Tensor] = None,
@@ -58,29 +70,35 @@ def conv3d(input: SparseTensor, weight: torch.Tensor, kernel_size=3, bias: Optio
     assert w.shape[0] == kv, f'weight has {w.shape[0]} offsets, kernel {ks} needs {kv}'
     c_in, c_out = w.shape[1], w.shape[2]
     cin_p, cout_p = max(16, (c_in + 7) // 8 * 8), max(16, c_out)
-    if _weight_t is None:
+    training = torch.is_grad_enabled() and (weight.requires_grad or input.F.requires_grad)
+    if _weight_t is None and not training:
         _weight_t = torch.zeros((kv, cout_p, cin_p), dtype=_COMPUTE, device=w.device)
         _weight_t[:, :c_out, :c_in] = w.detach().permute(0, 2, 1).to(_COMPUTE)
     b = None
     if bias is not None:
         b = torch.zeros(cout_p, dtype=torch.float32, device=w.device)
         b[:c_out] = bias.detach().reshape(-1).float()
-    f = _pad_cols(input.F.to(_COMPUTE), cin_p).contiguous()
+    f = None if training else _pad_cols(input.F.to(_COMPUTE), cin_p).contiguous()
     if residual is not None:
         residual = _pad_cols(residual.to(out_dtype or _COMPUTE), cout_p).contiguous()
     out_stride, out_c = _out_coords(input, st)
     caches = input._caches
+    if training:
+        # training: differentiable path (fastpcc_b200/autograd.py); activations / residuals stay in torch
+        assert fused_act == ops.ACT_NONE and residual is None and post_act == ops.ACT_NONE, 'fused epilogues are inference only'
+        from . import autograd
+        kmap = _kernel_map(input, out_c, ks, st)
+        out = autograd.sparse_conv(input.F, w, bias, kmap.table, _COMPUTE)
+        caches.cmaps.setdefault(input.stride, (input.C, input.spatial_range))
+        caches.cmaps.setdefault(out_stride, (out_c, None))
+        ret = SparseTensor(out, out_c, out_stride, None)
+        ret._caches = caches
+        return ret
     if kv == 1 and st == (1, 1, 1):
         out = ops.linear_f16(f, _weight_t[0], bias=b, act=fused_act, slope=slope, residual=residual, post_act=post_act,
                              post_slope=post_slope, out_dtype=out_dtype)
     else:
-        tag = (input.stride, ks, st)
-        entry = caches.kmaps.get(tag)
-        kmap = entry.get('in_out_maps') if entry is not None else None
-        if not isinstance(kmap, KernelMap):
-            kmap, hk = build_kernel_map(input.C, out_c, ks, st, caches.hashmaps.get(input.stride))
-            caches.hashmaps.setdefault(input.stride, hk)
-            caches.kmaps.setdefault(tag, {})['in_out_maps'] = kmap
+        kmap = _kernel_map(input, out_c, ks, st)
         if kmap.table.shape[1] >= GROUP_ROWS_MIN:
             table, perm = kmap.grouped()
         else:
@@ -129,9 +147,10 @@ class Conv3d(nn.Module):
 
     def forward(self, input: SparseTensor, fused_act: int = ops.ACT_NONE, slope: float = 0.0, residual=None,
                 post_act: int = ops.ACT_NONE, post_slope: float = 0.0, out_dtype=None) -> SparseTensor:
+        training = torch.is_grad_enabled() and (self.kernel.requires_grad or input.F.requires_grad)
         return conv3d(input, self.kernel, self.kernel_size, self.bias, self.stride, dilation=self.dilation,
                       fused_act=fused_act, slope=slope, residual=residual, post_act=post_act, post_slope=post_slope,
-                      out_dtype=out_dtype, _weight_t=self._weight_t())
+                      out_dtype=out_dtype, _weight_t=None if training else self._weight_t())
 
 
 class Block(nn.Module):
@@ -147,6 +166,12 @@ class Block(nn.Module):
         self.act2 = nn.PReLU()
 
     def forward(self, org: SparseTensor) -> SparseTensor:
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            x = self.conv(org)                     # training: the reference's own sequence, autograd through every step
+            x.F = self.act(x.F)
+            x = self.conv2(x)
+            x.F = self.act2(x.F + org.F)
+            return x
         x = self.conv(org, fused_act=ops.ACT_LEAKY, slope=float(self.act.weight.detach().reshape(-1)[0]))
         return self.conv2(x, residual=org.F, post_act=ops.ACT_LEAKY, post_slope=float(self.act2.weight.detach().reshape(-1)[0]),
                           out_dtype=org.F.dtype if org.F.dtype in (torch.float16, torch.bfloat16, torch.float32) else None)

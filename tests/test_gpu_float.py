@@ -105,7 +105,8 @@ def test_torchsparse_style_layers_match_fp32_reference():
     with torch.no_grad():
         blk.act.weight.fill_(0.2)
         blk.act2.weight.fill_(0.1)
-    got = blk(x).F.float().cpu().numpy()
+    with torch.no_grad():                                                      # inference: fused epilogues
+        got = blk(x).F.float().cpu().numpy()
     table = K.lookup_coords(C, C, (3, 3, 3), (1, 1, 1))                        # [K, n], input row + 1, 0 = none
     f16 = x.F.float().cpu().numpy()
     w1, w2 = (m.kernel.detach().half().float().cpu().numpy() for m in (blk.conv, blk.conv2))
@@ -122,3 +123,45 @@ def test_torchsparse_style_layers_match_fp32_reference():
     tb = K.lookup_coords(C, Cp, (2, 2, 2), (2, 2, 2))
     occ = ((tb != 0) * fold.reshape(8, 1).cpu().numpy()).sum(0)
     assert (ret.F.cpu().numpy()[:, 0] == occ).all()                            # exact: small integers in fp16 / fp32
+
+
+def test_sparse_conv_autograd_matches_dense_reference():
+    """Training slice: gradients of the fused sparse conv w.r.t. features, weights and bias against
+    torch autograd through the same sum written with index_select + matmul in fp32; then a Block trains one SGD step."""
+    from fastpcc_b200 import synth, autograd as AG, ops, torchsparse_nn as TS
+    from fastpcc_b200.sparse_tensor import SparseTensor
+    rng = np.random.default_rng(8)
+    C = synth.with_batch(synth.surface_cloud(6, bits=7, n_target=3000))
+    C = torch.from_numpy(C[np.lexsort((C[:, 3], C[:, 2], C[:, 1], C[:, 0]))]).cuda()
+    n, cin, cout = C.shape[0], 24, 40
+    keys, vals = ops.hash_build(C)
+    for ks, st, out_c in (((3, 3, 3), (1, 1, 1), C),
+                          ((2, 2, 2), (2, 2, 2), torch.unique(torch.cat([C[:, :1], C[:, 1:] >> 1], 1), dim=0))):
+        table = ops.kmap_lookup(keys, vals, out_c.contiguous(), ks, st)
+        kv = table.shape[0]
+        a = torch.randn(n, cin, device='cuda').half().float().requires_grad_()
+        w = (torch.randn(kv, cin, cout, device='cuda') / (kv * cin) ** 0.5).half().float().requires_grad_()
+        b = torch.randn(cout, device='cuda').requires_grad_()
+        gout = torch.randn(table.shape[1], cout, device='cuda').half().float()
+        out = AG.sparse_conv(a, w, b, table)
+        out.backward(gout)
+        got = (out.detach(), a.grad.clone(), w.grad.clone(), b.grad.clone())
+        a.grad = w.grad = b.grad = None
+        a_pad = torch.cat([torch.zeros(1, cin, device='cuda'), a])          # row 0 = "no neighbour"
+        ref = sum(a_pad[table[k].long()] @ w[k] for k in range(kv)) + b
+        ref.backward(gout)
+        for g_, r_, name in zip(got, (ref.detach(), a.grad, w.grad, b.grad), ('out', 'd_feats', 'd_weight', 'd_bias')):
+            err = float((g_ - r_).abs().max() / r_.abs().max().clamp(min=1e-6))
+            assert err < 1e-2, (ks, name, err)
+    blk = TS.Block(32).cuda()
+    x = SparseTensor(torch.randn(n, 32, device='cuda'), C, 1)
+    opt = torch.optim.SGD(blk.parameters(), lr=1e-2)
+    losses = []
+    for _ in range(3):
+        opt.zero_grad()
+        loss = blk(x).F.float().pow(2).mean()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss.detach()))
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in blk.parameters())
+    assert losses[-1] < losses[0]
