@@ -470,6 +470,7 @@ extern "C" int fpcc_slot_table(const int32_t *child_parent, const uint8_t *child
 // contraction of K = kvol*C_in per output row, which the tensor-core linear kernel then runs.
 // ---------------------------------------------------------------------------------------------
 namespace fpcc {
+// Generic form: one thread per (output row, offset); byte-granular, any C.
 __global__ void __launch_bounds__(256) gather_patches_kernel(const int8_t *__restrict__ feats, int c,
                                                              const int32_t *__restrict__ table, int64_t ld, int kvol, int n_out,
                                                              int8_t *__restrict__ patches, int kp) {
@@ -478,11 +479,35 @@ __global__ void __launch_bounds__(256) gather_patches_kernel(const int8_t *__res
     if (o >= n_out) return;
     int32_t v = table[(int64_t)k * ld + o];
     int8_t *dst = patches + (int64_t)o * kp + k * c;
-    if (c == 8 && (((uintptr_t)feats | (uintptr_t)patches) & 7) == 0 && (kp & 7) == 0) {
-        *reinterpret_cast<uint2 *>(dst) = v ? *reinterpret_cast<const uint2 *>(feats + (int64_t)(v - 1) * 8) : make_uint2(0, 0);
-    } else {
-        for (int j = 0; j < c; ++j) dst[j] = v ? feats[(int64_t)(v - 1) * c + j] : (int8_t)0;
+    for (int j = 0; j < c; ++j) dst[j] = v ? feats[(int64_t)(v - 1) * c + j] : (int8_t)0;
+}
+
+// C = 8 (occupancy-bit embeds) with 8-byte aligned rows: a block owns 32 output rows.  The table is read with the
+// rows of one offset contiguous (coalesced), the 8-byte feature rows are gathered into a shared-memory tile
+// [32 rows][kp], and the tile leaves as whole 16-byte vectors of contiguous patch rows.
+constexpr int GP_ROWS = 32;
+__global__ void __launch_bounds__(256) gather_patches8_kernel(const int8_t *__restrict__ feats, const int32_t *__restrict__ table,
+                                                              int64_t ld, int kvol, int n_out, int8_t *__restrict__ patches, int kp) {
+    extern __shared__ __align__(16) uint8_t tile[];  // [GP_ROWS][kp]
+    const int o0 = blockIdx.x * GP_ROWS;
+    const int rows = min(GP_ROWS, n_out - o0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = warp; k < kvol; k += 8) {   // lanes = consecutive rows of one offset
+        uint2 val = make_uint2(0, 0);
+        if (lane < rows) {
+            const int32_t v = __ldg(&table[(int64_t)k * ld + o0 + lane]);
+            if (v) val = __ldg(reinterpret_cast<const uint2 *>(feats) + (v - 1));
+        }
+        *reinterpret_cast<uint2 *>(tile + lane * kp + k * 8) = val;
     }
+    for (int i = threadIdx.x; i < GP_ROWS * ((kp - kvol * 8) / 8); i += 256) {  // zero the pad columns
+        const int per = (kp - kvol * 8) / 8;
+        *reinterpret_cast<uint2 *>(tile + (i / per) * kp + kvol * 8 + (i % per) * 8) = make_uint2(0, 0);
+    }
+    __syncthreads();
+    const int n16 = rows * kp / 16;  // kp % 16 == 0: the rows of the block are one contiguous byte range
+    uint4 *dst = reinterpret_cast<uint4 *>(patches + (int64_t)o0 * kp);
+    for (int i = threadIdx.x; i < n16; i += 256) dst[i] = reinterpret_cast<const uint4 *>(tile)[i];
 }
 }  // namespace fpcc
 
@@ -490,8 +515,13 @@ extern "C" int fpcc_gather_patches(const int8_t *feats, int c, const int32_t *ta
                                    int8_t *patches, int kp, void *stream) {
     FPCC_REQUIRE(feats && table && patches, "gather_patches: NULL pointer");
     FPCC_REQUIRE(c > 0 && kvol > 0 && n_out > 0 && ld >= n_out && kp >= kvol * c, "gather_patches: bad sizes");
-    dim3 grid(fpcc::ceil_div(n_out, 256), kvol);
-    fpcc::gather_patches_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(feats, c, table, ld, kvol, n_out, patches, kp);
+    if (c == 8 && kp % 16 == 0 && (size_t)fpcc::GP_ROWS * kp <= 48 * 1024 && (((uintptr_t)feats & 7) == 0) && (((uintptr_t)patches & 15) == 0)) {
+        fpcc::gather_patches8_kernel<<<fpcc::ceil_div(n_out, fpcc::GP_ROWS), 256, (size_t)fpcc::GP_ROWS * kp, (cudaStream_t)stream>>>(
+            feats, table, ld, kvol, n_out, patches, kp);
+    } else {
+        dim3 grid(fpcc::ceil_div(n_out, 256), kvol);
+        fpcc::gather_patches_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(feats, c, table, ld, kvol, n_out, patches, kp);
+    }
     FPCC_LAUNCH_CHECK();
     return FPCC_OK;
 }
