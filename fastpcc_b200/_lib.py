@@ -29,6 +29,7 @@ SIGNATURES = {
     'fpcc_kmap_lookup': (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i64, _vp]),
     'fpcc_kmap_compact_workspace': (_sz, [_i, _i]),
     'fpcc_kmap_compact': (_i, [_vp, _i, _i, _i64, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'fpcc_kmap_from_parent': (_i, [_vp, _i64, _i, _vp, _vp, _vp, _vp, _i, _vp, _i64, _vp]),
     'fpcc_kmap_row_masks': (_i, [_vp, _i, _i, _i64, _vp, _vp]),
     'fpcc_kmap_permute': (_i, [_vp, _i, _i, _i64, _vp, _vp, _i64, _vp]),
     'fpcc_scan_workspace': (_sz, [_i]),

@@ -106,6 +106,33 @@ __global__ void __launch_bounds__(256) kmap_lookup_kernel(const unsigned long lo
     else table[(int64_t)o * g.kvol + k] = v;
 }
 
+// 3x3x3 kernel map of a FINER pyramid level derived from the map of its parent level (octree neighbour finding), no
+// hashing: the neighbour of child (parent j, slot s) at offset d lives in the parent-level neighbour
+// D = floor((s + d) / 2) of j, at slot (s + d) mod 2, if that child exists; its row is the first-child row of that
+// parent plus the number of its occupied slots below.  Reads: one entry of the (8x smaller, cache-resident) parent
+// table, one occupancy byte, one child base -- instead of a random 12-byte probe of a hash table of all fine nodes.
+// Slots are 4x + 2y + z with children stored in slot order (Morton, x most significant); occupancy bit 7 - slot.
+__global__ void __launch_bounds__(256) kmap_from_parent_kernel(const int32_t *__restrict__ ctable, int64_t ldc,
+                                                               const uint8_t *__restrict__ cocc, const int32_t *__restrict__ cbase,
+                                                               const int32_t *__restrict__ parent, const uint8_t *__restrict__ slot,
+                                                               int n_fine, int32_t *__restrict__ table, int64_t ld) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;  // (dx+1) + 3 (dy+1) + 9 (dz+1): odd kernels enumerate x fastest (hashmap_cuda.cuh:239-258)
+    if (i >= n_fine) return;
+    const int j = parent[i];
+    const int s = slot[i];
+    const int tx = ((s >> 2) & 1) + (k % 3) - 1, ty = ((s >> 1) & 1) + (k / 3) % 3 - 1, tz = (s & 1) + (k / 9) - 1;
+    const int K = ((tx >> 1) + 1) + 3 * ((ty >> 1) + 1) + 9 * ((tz >> 1) + 1);   // arithmetic shift = floor
+    const int32_t jn = __ldg(&ctable[(int64_t)K * ldc + j]);
+    int32_t v = 0;
+    if (jn) {
+        const int sn = ((tx & 1) << 2) | ((ty & 1) << 1) | (tz & 1);
+        const uint32_t o = cocc[jn - 1];
+        if ((o >> (7 - sn)) & 1u) v = cbase[jn - 1] + __popc(o >> (8 - sn)) + 1;
+    }
+    table[(int64_t)k * ld + i] = v;
+}
+
 // Row grouping for the tensor-core conv: the kernel skips an offset for a whole 128-row tile only when NO row of
 // the tile has that neighbour, so rows with equal neighbour patterns should share tiles.  row_masks gives the
 // sort key (bit k = neighbour k present); permute_table rewrites the table in the sorted row order.
@@ -318,6 +345,18 @@ extern "C" int fpcc_kmap_lookup(const int64_t *keys, const int32_t *vals, int ca
     dim3 grid(ceil_div(n_out, 256), g.kvol);
     kmap_lookup_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const unsigned long long *)keys, vals, (uint32_t)capacity,
                                                                out_coords, n_out, layout, g, table, k_major, ld);
+    FPCC_LAUNCH_CHECK();
+    return FPCC_OK;
+}
+
+extern "C" int fpcc_kmap_from_parent(const int32_t *coarse_table, int64_t ld_coarse, int n_coarse, const uint8_t *coarse_occ,
+                                     const int32_t *child_base, const int32_t *parent, const uint8_t *slot, int n_fine,
+                                     int32_t *table, int64_t ld, void *stream) {
+    FPCC_REQUIRE(coarse_table && coarse_occ && child_base && parent && slot && table, "kmap_from_parent: NULL pointer");
+    FPCC_REQUIRE(n_coarse > 0 && ld_coarse >= n_coarse && n_fine >= 0 && ld >= n_fine, "kmap_from_parent: bad sizes");
+    if (n_fine == 0) return FPCC_OK;
+    kmap_from_parent_kernel<<<dim3(ceil_div(n_fine, 256), 27), 256, 0, (cudaStream_t)stream>>>(coarse_table, ld_coarse, coarse_occ, child_base,
+                                                                                                  parent, slot, n_fine, table, ld);
     FPCC_LAUNCH_CHECK();
     return FPCC_OK;
 }

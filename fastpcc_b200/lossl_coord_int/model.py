@@ -22,7 +22,7 @@ from .. import ops
 from ..int_sparse_conv.cuda_ops import (
     SharedFxpShift, SparseResBlockIn32W8Out32, SparseConvIn8W8Out8, SparseConvIn8W8Out32,  # noqa: F401
     SparseConvPReLUIn8W8Out8, SparseConvPReLUIn8W8Out32, PReLUIn32Out32, RequantFxpToScaledInt8,
-    LinearIn8W8Out8, LinearIn8W8Out32, LinearPReLUIn8W8Out8, LinearPReLUIn8W8Out32, LinearIn8W8)
+    LinearIn8W8Out8, LinearIn8W8Out32, LinearPReLUIn8W8Out8, LinearPReLUIn8W8Out32, LinearIn8W8, KernelMap)
 from ..sparse_tensor import SparseTensor
 
 _DENSE = (PReLUIn32Out32, RequantFxpToScaledInt8, LinearIn8W8)
@@ -126,6 +126,26 @@ def _with(f, ref: SparseTensor, C=None, stride=None):
     return x
 
 
+_K3 = ((3, 3, 3), (1, 1, 1))
+
+
+def seed_kernel_map(src_caches, dst_caches, coarse_stride, coarse_occ: torch.Tensor, fine: Level):
+    """Octree neighbour finding: if the 3x3x3 kernel map of the parent level (stride `coarse_stride`) is cached, derive
+    the map of its child level from it (ops.kmap_from_parent: same table as the hash lookup, no hash table of the fine
+    level at all) and store it where the conv layers look for it (`_caches.kmaps[(stride, kernel_size, conv_stride)]`).
+    The reference rebuilds a hash map per level (lib/int_sparse_conv/cuda_ops.py:113-131)."""
+    if fine.parent is None or fine.slot is None or coarse_occ is None:
+        return
+    entry = src_caches.kmaps.get((tuple(coarse_stride),) + _K3)
+    kmap = entry.get('in_out_maps') if entry is not None else None
+    if not isinstance(kmap, KernelMap) or kmap.table.shape[1] != coarse_occ.shape[0]:
+        return
+    tag = (tuple(s // 2 for s in coarse_stride),) + _K3
+    if tag not in dst_caches.kmaps:
+        table = ops.kmap_from_parent(kmap.table, coarse_occ.contiguous(), fine.parent.contiguous(), fine.slot.contiguous())
+        dst_caches.kmaps[tag] = {'in_out_maps': KernelMap(table)}
+
+
 class OneScalePredictor(nn.Module):
     """model.py:28-92"""
 
@@ -226,6 +246,7 @@ class OneScaleMultiStepPredictor(nn.Module):
             lv = levels[j]
             f = x.F  # [n_j, C]: features of the occupied children (selection already applied)
             st = tuple(s >> j for s in cur.stride)
+            seed_kernel_map(cur._caches, cur._caches, tuple(s >> (j - 1) for s in cur.stride), levels[j - 1].occ, lv)
             if j != S - 1:
                 # PReLU -> Requant -> LinearPReLU(C+8 -> C) on cat(f, bits) -> Conv -> Linear(C -> 8C)[child mask]
                 f = linear_with_bits(block[1], block[2], f, lv.occ, prelu=block[0])
@@ -423,6 +444,7 @@ class Model(nn.Module):
                 cur, pred = blk.trunk(cur)
                 if idx != 1 and blk.if_upsample:
                     f = blk.up(cur, lv.occ, levels[idx - 1])
+                    seed_kernel_map(cur._caches, cur._caches, cur.stride, lv.occ, levels[idx - 1])
                     cur = _with(f, cur, C=levels[idx - 1].C, stride=tuple(s // 2 for s in cur.stride))
             else:
                 S = blk.pred_steps
@@ -529,7 +551,9 @@ class Model(nn.Module):
                 child = decode_level(pred, lv)
                 if idx != 1 and blk.if_upsample:
                     f = blk.up(cur, lv.occ, child)
-                    cur = SparseTensor(f, child.C, tuple(s // 2 for s in cur.stride))  # fresh caches (model.py:88-91)
+                    nxt = SparseTensor(f, child.C, tuple(s // 2 for s in cur.stride))  # fresh caches (model.py:88-91)
+                    seed_kernel_map(cur._caches, nxt._caches, cur.stride, lv.occ, child)
+                    cur = nxt
                 else:
                     ms_levels = [lv]
                 lv = child

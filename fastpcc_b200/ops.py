@@ -277,6 +277,29 @@ def prelu_i32(inp, slope):
     return out
 
 
+_POPC8 = None
+
+
+def kmap_from_parent(coarse_table, coarse_occ, parent, slot):
+    """3x3x3 same-stride neighbour table of a level from its parent level's table (see fpcc_kmap_from_parent)."""
+    global _POPC8
+    _need(coarse_table, torch.int32, 'coarse table', 2)
+    _need(coarse_occ, torch.uint8, 'coarse occupancy', 1)
+    _need(parent, torch.int32, 'parent', 1)
+    _need(slot, torch.uint8, 'slot', 1)
+    if coarse_table.shape[0] != 27 or coarse_table.shape[1] != coarse_occ.shape[0] or parent.shape[0] != slot.shape[0]:
+        raise RuntimeError('kmap_from_parent: shape mismatch')
+    dev = coarse_table.device
+    if _POPC8 is None or _POPC8.device != dev:
+        _POPC8 = torch.tensor([bin(v).count('1') for v in range(256)], dtype=torch.int32, device=dev)
+    cnt = _POPC8[coarse_occ.long()]
+    base = (torch.cumsum(cnt, 0, dtype=torch.int32) - cnt).contiguous()
+    n_c, n_f = coarse_occ.shape[0], parent.shape[0]
+    table = torch.empty((27, n_f), dtype=torch.int32, device=dev)
+    _call('fpcc_kmap_from_parent', _p(coarse_table), n_c, n_c, _p(coarse_occ), _p(base), _p(parent), _p(slot), n_f, _p(table), n_f, _s())
+    return table
+
+
 def _tile_offsets_of(table):
     """profiling only: sum over 128-row tiles of the number of offsets with a neighbour in the tile (= MMA steps run)"""
     kv, n = table.shape

@@ -81,6 +81,15 @@ int fpcc_kmap_compact(const int32_t *table, int kvol, int n_out, int64_t ld, int
                       int32_t *in_map, int32_t *out_map, int32_t *offsets /* [kvol+1] */,
                       void *workspace, size_t workspace_bytes, void *stream);
 
+/* 3x3x3, stride-1 neighbour table of a pyramid level from the table of its PARENT level (octree neighbour finding)
+ * instead of hash probes: same values as fpcc_kmap_lookup(ks = 3, stride = 1) on the level's coordinates (the
+ * reference rebuilds a hash table per level, hashmap_cuda.cuh:171-275).  coarse_table: k-major [27, ld_coarse] of
+ * the parent level; coarse_occ[j] bit 7-s = child slot s = 4x+2y+z of parent j exists; child_base[j] = row of its
+ * first child (children stored in slot order); parent / slot: per fine node. */
+int fpcc_kmap_from_parent(const int32_t *coarse_table, int64_t ld_coarse, int n_coarse, const uint8_t *coarse_occ,
+                          const int32_t *child_base, const int32_t *parent, const uint8_t *slot, int n_fine,
+                          int32_t *table, int64_t ld, void *stream);
+
 /* Row grouping for fpcc_spconv_*: masks[o] = OR_k (table[k*ld+o] != 0) << min(k,31) (non-negative int32, the sort
  * key), and out[k*ld_out + j] = table[k*ld + perm[j]] for a permutation `perm` of the output rows (e.g. the
  * argsort of the masks).  No reference counterpart: the reference runs one GEMM per offset on pair lists

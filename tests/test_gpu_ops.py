@@ -89,6 +89,28 @@ def test_downsample_upsample_roundtrip(ops):
     assert (cpar.cpu().numpy() == par.cpu().numpy()).all() and (cslot.cpu().numpy() == slot.cpu().numpy()).all()
 
 
+def test_kernel_map_from_parent_level_equals_hash_lookup(ops):
+    """Octree neighbour finding (fpcc_kmap_from_parent) gives exactly the hash-built 3x3x3 table, level after level."""
+    from oracle.lossl_coord_int import morton_xmajor
+    C = _cloud(11, n=20000, bits=6, batch=3)
+    C = C[np.lexsort((morton_xmajor(C[:, 1:]), C[:, 0]))]
+    lv = [dev(C)]
+    meta = []
+    for _ in range(4):                                              # fine -> coarse
+        pc, occ, par, slot, cnt = ops.downsample(lv[-1])
+        n2 = int(cnt.item())
+        meta.append((occ[:n2].contiguous(), par.contiguous(), slot.contiguous()))
+        lv.append(pc[:n2].contiguous())
+    keys, vals = ops.hash_build(lv[-1])
+    table = ops.kmap_lookup(keys, vals, lv[-1], (3, 3, 3), (1, 1, 1))  # coarsest level: hash
+    for l in range(3, -1, -1):                                      # derive every finer level from its parent level
+        occ, par, slot = meta[l]
+        table = ops.kmap_from_parent(table, occ, par, slot)
+        keys, vals = ops.hash_build(lv[l])
+        want = ops.kmap_lookup(keys, vals, lv[l], (3, 3, 3), (1, 1, 1))
+        assert torch.equal(table, want), l
+
+
 def _epi_args(rng, ch, prelu, out8, zp=True):
     mul = rng.integers(1 << 18, 1 << 22, ch).astype(np.uint32)
     z = np.array([int(rng.integers(-(1 << 20), 1 << 20)) if zp else 0], np.int64)
