@@ -291,7 +291,9 @@ def kmap_from_parent(coarse_table, coarse_occ, parent, slot):
         raise RuntimeError('kmap_from_parent: shape mismatch')
     dev = coarse_table.device
     if _POPC8 is None or _POPC8.device != dev:
-        _POPC8 = torch.tensor([bin(v).count('1') for v in range(256)], dtype=torch.int32, device=dev)
+        lut = torch.tensor([bin(v).count('1') for v in range(256)], dtype=torch.int32, device=dev)
+        torch.cuda.current_stream(dev).synchronize()  # shared by every stream from here on (concurrent coding groups)
+        _POPC8 = lut
     cnt = _POPC8[coarse_occ.long()]
     base = (torch.cumsum(cnt, 0, dtype=torch.int32) - cnt).contiguous()
     n_c, n_f = coarse_occ.shape[0], parent.shape[0]
