@@ -23,8 +23,8 @@ WeightRange = 127
 # point clouds
 # ------------------------------------------------------------------------------------------------
 
-def lidar_frame(seed: int, resolution: int = 65536, n_boxes: int = 40, azimuths: int = 2048, beams: int = 64):
-    """One KITTI-shaped scan -> int32 [N,3] unique voxels (N ~ 115-125k at the defaults)."""
+def lidar_points(seed: int, n_boxes: int = 40, azimuths: int = 2048, beams: int = 64):
+    """One KITTI-shaped scan as the sensor delivers it: float32 [N,3] metres (the rows of a velodyne .bin)."""
     rng = np.random.default_rng(seed)
     elev = np.deg2rad(np.linspace(-24.8, 2.0, beams))
     azim = np.linspace(0, 2 * np.pi, azimuths, endpoint=False)
@@ -49,7 +49,13 @@ def lidar_frame(seed: int, resolution: int = 65536, n_boxes: int = 40, azimuths:
         hit = (tn <= tf) & (tn > 0)
         t = np.where(hit & (tn < t), tn, t)
     keep = np.isfinite(t) & (t < 120.0) & (rng.random(t.shape[0]) > 0.08)
-    xyz = (d[keep] * t[keep, None] * (1 + rng.normal(0, 0.002, (int(keep.sum()), 1)))).astype(np.float32)
+    return (d[keep] * t[keep, None] * (1 + rng.normal(0, 0.002, (int(keep.sum()), 1)))).astype(np.float32)
+
+
+def lidar_frame(seed: int, resolution: int = 65536, n_boxes: int = 40, azimuths: int = 2048, beams: int = 64):
+    """One KITTI-shaped scan -> int32 [N,3] unique voxels (N ~ 115-125k at the defaults): the dataset transform of
+    lib/datasets/KITTIOdometry/dataset.py:90-102 applied to `lidar_points`."""
+    xyz = lidar_points(seed, n_boxes, azimuths, beams)
     xyz -= xyz.min(0)
     xyz *= np.float32((resolution - 1) / 400)
     return np.unique(np.round(xyz).astype(np.int32), axis=0)

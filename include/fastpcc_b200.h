@@ -126,6 +126,31 @@ int fpcc_occ_to_bits(const uint8_t *occ, int n, int32_t *bits_i32 /* [n,8] */, v
 int fpcc_morton_encode(const int32_t *xyz, int64_t ld, int n, int msb_axis, int64_t *codes, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Front end: the step immediately before the codec.
+ *
+ * fpcc_voxelize_f32 replaces the host NumPy of lib/datasets/KITTIOdometry/dataset.py:96-102 followed by the
+ * Morton argsort of dataset.py:117-118 / lossl_coord_int/model.py:398:
+ *     org = xyz.min(0); xyz -= org; xyz *= scale; xyz = np.unique(xyz.round().astype(int32), axis=0); Morton sort
+ * points: float32 rows of `ld` floats (x,y,z first; KITTI .bin rows have ld = 4).  Arithmetic is float32 with one
+ * rounding per operation and round-half-to-even, exactly as NumPy evaluates the in-place ops.  Output: unique voxels
+ * as int32 (batch,x,y,z) rows in Morton order (msb_axis as fpcc_morton_encode), min_xyz_dev[3] = org (the
+ * inv_transform origin), *n_out_dev = voxel count, or -1 if a quantised coordinate does not fit `coord_bits`
+ * (1..21) bits.  out_coords sized for n rows.  workspace: fpcc_voxelize_workspace(n) bytes. */
+size_t fpcc_voxelize_workspace(int64_t n);
+int fpcc_voxelize_f32(const float *points, int64_t n, int ld, float scale, int coord_bits, int msb_axis, int batch,
+                      int32_t *out_coords, float *min_xyz_dev, int32_t *n_out_dev, void *workspace,
+                      size_t workspace_bytes, void *stream);
+
+/* One node of _kd_tree_partition (lib/data_utils.py:196-205): axis = argmax of the coordinate variance,
+ * split value = kthvalue(n/2) of that axis, left = rows <= value, right = the rest, both in their input order.
+ * coords / out_coords int32 [n,4] (batch,x,y,z), coordinates in [0, 2^coord_bits).  out_coords = left rows then
+ * right rows; info_dev[3] (device int32) = {axis, split value, number of left rows}.  The caller recurses
+ * (fastpcc_b200/frontend.py).  workspace: fpcc_kd_split_workspace(n, coord_bits) bytes. */
+size_t fpcc_kd_split_workspace(int64_t n, int coord_bits);
+int fpcc_kd_split(const int32_t *coords, int64_t n, int coord_bits, int32_t *out_coords, int32_t *info_dev,
+                  void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * int8 GEMMs.  A [M,K] int8 row-major, B [N,K] int8 row-major (= one kernel offset's weight
  * C_out x C_in), int32 accumulation (exact; wraps, never saturates at the sizes in use).
  * ---------------------------------------------------------------------------------------------- */

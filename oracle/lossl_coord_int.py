@@ -1,10 +1,12 @@
 """numpy restatement of the reference's integer-only lossless LiDAR geometry codec
 (models/convolutional/lossl_coord_int/model.py) on top of oracle/int_ops.py and oracle/rans.py.
 
-TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Parity status: see oracle/int_ops.py -- pinned to
-the reference source line by line (no reference outputs exist: no trained weights ship with the repo
-and its CUDA extension cannot be built offline); the range-coder half is pinned to the compiled
-reference.  Parameters come in as a plain {state_dict_key: ndarray} mapping with the reference's
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Parity status: PINNED at the codec level -- the bitstreams and
+decoded point order of this file equal those of the reference's own Python (unmodified model.py + cuda_ops.py +
+compiled range coder, run on the CPU by tests/golden/make_int_codec_golden.py; fixture
+tests/golden/int_codec_golden.json, test tests/test_oracle_int_codec_golden.py).  The 20 primitive entry points of
+the CUDA extension underneath (oracle/int_ops.py) are pinned to their sources only: the extension cannot be built
+offline.  Parameters come in as a plain {state_dict_key: ndarray} mapping with the reference's
 own key names (lib/int_sparse_conv/cuda_ops.py:194-206, 476-481, 516-528).
 """
 import numpy as np
