@@ -43,6 +43,12 @@ SIGNATURES = {
     'fpcc_voxelize_f32': (_i, [_vp, _i64, _i, C.c_float, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     'fpcc_kd_split_workspace': (_sz, [_i64, _i]),
     'fpcc_kd_split': (_i, [_vp, _i64, _i, _vp, _vp, _vp, _sz, _vp]),
+    'fpcc_frame_header_write': (_i, [_vp, _i, _vp]),
+    'fpcc_frame_header_read': (_i, [_vp, _i64, _vp, _vp]),
+    'fpcc_partitions_pack': (_i64, [_vp, _vp, _i, _vp, _i64]),
+    'fpcc_partitions_index': (_i, [_vp, _i64, _i, _vp, _vp]),
+    'fpcc_bytes_list_concat': (_i64, [_vp, _vp, _i, _vp, _i64]),
+    'fpcc_bytes_list_split': (_i64, [_vp, _i64, _i, _vp, _vp]),
     'fpcc_gemm_i8': (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp]),
     'fpcc_gather_gemm_scatter_i8': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'fpcc_requant': (_i, [_vp, _i64, _i, _EP, _vp, _vp]),

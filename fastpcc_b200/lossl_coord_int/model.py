@@ -18,7 +18,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .. import ops
+from .. import bitstream, ops
 from ..int_sparse_conv.cuda_ops import (
     SharedFxpShift, SparseResBlockIn32W8Out32, SparseConvIn8W8Out8, SparseConvIn8W8Out32,  # noqa: F401
     SparseConvPReLUIn8W8Out8, SparseConvPReLUIn8W8Out32, PReLUIn32Out32, RequantFxpToScaledInt8,
@@ -499,7 +499,7 @@ class Model(nn.Module):
 
     def compress_partitions(self, batched_coord: List[torch.Tensor]) -> bytes:
         out = self.compress_batch(list(batched_coord[1:]))  # model.py:455-463 (partitions are independent streams)
-        return b''.join(len(s).to_bytes(3, 'little') + s for s in out)
+        return bitstream.pack_partitions(out)
 
     # ---- decompress -------------------------------------------------------------------------
     @torch.no_grad()
@@ -573,9 +573,5 @@ class Model(nn.Module):
         return self.decompress_batch([compressed_bytes])[0]
 
     def decompress_partitions(self, concat_bytes: bytes) -> torch.Tensor:
-        parts, pos = [], 0
-        while pos != len(concat_bytes):  # model.py:510-521
-            n = int.from_bytes(concat_bytes[pos: pos + 3], 'little')
-            parts.append(concat_bytes[pos + 3: pos + 3 + n])
-            pos += 3 + n
+        parts = bitstream.split_partitions(concat_bytes)  # model.py:510-521; raises on a truncated container
         return torch.cat(self.decompress_batch(parts), 0)

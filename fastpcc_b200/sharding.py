@@ -62,13 +62,10 @@ def compress_sharded(compress_batch: Callable[[list], List[bytes]], units: list,
 
 def pack_partitions(streams: List[bytes]) -> bytes:
     """3-byte little-endian length prefix per stream (model.py:462)."""
-    return b''.join(len(s).to_bytes(3, 'little') + s for s in streams)
+    from . import bitstream
+    return bitstream.pack_partitions(streams)
 
 
 def unpack_partitions(blob: bytes) -> List[bytes]:
-    out, pos = [], 0
-    while pos != len(blob):
-        n = int.from_bytes(blob[pos: pos + 3], 'little')
-        out.append(blob[pos + 3: pos + 3 + n])
-        pos += 3 + n
-    return out
+    from . import bitstream
+    return bitstream.split_partitions(blob)

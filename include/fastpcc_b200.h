@@ -151,6 +151,26 @@ int fpcc_kd_split(const int32_t *coords, int64_t n, int coord_bits, int32_t *out
                   void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Bitstream containers, host memory only: the byte layouts needed to exchange streams with the
+ * reference decoder.  The int64 functions return a byte count, or -1 with fpcc_last_error() set.
+ *
+ * frame header: lossl_coord_int/model.py:447-452 / 466-473 -- three uint16 LE coord offsets, uint16 LE bottom
+ * point count; the rANS payload follows. */
+int fpcc_frame_header_write(const int32_t coord_offset[3], int bottom_points, uint8_t out[8]);
+int fpcc_frame_header_read(const uint8_t *data, int64_t len, int32_t coord_offset[3], int *bottom_points);
+/* partition container: compress_partitions / decompress_partitions (model.py:455-463, 510-521): a 3-byte LE
+ * length before every partition stream.  pack: out == NULL returns the size.  index: returns the partition
+ * count (offsets / lens may be NULL to count only), -1 on a truncated container. */
+int64_t fpcc_partitions_pack(const uint8_t *const *items, const int64_t *lens, int n, uint8_t *out, int64_t out_cap);
+int fpcc_partitions_index(const uint8_t *data, int64_t len, int max_n, int64_t *offsets, int64_t *lens);
+/* BytesListUtils.concat_bytes_list / split_bytes_list
+ * (lib/entropy_models/hyperprior/noisy_deep_factorized/utils.py:8-45, 47-76): bit-packed head with the byte width
+ * of every length, the LE lengths, the payloads.  concat: n >= 2 as the reference asserts, out == NULL returns
+ * the size.  split: the caller knows n (as in the reference); returns the bytes consumed. */
+int64_t fpcc_bytes_list_concat(const uint8_t *const *items, const int64_t *lens, int n, uint8_t *out, int64_t out_cap);
+int64_t fpcc_bytes_list_split(const uint8_t *data, int64_t len, int n, int64_t *offsets, int64_t *lens);
+
+/* ------------------------------------------------------------------------------------------------
  * int8 GEMMs.  A [M,K] int8 row-major, B [N,K] int8 row-major (= one kernel offset's weight
  * C_out x C_in), int32 accumulation (exact; wraps, never saturates at the sizes in use).
  * ---------------------------------------------------------------------------------------------- */
