@@ -171,6 +171,15 @@ int64_t fpcc_bytes_list_concat(const uint8_t *const *items, const int64_t *lens,
 int64_t fpcc_bytes_list_split(const uint8_t *data, int64_t len, int n, int64_t *offsets, int64_t *lens);
 
 /* ------------------------------------------------------------------------------------------------
+ * Distortion metric: exact nearest neighbour, the kernel under D1 / D2 PSNR.  Replaces the MPEG
+ * `pc_error` subprocess of lib/metrics/pc_error_wrapper.py:40-106 (lib/evaluators.py:49-124) for geometry.
+ * query / ref: int32 rows of q_ld / r_ld ints, xyz starting at column q_col / r_col ((batch,x,y,z) rows: ld 4,
+ * col 1); |coordinates| < 2^coord_bits.  d2_out[nq] = exact squared distance to the nearest reference point,
+ * idx_out[nq] (optional) = its row, the lowest row among equidistant ones. */
+int fpcc_nn_search(const int32_t *query, int nq, int q_ld, int q_col, const int32_t *ref, int nr, int r_ld, int r_col,
+                   int coord_bits, int64_t *d2_out, int32_t *idx_out, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * int8 GEMMs.  A [M,K] int8 row-major, B [N,K] int8 row-major (= one kernel offset's weight
  * C_out x C_in), int32 accumulation (exact; wraps, never saturates at the sizes in use).
  * ---------------------------------------------------------------------------------------------- */
