@@ -253,6 +253,14 @@ def main():
             'share_of_step': conv['ms'] / ms_dev if ms_dev else 0.0}
     roof['frac'] = roof['achieved'] / roof['peak'] if roof['peak'] else 0.0
     launches = sum(v['launches'] for v in stats.values())
+    # HBM-class kernels (kernel map, coordinate generation, requant, CDF head): algorithmic bytes (stated per
+    # wrapper in fastpcc_b200/ops.py) / CUDA-event time of the same instrumented pass, against the measured copy bandwidth
+    hbm_peak = float(peaks['hbm_gbs'])
+    hbm = {}
+    for k, v in stats.items():
+        if v.get('bytes') and v['ms'] > 0 and k not in ('spconv_tc', 'linear_tc', 'linear_sel_tc'):
+            gbs = v['bytes'] / (v['ms'] * 1e-3) / 1e9
+            hbm[k] = {'gb_per_step': round(v['bytes'] / 1e9, 3), 'achieved_gbs': round(gbs, 1), 'frac': round(gbs / hbm_peak, 3)}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -279,6 +287,7 @@ def main():
                     'ms_per_step': ms_e2e},
             'gpu_launches': launches * args.steps,
             'roofline': roof, 'cpu_baseline': cpu,
+            'hbm_kernels': {'peak_gbs': hbm_peak, 'peak_source': f'MEASURED_PEAKS.json hbm_gbs ({peak_kind})', 'kernels': hbm},
             'kernels': {k: {'ms': round(v['ms'], 3), 'launches': v['launches']} for k, v in stats.items()},
         }))
     if world > 1:

@@ -112,25 +112,54 @@ __global__ void __launch_bounds__(256) kmap_lookup_kernel(const unsigned long lo
 // parent plus the number of its occupied slots below.  Reads: one entry of the (8x smaller, cache-resident) parent
 // table, one occupancy byte, one child base -- instead of a random 12-byte probe of a hash table of all fine nodes.
 // Slots are 4x + 2y + z with children stored in slot order (Morton, x most significant); occupancy bit 7 - slot.
+// One thread per fine node for all 27 offsets: per axis the target s + d (d = -1,0,1) falls into one of only two
+// parent-level offsets (D0 = s - 1, D0 + 1), so the node needs 8 parent-table entries (+ occupancy byte and child base
+// of each), not 27; parent / slot are read once; the k-major stores of consecutive threads stay coalesced.
 __global__ void __launch_bounds__(256) kmap_from_parent_kernel(const int32_t *__restrict__ ctable, int64_t ldc,
                                                                const uint8_t *__restrict__ cocc, const int32_t *__restrict__ cbase,
                                                                const int32_t *__restrict__ parent, const uint8_t *__restrict__ slot,
                                                                int n_fine, int32_t *__restrict__ table, int64_t ld) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int k = blockIdx.y;  // (dx+1) + 3 (dy+1) + 9 (dz+1): odd kernels enumerate x fastest (hashmap_cuda.cuh:239-258)
     if (i >= n_fine) return;
     const int j = parent[i];
     const int s = slot[i];
-    const int tx = ((s >> 2) & 1) + (k % 3) - 1, ty = ((s >> 1) & 1) + (k / 3) % 3 - 1, tz = (s & 1) + (k / 9) - 1;
-    const int K = ((tx >> 1) + 1) + 3 * ((ty >> 1) + 1) + 9 * ((tz >> 1) + 1);   // arithmetic shift = floor
-    const int32_t jn = __ldg(&ctable[(int64_t)K * ldc + j]);
-    int32_t v = 0;
-    if (jn) {
-        const int sn = ((tx & 1) << 2) | ((ty & 1) << 1) | (tz & 1);
-        const uint32_t o = cocc[jn - 1];
-        if ((o >> (7 - sn)) & 1u) v = cbase[jn - 1] + __popc(o >> (8 - sn)) + 1;
+    const int sx = (s >> 2) & 1, sy = (s >> 1) & 1, sz = s & 1;
+    uint32_t pocc[8];
+    int32_t pbase[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {  // q = a + 2b + 4c: parent offset (sx - 1 + a, sy - 1 + b, sz - 1 + c)
+        const int K = (sx + (q & 1)) + 3 * (sy + ((q >> 1) & 1)) + 9 * (sz + (q >> 2));
+        const int32_t jn = __ldg(&ctable[(int64_t)K * ldc + j]);
+        pocc[q] = jn ? (uint32_t)__ldg(&cocc[jn - 1]) : 0u;
+        pbase[q] = jn ? __ldg(&cbase[jn - 1]) : 0;
     }
-    table[(int64_t)k * ld + i] = v;
+#pragma unroll
+    for (int dz = -1; dz <= 1; ++dz) {
+        const int tz = sz + dz;
+        const bool cz = ((tz >> 1) - (sz - 1)) != 0;  // arithmetic shift = floor
+        uint32_t o4[4];
+        int32_t b4[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { o4[q] = cz ? pocc[4 + q] : pocc[q]; b4[q] = cz ? pbase[4 + q] : pbase[q]; }
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int ty = sy + dy;
+            const bool cy = ((ty >> 1) - (sy - 1)) != 0;
+            const uint32_t o2a = cy ? o4[2] : o4[0], o2b = cy ? o4[3] : o4[1];
+            const int32_t b2a = cy ? b4[2] : b4[0], b2b = cy ? b4[3] : b4[1];
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int tx = sx + dx;
+                const bool cx = ((tx >> 1) - (sx - 1)) != 0;
+                const uint32_t o = cx ? o2b : o2a;
+                const int32_t b = cx ? b2b : b2a;
+                const int sn = ((tx & 1) << 2) | ((ty & 1) << 1) | (tz & 1);
+                const int32_t v = ((o >> (7 - sn)) & 1u) ? b + __popc(o >> (8 - sn)) + 1 : 0;
+                const int k = (dx + 1) + 3 * (dy + 1) + 9 * (dz + 1);  // odd kernels enumerate x fastest (hashmap_cuda.cuh:239-258)
+                table[(int64_t)k * ld + i] = v;
+            }
+        }
+    }
 }
 
 // Row grouping for the tensor-core conv: the kernel skips an offset for a whole 128-row tile only when NO row of
@@ -355,7 +384,7 @@ extern "C" int fpcc_kmap_from_parent(const int32_t *coarse_table, int64_t ld_coa
     FPCC_REQUIRE(coarse_table && coarse_occ && child_base && parent && slot && table, "kmap_from_parent: NULL pointer");
     FPCC_REQUIRE(n_coarse > 0 && ld_coarse >= n_coarse && n_fine >= 0 && ld >= n_fine, "kmap_from_parent: bad sizes");
     if (n_fine == 0) return FPCC_OK;
-    kmap_from_parent_kernel<<<dim3(ceil_div(n_fine, 256), 27), 256, 0, (cudaStream_t)stream>>>(coarse_table, ld_coarse, coarse_occ, child_base,
+    kmap_from_parent_kernel<<<ceil_div(n_fine, 256), 256, 0, (cudaStream_t)stream>>>(coarse_table, ld_coarse, coarse_occ, child_base,
                                                                                                   parent, slot, n_fine, table, ld);
     FPCC_LAUNCH_CHECK();
     return FPCC_OK;

@@ -394,17 +394,27 @@ class Model(nn.Module):
         dev, B, L = self.device, len(frames), self._num_levels()
         tr = _Trace()
         tr.mark('start')
-        offs, parts = [], []
-        for b, xyz in enumerate(frames):
+        # model.py:396-398 for all frames at once: per-frame minimum, shift, Morton code (x most significant), then
+        # ONE pair of stable sorts (Morton, then frame) instead of a sort per frame -- a segmented sort whatever the
+        # coordinate width.  Equal points of a frame cannot occur (the input is a voxel set), so the order is unique.
+        for xyz in frames:
             assert xyz.dtype == torch.int32 and xyz.dim() == 2 and xyz.shape[1] == 4
-            xyz = xyz.to(dev)
-            off = xyz[:, 1:].amin(0)  # model.py:396-398
-            xyz = xyz - torch.nn.functional.pad(off, (1, 0))
-            xyz[:, 0] = b
-            xyz = xyz[torch.argsort(ops.morton_encode(xyz.contiguous(), col0=1, msb_axis=0))]
-            offs.append(off)
-            parts.append(xyz)
-        xyz = torch.cat(parts).contiguous()
+        sizes = [int(f.shape[0]) for f in frames]
+        xyz = torch.cat([f.to(dev) for f in frames]) if B > 1 else frames[0].to(dev).clone()
+        frame_id = torch.repeat_interleave(torch.arange(B, dtype=torch.int32, device=dev),
+                                           torch.tensor(sizes, device=dev), output_size=sum(sizes))
+        big = torch.iinfo(torch.int32).max
+        off_all = torch.full((B, 3), big, dtype=torch.int32, device=dev)
+        off_all.scatter_reduce_(0, frame_id.long()[:, None].expand(-1, 3), xyz[:, 1:], 'amin')
+        xyz[:, 1:] -= off_all[frame_id.long()]
+        xyz[:, 0] = frame_id
+        if B == 1:
+            order = torch.argsort(ops.morton_encode(xyz, col0=1, msb_axis=0))
+        else:
+            o1 = torch.argsort(ops.morton_encode(xyz, col0=1, msb_axis=0))
+            o2 = torch.sort(frame_id[o1].to(torch.int16) if B < 32768 else frame_id[o1], stable=True).indices
+            order = o1[o2]
+        xyz = xyz[order].contiguous()
         tr.mark('sort')
         levels = self.build_pyramid(xyz)
         tr.mark('pyramid')
@@ -477,7 +487,7 @@ class Model(nn.Module):
         out, out_len = ops.rans_encode(ranges, rng_off, cap)
         lens = out_len.tolist()
         tr.mark('rans')
-        heads = torch.cat([torch.stack(offs).long(), (n_sym // 3)[:, None]], 1).tolist()
+        heads = torch.cat([off_all.long(), (n_sym // 3)[:, None]], 1).tolist()
         assert min(lens) > 0, 'rANS output buffer overflow'
         # only the written tails of the per-stream slots travel to the host (the slots are sized for the worst case)
         packed = torch.cat([out[b, cap - lens[b]:] for b in range(B)])

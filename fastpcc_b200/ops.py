@@ -152,7 +152,8 @@ def hash_build(coords, layout=0, keys=None, vals=None):
     if keys is None:
         keys = torch.zeros(2 * n + 2, dtype=torch.int64, device=coords.device)
         vals = torch.zeros(2 * n + 2, dtype=torch.int32, device=coords.device)
-    _call('fpcc_hash_insert_coords', _p(keys), _p(vals), keys.numel(), _p(coords), n, layout, _s())
+    _call('fpcc_hash_insert_coords', _p(keys), _p(vals), keys.numel(), _p(coords), n, layout, _s(),
+          work={'bytes': 28.0 * n})  # 16 B coords + 12 B table entry per point
     return keys, vals
 
 
@@ -169,7 +170,8 @@ def kmap_lookup(keys, vals, out_coords, kernel_size, stride, layout=0, k_major=T
         ld = 0
     _call('fpcc_kmap_lookup', _p(keys), _p(vals), keys.numel(), _p(out_coords), n, layout,
               kernel_size[0], kernel_size[1], kernel_size[2], stride[0], stride[1], stride[2], convention,
-              _p(table), 1 if k_major else 0, ld, _s())
+              _p(table), 1 if k_major else 0, ld, _s(),
+          work={'bytes': 16.0 * n + 12.0 * kv * n})  # coords + one 8-byte key probe and a 4-byte entry per (offset, row)
     return table
 
 
@@ -196,7 +198,8 @@ def downsample(coords, want_parent=True):
     slot = torch.empty(n, dtype=torch.uint8, device=dev) if want_parent else None
     cnt = torch.empty(1, dtype=torch.int32, device=dev)
     ws = workspace(_lib.load().fpcc_scan_workspace(n), dev)
-    _call('fpcc_downsample', _p(coords), n, _p(out_c), _p(occ), _p(par), _p(slot), _p(cnt), _p(ws), ws.numel(), _s())
+    _call('fpcc_downsample', _p(coords), n, _p(out_c), _p(occ), _p(par), _p(slot), _p(cnt), _p(ws), ws.numel(), _s(),
+          work={'bytes': 16.0 * n})  # lower bound: input coords only (outputs depend on the parent count)
     return out_c, occ, par, slot, cnt
 
 
@@ -241,7 +244,8 @@ def gather_patches(feats, table, kp):
     c = feats.shape[1]
     alloc = torch.empty if kp == kv * c else torch.zeros
     out = alloc((n_out, kp), dtype=torch.int8, device=feats.device)
-    _call('fpcc_gather_patches', _p(feats), c, _p(table), n_out, kv, n_out, _p(out), kp, _s())
+    _call('fpcc_gather_patches', _p(feats), c, _p(table), n_out, kv, n_out, _p(out), kp, _s(),
+          work={'bytes': float(n_out) * kv * (4 + c)})  # table read + patch bytes written
     return out
 
 
@@ -298,7 +302,8 @@ def kmap_from_parent(coarse_table, coarse_occ, parent, slot):
     base = (torch.cumsum(cnt, 0, dtype=torch.int32) - cnt).contiguous()
     n_c, n_f = coarse_occ.shape[0], parent.shape[0]
     table = torch.empty((27, n_f), dtype=torch.int32, device=dev)
-    _call('fpcc_kmap_from_parent', _p(coarse_table), n_c, n_c, _p(coarse_occ), _p(base), _p(parent), _p(slot), n_f, _p(table), n_f, _s())
+    _call('fpcc_kmap_from_parent', _p(coarse_table), n_c, n_c, _p(coarse_occ), _p(base), _p(parent), _p(slot), n_f, _p(table), n_f, _s(),
+          work={'bytes': 4.0 * 27 * n_f + 5.0 * n_f + 4.0 * 27 * n_c})  # table written + parent/slot + parent table read once
     return table
 
 
@@ -321,10 +326,10 @@ def group_rows(table):
     _need(table, torch.int32, 'table', 2)
     kv, n_out = table.shape
     masks = torch.empty(n_out, dtype=torch.int32, device=table.device)
-    _call('fpcc_kmap_row_masks', _p(table), kv, n_out, n_out, _p(masks), _s())
+    _call('fpcc_kmap_row_masks', _p(table), kv, n_out, n_out, _p(masks), _s(), work={'bytes': 4.0 * kv * n_out + 4.0 * n_out})
     perm = torch.sort(masks, stable=True)[1].to(torch.int32)  # stable: neighbouring rows stay neighbours within a pattern
     table_p = torch.empty_like(table)
-    _call('fpcc_kmap_permute', _p(table), kv, n_out, n_out, _p(perm), _p(table_p), n_out, _s())
+    _call('fpcc_kmap_permute', _p(table), kv, n_out, n_out, _p(perm), _p(table_p), n_out, _s(), work={'bytes': 8.0 * kv * n_out + 4.0 * n_out})
     return table_p, perm
 
 
@@ -441,7 +446,7 @@ def quantize_cdf(logits, ld=CDF_LD):
     n, s = logits.shape
     ld = max(ld, s)
     out = torch.empty((n, ld), dtype=torch.uint16, device=logits.device)
-    _call('fpcc_quantize_cdf', _p(logits), pitch, n, s, _p(out), ld, _s())
+    _call('fpcc_quantize_cdf', _p(logits), pitch, n, s, _p(out), ld, _s(), work={'bytes': 4.0 * s * n + 2.0 * ld * n})
     return out
 
 
@@ -450,7 +455,7 @@ def cdf_symbol_ranges(logits, symbols, out=None):
     _need(symbols, torch.int32, 'symbols', 1)
     n, s = logits.shape
     out = torch.empty(n, dtype=torch.int32, device=logits.device) if out is None else out
-    _call('fpcc_cdf_symbol_ranges', _p(logits), pitch, n, s, _p(symbols), _p(out), _s())
+    _call('fpcc_cdf_symbol_ranges', _p(logits), pitch, n, s, _p(symbols), _p(out), _s(), work={'bytes': 4.0 * s * n + 6.0 * n})
     return out
 
 
