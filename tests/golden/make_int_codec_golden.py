@@ -228,6 +228,34 @@ def main():
         json.dump(run_cases(ref_ops), f, indent=1)
     print('ptq cases written')
 
+    # the convert pipeline (lossl_coord/model.py:685-888): reference functions on the reference's float trees, with
+    # a parameter-only stand-in for torchsparse.nn.Conv3d (kernel [K,Cin,Cout], bias, sizes -- all the pass reads)
+    import math
+    import torchsparse.nn as tsn
+
+    class Conv3dParams(nn.Module):
+        def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, dilation=1, bias=False):
+            super().__init__()
+            t = lambda v: tuple(v) if isinstance(v, (tuple, list)) else (v,) * 3  # noqa: E731
+            self.in_channels, self.out_channels = in_channels, out_channels
+            self.kernel_size, self.stride = t(kernel_size), t(stride)
+            self.kernel = nn.Parameter(torch.zeros(math.prod(self.kernel_size), in_channels, out_channels))
+            self.bias = nn.Parameter(torch.zeros(out_channels)) if bias else None
+    tsn.Conv3d = Conv3dParams
+    sys.modules['torchsparse.nn.functional'] = types.ModuleType('torchsparse.nn.functional')
+    tsn.functional = sys.modules['torchsparse.nn.functional']
+    fm = importlib.import_module('models.convolutional.lossl_coord.model')
+    fm.spnn.Conv3d = Conv3dParams
+    from tests.golden.ptq_cases import run_pipeline
+    ns = types.SimpleNamespace(
+        OneScalePredictor=fm.OneScalePredictor, OneScaleMultiStepPredictor=fm.OneScaleMultiStepPredictor,
+        insert_obs_into_resblocks=fm.insert_obs_into_resblocks, insert_obs_into_seqs=fm.insert_obs_into_seqs,
+        replace_resblocks_with_int_impl=fm.replace_resblocks_with_int_impl, replace_seqs_with_int_impl=fm.replace_seqs_with_int_impl,
+        SparseTensorHistogramObserver=ref_ops.SparseTensorHistogramObserver, SparseTensor=sys.modules['torchsparse'].SparseTensor)
+    with open(osp.join(HERE, 'ptq_pipeline_golden.json'), 'w') as f:
+        json.dump(run_pipeline(ns), f, indent=1)
+    print('ptq pipeline written')
+
 
 if __name__ == '__main__':
     main()

@@ -87,3 +87,51 @@ def run_cases(mod):
     layer.import_parameters(_prelu(0.2))
     record('prelu32', layer)
     return out
+
+
+# ---- the convert pipeline (lossl_coord/model.py:685-888) on the float predictor trees ---------------------------
+
+def seed_parameters(model):
+    """Deterministic values by parameter name (identical for the reference tree and the twin)."""
+    import zlib
+    for name, p in model.named_parameters():
+        g = torch.Generator().manual_seed(zlib.crc32(name.encode()))
+        with torch.no_grad():
+            if p.numel() == 1:  # PReLU slope
+                p.fill_(0.05 + 0.25 * torch.rand(1, generator=g).item())
+            else:
+                p.copy_(torch.randn(p.shape, generator=g) * (0.1 if p.dim() == 1 else 0.05))
+
+
+def run_pipeline(ns):
+    """`ns`: namespace with OneScalePredictor, OneScaleMultiStepPredictor, the two insert_* and two replace_*
+    functions, SparseTensorHistogramObserver and SparseTensor.  Builds float trees, inserts observers, feeds every
+    observer seeded activations, converts, and returns the hashes of the integer state dict."""
+    import zlib
+    model = nn.ModuleDict({
+        'recurrent': ns.OneScalePredictor(16, True, True),
+        'plain': ns.OneScalePredictor(24, False, False),
+        'two_step': ns.OneScaleMultiStepPredictor(16, 2, False),
+        'three_step': ns.OneScaleMultiStepPredictor(16, 3, False),
+        'four_step_wide': ns.OneScaleMultiStepPredictor(16, 4, True),
+        'three_step_256': ns.OneScaleMultiStepPredictor(256, 3, False),
+    })
+    seed_parameters(model)
+    ns.insert_obs_into_resblocks(model)
+    ns.insert_obs_into_seqs(model)
+    for name, m in model.named_modules():
+        if isinstance(m, ns.SparseTensorHistogramObserver):
+            g = torch.Generator().manual_seed(zlib.crc32(name.encode()))
+            spread = 0.2 + 3.0 * torch.rand(1, generator=g).item()
+            shift = 0.4 if m.qscheme == torch.per_tensor_affine else 0.0
+            for _ in range(2):
+                m(ns.SparseTensor(torch.randn(600, 8, generator=g) * spread + shift, torch.zeros((600, 4), dtype=torch.int32)))
+    ns.replace_resblocks_with_int_impl(model)
+    ns.replace_seqs_with_int_impl(model)
+    out = {}
+    for k, v in model.state_dict().items():
+        if k.split('.')[-1].startswith(('scale_', 'zero_point_')):
+            continue
+        a = v.view(torch.int32).numpy() if v.dtype == torch.uint32 else v.numpy()
+        out[k] = hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:24] + ':' + str(a.dtype) + str(list(a.shape))
+    return out
