@@ -31,7 +31,8 @@ ROOT = osp.dirname(osp.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CFG = dict(channels=256, max_stride_wo_recurrent=2048, max_stride=8192, fea_stride=16)
-WORKLOAD = 'lossl_coord_int LiDAR lossless (KITTI-shaped synthetic scans ~120k pts/frame, 16-bit grid, C=256)'
+WORKLOAD = ('lossl_coord LiDAR lossless (BASELINE configs[1]: KITTI-shaped synthetic scans ~120k pts/frame, 16-bit grid, '
+            'C=256 default topology) coded by its integer-only inference path lossl_coord_int (configs[2], bit-exact bitstreams)')
 
 
 def load_peaks():

@@ -253,12 +253,23 @@ template <int OUT, bool SLOPE, bool ROWBIAS, bool ZP0>
 __device__ __forceinline__ bool epi_chunk_fast(const uint32_t (&acc)[EC], const FastCtx &fx, const int32_t *row_bias,
                                                int nvalid, int32_t (&o)[EC]) {
     bool bad = false;
+    // occupancy-indexed bias row: every lane reads its own table row, so a 4-byte load per element costs 32 L1
+    // wavefronts each; one 16-byte load per four elements when the chunk is whole and aligned
+    const bool rb_vec = ROWBIAS && nvalid == EC && ((uintptr_t)row_bias & 15) == 0;
+    int4 rb4 = make_int4(0, 0, 0, 0);
 #pragma unroll
     for (int q = 0; q < EC; ++q) {
         const int4 ch = lds128(fx.chan + q * 16);
         int32_t v = (int32_t)acc[q];
         if (ROWBIAS) {
-            v = (int32_t)((uint32_t)v + (uint32_t)__ldg(&row_bias[q < nvalid ? q : 0]));
+            int32_t rbv;
+            if (rb_vec) {
+                if ((q & 3) == 0) rb4 = __ldg(reinterpret_cast<const int4 *>(row_bias) + (q >> 2));
+                rbv = (q & 3) == 0 ? rb4.x : ((q & 3) == 1 ? rb4.y : ((q & 3) == 2 ? rb4.z : rb4.w));
+            } else {
+                rbv = __ldg(&row_bias[q < nvalid ? q : 0]);
+            }
+            v = (int32_t)((uint32_t)v + (uint32_t)rbv);
             bad |= (uint32_t)v + (1u << 30) > (1u << 31);  // keeps v + bias inside int32
         }
         v += ch.x;

@@ -1,4 +1,6 @@
 // C-ABI entry points for the GEMM family and the element-wise requant epilogues.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace fpcc {
@@ -130,6 +132,74 @@ __global__ void __launch_bounds__(256) prelu_kernel(const int32_t *__restrict__ 
         out[i] = clamp_i32(prelu_q25((int64_t)in[i], sl));
 }
 
+__global__ void __launch_bounds__(256) requant_scalar_i8_coalesced_kernel(const int4 *__restrict__ in, int64_t total4, EpiParams ep,
+                                                                          uint32_t *__restrict__ out) {
+    const int64_t zp = ep.zp[0];
+    const uint32_t mul = ep.mul[0];
+    const int shift = ep.shift;
+    const bool has_slope = ep.slope != nullptr;  // optional Q6.25 PReLU in front (PReLUIn32Out32 -> Requant chains)
+    const int32_t slope = has_slope ? ep.slope[0] : 0;
+    const int64_t half = shift > 0 ? (int64_t)1 << (shift - 1) : 0;
+    const int64_t c0 = zp + half;
+    const int64_t azp = zp < 0 ? -zp : zp;
+    bool fast = shift <= 31 && mul < (1u << 31) && (uint32_t)c0 != 0u && azp < ((int64_t)1 << 60) &&
+                (!has_slope || (slope >= 0 && slope <= (1 << 25)));
+    int32_t B = 0, thr = 0;
+    if (fast) {
+        const int64_t num = ((int64_t)129 << shift) + azp;
+        int64_t b = mul ? (num + (int64_t)mul - 1) / (int64_t)mul : 0;
+        fast = b <= 2147483646ll;  // inputs span all of int32 here: the clamp must not bind below saturation
+        fast = fast && ((num + (int64_t)mul + azp + ((int64_t)1 << 31)) >> shift) < 2147483647ll;
+        int64_t t;
+        if (mul == 0) t = zp < 0 ? 2147483647ll : -2147483648ll;
+        else { const int64_t nz = -zp, m = (int64_t)mul; t = nz >= 0 ? (nz + m - 1) / m : -((-nz) / m); }
+        t = t > 2147483647ll ? 2147483647ll : (t < -2147483648ll ? -2147483648ll : t);
+        B = (int32_t)b; thr = (int32_t)t;
+    }
+    const uint32_t c_lo = (uint32_t)c0, c_hi = (uint32_t)((uint64_t)c0 >> 32);
+    // every warp instruction touches 512 contiguous input bytes / 128 contiguous output bytes: four int4 loads per
+    // thread at a 256-vector stride (all in flight before the first use), four packed 4-byte stores
+    const int64_t tiles = (total4 + 1023) / 1024;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int64_t base = t * 1024 + threadIdx.x;
+        int4 v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int64_t i = base + q * 256;
+            v[q] = i < total4 ? __ldcs(&in[i]) : make_int4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int32_t a[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+            int32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (fast) {
+                    int32_t x = a[e];
+                    if (has_slope) {
+                        int64_t p;
+                        asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(p) : "r"(x), "r"(slope), "l"((int64_t)((1 << 24) - 1)));
+                        const int32_t pv = (int32_t)__funnelshift_r((uint32_t)p, (uint32_t)((uint64_t)p >> 32), 25);
+                        x = x < 0 ? pv : x;
+                    }
+                    x = max(min(x, B), -B);
+                    const int64_t c = (int64_t)(((uint64_t)c_hi << 32) | (uint64_t)(c_lo - (x < thr ? 1u : 0u)));
+                    int64_t tt;
+                    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(tt) : "r"(x), "r"((int32_t)mul), "l"(c));
+                    const int32_t r = (int32_t)__funnelshift_r((uint32_t)tt, (uint32_t)((uint64_t)tt >> 32), shift);
+                    o[e] = max(min(r, 127), -128);
+                } else {
+                    const int64_t r = epi_value(a[e], 0, has_slope, slope, mul, zp, shift);
+                    o[e] = (int32_t)(r < -128 ? -128 : (r > 127 ? 127 : r));
+                }
+            }
+            const int64_t i = base + q * 256;
+            if (i < total4)
+                out[i] = (uint32_t)(o[0] & 0xff) | ((uint32_t)(o[1] & 0xff) << 8) | ((uint32_t)(o[2] & 0xff) << 16) | ((uint32_t)(o[3] & 0xff) << 24);
+        }
+    }
+}
+
 static int ew_grid(int64_t total) {
     int64_t b = (total + 255) / 256;
     int64_t cap = (int64_t)sm_count() * 8;  // 8 resident 256-thread blocks per SM, grid-stride beyond that
@@ -150,7 +220,13 @@ extern "C" int fpcc_requant(const int32_t *in, int64_t rows, int ch, const fpcc_
     EpiParams ep = to_params(e);
     if (e->out_type == FPCC_OUT_I8 && e->mul_is_scalar && !e->bias && total % 16 == 0 &&
         (((uintptr_t)in | (uintptr_t)out) & 15) == 0) {
-        requant_scalar_i8_kernel<<<ew_grid(total / 16), 256, 0, s>>>((const int4 *)in, total / 16, ep, (uint4 *)out);
+        static const int variant = [] { const char *v = getenv("FPCC_REQUANT_VARIANT"); return v ? atoi(v) : 0; }();
+        if (variant == 1) {
+            const int64_t total4 = total / 4, tiles = (total4 + 1023) / 1024, cap = (int64_t)sm_count() * 8;
+            requant_scalar_i8_coalesced_kernel<<<(int)(tiles < cap ? tiles : cap), 256, 0, s>>>((const int4 *)in, total4, ep, (uint32_t *)out);
+        } else {
+            requant_scalar_i8_kernel<<<ew_grid(total / 16), 256, 0, s>>>((const int4 *)in, total / 16, ep, (uint4 *)out);
+        }
     } else if (ch % 4 == 0 && (((uintptr_t)in | (uintptr_t)out) & 15) == 0) {
         int64_t t4 = total / 4;
         if (e->out_type == FPCC_OUT_I8) requant_vec4_kernel<FPCC_OUT_I8><<<ew_grid(t4), 256, 0, s>>>((const int4 *)in, t4, ch / 4, ep, out);
