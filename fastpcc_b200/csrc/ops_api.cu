@@ -60,6 +60,41 @@ __global__ void __launch_bounds__(256) requant_vec4_kernel(const int4 *__restric
     }
 }
 
+template <bool SLOPE>
+__device__ __forceinline__ void requant_scalar_fast_loop(const int4 *__restrict__ in, int64_t total16, uint4 *__restrict__ out,
+                                                         int32_t slope, int32_t B, int32_t thr, int32_t mul, int64_t c0, int shift) {
+    const int64_t c_pos = c0, c_neg = c0 - 1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total16; i += (int64_t)gridDim.x * blockDim.x) {
+        int4 v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = __ldg(&in[4 * i + q]);
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int32_t a[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+            int32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                int32_t x = a[e];
+                if (SLOPE) {  // 0 <= slope <= 2^25: |result| <= |x|, the product is <= 0 for x < 0 so the -1 applies
+                    int64_t p;
+                    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(p) : "r"(x), "r"(slope), "l"((int64_t)((1 << 24) - 1)));
+                    const int32_t pv = (int32_t)__funnelshift_r((uint32_t)p, (uint32_t)((uint64_t)p >> 32), 25);
+                    x = x < 0 ? pv : x;
+                }
+                x = max(min(x, B), -B);
+                int64_t t;
+                asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(t) : "r"(x), "r"(mul), "l"(x < thr ? c_neg : c_pos));
+                o[e] = (int32_t)__funnelshift_r((uint32_t)t, (uint32_t)((uint64_t)t >> 32), shift);
+            }
+            uint32_t up;  // saturating pack: d = c[15:0] << 16 | sat8(a) << 8 | sat8(b)
+            asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(up) : "r"(o[3]), "r"(o[2]), "r"(0));
+            asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(w[q]) : "r"(o[1]), "r"(o[0]), "r"(up));
+        }
+        out[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
 // RequantFxpToScaledInt8 between layers: ONE multiplier, no bias, no PReLU, int8 out.  16 elements per thread per
 // step (four 16-byte loads in flight, one 16-byte store) and, when the ranges allow it, exact 32-bit arithmetic:
 // v is first clamped to [-B, B] with B the smallest magnitude that already saturates int8, so v*mul + zp fits a
@@ -88,38 +123,26 @@ __global__ void __launch_bounds__(256) requant_scalar_i8_kernel(const int4 *__re
         t = t > 2147483647ll ? 2147483647ll : (t < -2147483648ll ? -2147483648ll : t);
         B = (int32_t)b; thr = (int32_t)t;
     }
-    const uint32_t c_lo = (uint32_t)c0, c_hi = (uint32_t)((uint64_t)c0 >> 32);
+    // `fast` and `has_slope` are grid-uniform: one branch-free loop body per case, so that the 16 independent element
+    // chains of a thread interleave (a per-element fast/slow branch serialises them)
+    if (fast) {
+        if (has_slope) requant_scalar_fast_loop<true>(in, total16, out, slope, B, thr, (int32_t)mul, c0, shift);
+        else requant_scalar_fast_loop<false>(in, total16, out, slope, B, thr, (int32_t)mul, c0, shift);
+        return;
+    }
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total16; i += (int64_t)gridDim.x * blockDim.x) {
-        int4 v[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) v[q] = __ldg(&in[4 * i + q]);
         uint32_t w[4];
-#pragma unroll
+#pragma unroll 1
         for (int q = 0; q < 4; ++q) {
-            const int32_t a[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
-            int32_t o[4];
+            const int4 v = __ldg(&in[4 * i + q]);
+            const int32_t a[4] = {v.x, v.y, v.z, v.w};
+            uint32_t word = 0;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                if (fast) {
-                    int32_t x = a[e];
-                    if (has_slope) {  // 0 <= slope <= 2^25: |result| <= |x|, the product is <= 0 for x < 0 so the -1 applies
-                        int64_t p;
-                        asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(p) : "r"(x), "r"(slope), "l"((int64_t)((1 << 24) - 1)));
-                        const int32_t pv = (int32_t)__funnelshift_r((uint32_t)p, (uint32_t)((uint64_t)p >> 32), 25);
-                        x = x < 0 ? pv : x;
-                    }
-                    x = max(min(x, B), -B);
-                    const int64_t c = (int64_t)(((uint64_t)c_hi << 32) | (uint64_t)(c_lo - (x < thr ? 1u : 0u)));
-                    int64_t t;
-                    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(t) : "r"(x), "r"((int32_t)mul), "l"(c));
-                    const int32_t r = (int32_t)__funnelshift_r((uint32_t)t, (uint32_t)((uint64_t)t >> 32), shift);
-                    o[e] = max(min(r, 127), -128);
-                } else {
-                    const int64_t r = epi_value(a[e], 0, has_slope, slope, mul, zp, shift);
-                    o[e] = (int32_t)(r < -128 ? -128 : (r > 127 ? 127 : r));
-                }
+                const int64_t r = epi_value(a[e], 0, has_slope, slope, mul, zp, shift);
+                word |= (uint32_t)((int32_t)(r < -128 ? -128 : (r > 127 ? 127 : r)) & 0xff) << (8 * e);
             }
-            w[q] = (uint32_t)(o[0] & 0xff) | ((uint32_t)(o[1] & 0xff) << 8) | ((uint32_t)(o[2] & 0xff) << 16) | ((uint32_t)(o[3] & 0xff) << 24);
+            w[q] = word;
         }
         out[i] = make_uint4(w[0], w[1], w[2], w[3]);
     }
@@ -130,74 +153,6 @@ __global__ void __launch_bounds__(256) prelu_kernel(const int32_t *__restrict__ 
     const int32_t sl = slope[0];
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
         out[i] = clamp_i32(prelu_q25((int64_t)in[i], sl));
-}
-
-__global__ void __launch_bounds__(256) requant_scalar_i8_coalesced_kernel(const int4 *__restrict__ in, int64_t total4, EpiParams ep,
-                                                                          uint32_t *__restrict__ out) {
-    const int64_t zp = ep.zp[0];
-    const uint32_t mul = ep.mul[0];
-    const int shift = ep.shift;
-    const bool has_slope = ep.slope != nullptr;  // optional Q6.25 PReLU in front (PReLUIn32Out32 -> Requant chains)
-    const int32_t slope = has_slope ? ep.slope[0] : 0;
-    const int64_t half = shift > 0 ? (int64_t)1 << (shift - 1) : 0;
-    const int64_t c0 = zp + half;
-    const int64_t azp = zp < 0 ? -zp : zp;
-    bool fast = shift <= 31 && mul < (1u << 31) && (uint32_t)c0 != 0u && azp < ((int64_t)1 << 60) &&
-                (!has_slope || (slope >= 0 && slope <= (1 << 25)));
-    int32_t B = 0, thr = 0;
-    if (fast) {
-        const int64_t num = ((int64_t)129 << shift) + azp;
-        int64_t b = mul ? (num + (int64_t)mul - 1) / (int64_t)mul : 0;
-        fast = b <= 2147483646ll;  // inputs span all of int32 here: the clamp must not bind below saturation
-        fast = fast && ((num + (int64_t)mul + azp + ((int64_t)1 << 31)) >> shift) < 2147483647ll;
-        int64_t t;
-        if (mul == 0) t = zp < 0 ? 2147483647ll : -2147483648ll;
-        else { const int64_t nz = -zp, m = (int64_t)mul; t = nz >= 0 ? (nz + m - 1) / m : -((-nz) / m); }
-        t = t > 2147483647ll ? 2147483647ll : (t < -2147483648ll ? -2147483648ll : t);
-        B = (int32_t)b; thr = (int32_t)t;
-    }
-    const uint32_t c_lo = (uint32_t)c0, c_hi = (uint32_t)((uint64_t)c0 >> 32);
-    // every warp instruction touches 512 contiguous input bytes / 128 contiguous output bytes: four int4 loads per
-    // thread at a 256-vector stride (all in flight before the first use), four packed 4-byte stores
-    const int64_t tiles = (total4 + 1023) / 1024;
-    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-        const int64_t base = t * 1024 + threadIdx.x;
-        int4 v[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int64_t i = base + q * 256;
-            v[q] = i < total4 ? __ldcs(&in[i]) : make_int4(0, 0, 0, 0);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int32_t a[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
-            int32_t o[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                if (fast) {
-                    int32_t x = a[e];
-                    if (has_slope) {
-                        int64_t p;
-                        asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(p) : "r"(x), "r"(slope), "l"((int64_t)((1 << 24) - 1)));
-                        const int32_t pv = (int32_t)__funnelshift_r((uint32_t)p, (uint32_t)((uint64_t)p >> 32), 25);
-                        x = x < 0 ? pv : x;
-                    }
-                    x = max(min(x, B), -B);
-                    const int64_t c = (int64_t)(((uint64_t)c_hi << 32) | (uint64_t)(c_lo - (x < thr ? 1u : 0u)));
-                    int64_t tt;
-                    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(tt) : "r"(x), "r"((int32_t)mul), "l"(c));
-                    const int32_t r = (int32_t)__funnelshift_r((uint32_t)tt, (uint32_t)((uint64_t)tt >> 32), shift);
-                    o[e] = max(min(r, 127), -128);
-                } else {
-                    const int64_t r = epi_value(a[e], 0, has_slope, slope, mul, zp, shift);
-                    o[e] = (int32_t)(r < -128 ? -128 : (r > 127 ? 127 : r));
-                }
-            }
-            const int64_t i = base + q * 256;
-            if (i < total4)
-                out[i] = (uint32_t)(o[0] & 0xff) | ((uint32_t)(o[1] & 0xff) << 8) | ((uint32_t)(o[2] & 0xff) << 16) | ((uint32_t)(o[3] & 0xff) << 24);
-        }
-    }
 }
 
 static int ew_grid(int64_t total) {
@@ -220,13 +175,7 @@ extern "C" int fpcc_requant(const int32_t *in, int64_t rows, int ch, const fpcc_
     EpiParams ep = to_params(e);
     if (e->out_type == FPCC_OUT_I8 && e->mul_is_scalar && !e->bias && total % 16 == 0 &&
         (((uintptr_t)in | (uintptr_t)out) & 15) == 0) {
-        static const int variant = [] { const char *v = getenv("FPCC_REQUANT_VARIANT"); return v ? atoi(v) : 0; }();
-        if (variant == 1) {
-            const int64_t total4 = total / 4, tiles = (total4 + 1023) / 1024, cap = (int64_t)sm_count() * 8;
-            requant_scalar_i8_coalesced_kernel<<<(int)(tiles < cap ? tiles : cap), 256, 0, s>>>((const int4 *)in, total4, ep, (uint32_t *)out);
-        } else {
-            requant_scalar_i8_kernel<<<ew_grid(total / 16), 256, 0, s>>>((const int4 *)in, total / 16, ep, (uint4 *)out);
-        }
+        requant_scalar_i8_kernel<<<ew_grid(total / 16), 256, 0, s>>>((const int4 *)in, total / 16, ep, (uint4 *)out);
     } else if (ch % 4 == 0 && (((uintptr_t)in | (uintptr_t)out) & 15) == 0) {
         int64_t t4 = total / 4;
         if (e->out_type == FPCC_OUT_I8) requant_vec4_kernel<FPCC_OUT_I8><<<ew_grid(t4), 256, 0, s>>>((const int4 *)in, t4, ch / 4, ep, out);

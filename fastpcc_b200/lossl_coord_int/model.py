@@ -364,7 +364,9 @@ class Model(nn.Module):
         sys.setswitchinterval(1e-4)  # the groups interleave thousands of short launches: hand the GIL over quickly
         # leave one SM per concurrently coded stream of the other groups to the serial range-coder kernels
         sms = torch.cuda.get_device_properties(self.device).multi_processor_count
-        _lib.load().fpcc_set_sm_budget(max(sms // 2, sms - (len(items) - len(items) // n_groups)))
+        import os
+        budget = int(os.environ.get('FPCC_SM_BUDGET', '0')) or max(sms // 2, sms - (len(items) - len(items) // n_groups))
+        _lib.load().fpcc_set_sm_budget(budget)
         try:
             threads = [threading.Thread(target=work, args=(g,)) for g in range(n_groups)]
             for t in threads:
