@@ -18,8 +18,12 @@ for phase in ('compress', 'decompress'):
     else:
         m.decompress_batch(d)
     torch.cuda.synchronize()
-    rows = [(e0.elapsed_time(e1), tag, w.get('desc', '')) for tag, e0, e1, w in prof]
+    rows = []
+    for tag, e0, e1, w in prof:
+        ms = e0.elapsed_time(e1)
+        rate = f"{w['bytes'] / ms / 1e6:7.0f} GB/s " if w.get('bytes') else (f"{w['ops'] / ms / 1e9:7.0f} TOP/s" if w.get('ops') else ' ' * 13)
+        rows.append((ms, tag, rate + ' ' + str(w.get('desc', ''))))
     ops.enable_profile(False)
     print(f'== {phase}: {len(rows)} calls, {sum(r[0] for r in rows):.1f} ms in kernels')
-    for ms, tag, desc in sorted(rows, reverse=True)[:45]:
+    for ms, tag, desc in sorted(rows, reverse=True)[:80]:
         print(f'  {ms:8.3f} ms  {tag:28s} {desc}')
