@@ -224,8 +224,8 @@ struct FastCtx {
     uint32_t c0_lo, c0_hi;   // zp + 2^(shift-1)
     int64_t c_pos, c_neg;    // the same constant and constant - 1 as ready-made 64-bit addends of IMAD.WIDE
     int64_t k24;             // 2^24 - 1 (kernel argument, so that it stays a register-pair addend)
-    int shift;
-    uint32_t ovf_add, ovf_lim;  // I32: result fits iff (hi + ovf_add) < ovf_lim (unsigned)
+    int shift, shift_hi;        // min(shift, 32), max(shift - 32, 0)
+    uint32_t ovf_add, ovf_lim_m1;  // I32: result fits iff (hi + ovf_add) <= ovf_lim_m1 (unsigned)
 };
 
 __device__ __forceinline__ int64_t mad_wide(int32_t a, int32_t b, int64_t c) {  // one IMAD.WIDE
@@ -249,6 +249,11 @@ __device__ __forceinline__ int32_t prelu_fast(int32_t v, int32_t slope, int64_t 
     return v < 0 ? pv : v;
 }
 
+// Shifts 32..62 (the int32 / Q8.23 producing layers and most linears of a PTQ-converted model sit at 36-39) take the
+// same code: the clamped funnel shift by min(shift, 32) yields the HIGH word of the 64-bit sum, which a second
+// arithmetic shift by shift - 32 (0 below 32) turns into the quotient.  That quotient always fits int32, so for these
+// shifts the I32 overflow test is switched off (ovf_lim_m1 = 2^32 - 1); the saturation clamp of I8 / I16 stays valid
+// for any shift; |v*mul| < 2^62, |zp| <= 2^60, half <= 2^61 keep the sum inside int64.
 template <int OUT, bool SLOPE, bool ROWBIAS, bool ZP0>
 __device__ __forceinline__ bool epi_chunk_fast(const uint32_t (&acc)[EC], const FastCtx &fx, const int32_t *row_bias,
                                                int nvalid, int32_t (&o)[EC]) {
@@ -279,9 +284,9 @@ __device__ __forceinline__ bool epi_chunk_fast(const uint32_t (&acc)[EC], const 
         const int32_t thr = ZP0 ? 0 : lds32(fx.thr + q * 4);
         const int64_t t = mad_wide(v, ch.y, v < thr ? fx.c_neg : fx.c_pos);
         const uint32_t lo = (uint32_t)t, hi = (uint32_t)((uint64_t)t >> 32);
-        int32_t r = (int32_t)__funnelshift_r(lo, hi, fx.shift);
+        int32_t r = (int32_t)__funnelshift_rc(lo, hi, fx.shift) >> fx.shift_hi;  // fx.shift = min(shift, 32), shift_hi = max(shift - 32, 0)
         if (OUT == FPCC_OUT_I16) r = max(min(r, 32767), -32768);
-        if (OUT == FPCC_OUT_I32) bad |= hi + fx.ovf_add >= fx.ovf_lim;
+        if (OUT == FPCC_OUT_I32) bad |= hi + fx.ovf_add > fx.ovf_lim_m1;
         o[q] = r;  // I8: saturated by the packing conversion (or the scalar store path)
     }
     return !bad;
@@ -290,9 +295,11 @@ __device__ __forceinline__ bool epi_chunk_fast(const uint32_t (&acc)[EC], const 
 // CTA-uniform part of the fast-path preconditions
 __device__ __forceinline__ bool fast_uniform_ok(const EpiParams &ep, int out_type, int64_t zp, int64_t kk) {
     const int shift = ep.shift;
-    if (shift > 31 || shift < (out_type == FPCC_OUT_I32 ? 1 : 0) || kk > 65536) return false;
+    // upper limits: fast_channel's saturation bound (hi_t + 2) << shift must stay inside int64 (I8 / I16); I32 has no bound
+    const int shift_max = out_type == FPCC_OUT_I32 ? 62 : (out_type == FPCC_OUT_I8 ? 54 : 46);
+    if (shift > shift_max || shift < (out_type == FPCC_OUT_I32 ? 1 : 0) || kk > 65536) return false;
     const int64_t c0 = zp + (shift > 0 ? (int64_t)1 << (shift - 1) : 0);
-    if ((uint32_t)c0 == 0u || zp > ((int64_t)1 << 60) || zp < -((int64_t)1 << 60)) return false;
+    if ((shift <= 31 && (uint32_t)c0 == 0u) || zp > ((int64_t)1 << 60) || zp < -((int64_t)1 << 60)) return false;
     if (ep.slope) { const int32_t sl = ep.slope[0]; if (sl < 0 || sl > (1 << 25)) return false; }
     if (ep.post_slope) { const int32_t sl = ep.post_slope[0]; if (sl < 0 || sl > (1 << 25)) return false; }
     return true;
@@ -773,11 +780,13 @@ __global__ void __launch_bounds__((EW + 6) * 32, 1) igemm_tc_persistent(TcArgs a
                 cx.has_post = has_post; cx.dbg = a.dbg;
                 cx.nvalid = min(EC, a.N - nb);
                 FastCtx fx;
-                fx.chan = smem_u32(chan4_s + c0); fx.thr = smem_u32(thr_s + c0); fx.slope = slope; fx.post = post; fx.shift = shift;
+                fx.chan = smem_u32(chan4_s + c0); fx.thr = smem_u32(thr_s + c0); fx.slope = slope; fx.post = post;
+                fx.shift = min(shift, 32); fx.shift_hi = max(shift - 32, 0);
                 const int64_t c0v = zp + cx.half;
                 fx.c0_lo = (uint32_t)c0v; fx.c0_hi = (uint32_t)((uint64_t)c0v >> 32);
                 fx.c_pos = c0v; fx.c_neg = c0v - 1; fx.k24 = (int64_t)a.k24;
-                fx.ovf_add = shift > 0 ? 1u << (shift - 1) : 0u; fx.ovf_lim = 1u << (shift & 31);
+                fx.ovf_add = shift > 0 && shift <= 31 ? 1u << (shift - 1) : 0u;
+                fx.ovf_lim_m1 = shift <= 31 ? (1u << shift) - 1u : 0xffffffffu;
                 void *optr = (char *)out + (m * a.N + nb) * (ep.out_type == FPCC_OUT_I8 ? 1 : (ep.out_type == FPCC_OUT_I16 ? 2 : 4));
                 const bool vec = out_al && (a.N & 15) == 0;
                 const bool rb = ep.row_bias != nullptr;

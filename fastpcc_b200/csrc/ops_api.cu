@@ -60,7 +60,10 @@ __global__ void __launch_bounds__(256) requant_vec4_kernel(const int4 *__restric
     }
 }
 
-template <bool SLOPE>
+// HI: shift in [32, 62] (every RequantFxpToScaledInt8 of a PTQ-converted model: 23 + requant_shift is ~48).  The
+// quotient is then the high word of the 64-bit sum shifted by shift - 32: it always fits int32, so no clamp of the
+// input is needed, and |x*mul| < 2^62, |zp| < 2^60, half <= 2^61 keep the sum inside int64.
+template <bool SLOPE, bool HI>
 __device__ __forceinline__ void requant_scalar_fast_loop(const int4 *__restrict__ in, int64_t total16, uint4 *__restrict__ out,
                                                          int32_t slope, int32_t B, int32_t thr, int32_t mul, int64_t c0, int shift) {
     const int64_t c_pos = c0, c_neg = c0 - 1;
@@ -82,10 +85,11 @@ __device__ __forceinline__ void requant_scalar_fast_loop(const int4 *__restrict_
                     const int32_t pv = (int32_t)__funnelshift_r((uint32_t)p, (uint32_t)((uint64_t)p >> 32), 25);
                     x = x < 0 ? pv : x;
                 }
-                x = max(min(x, B), -B);
+                if (!HI) x = max(min(x, B), -B);
                 int64_t t;
                 asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(t) : "r"(x), "r"(mul), "l"(x < thr ? c_neg : c_pos));
-                o[e] = (int32_t)__funnelshift_r((uint32_t)t, (uint32_t)((uint64_t)t >> 32), shift);
+                o[e] = HI ? ((int32_t)((uint64_t)t >> 32) >> (shift - 32))
+                          : (int32_t)__funnelshift_r((uint32_t)t, (uint32_t)((uint64_t)t >> 32), shift);
             }
             uint32_t up;  // saturating pack: d = c[15:0] << 16 | sat8(a) << 8 | sat8(b)
             asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(up) : "r"(o[3]), "r"(o[2]), "r"(0));
@@ -109,25 +113,35 @@ __global__ void __launch_bounds__(256) requant_scalar_i8_kernel(const int4 *__re
     const int64_t half = shift > 0 ? (int64_t)1 << (shift - 1) : 0;
     const int64_t c0 = zp + half;
     const int64_t azp = zp < 0 ? -zp : zp;
-    bool fast = shift <= 31 && mul < (1u << 31) && (uint32_t)c0 != 0u && azp < ((int64_t)1 << 60) &&
+    const bool hi = shift >= 32 && shift <= 62;
+    bool fast = (hi || (shift <= 31 && (uint32_t)c0 != 0u)) && mul < (1u << 31) && azp < ((int64_t)1 << 60) &&
                 (!has_slope || (slope >= 0 && slope <= (1 << 25)));
     int32_t B = 0, thr = 0;
     if (fast) {
-        const int64_t num = ((int64_t)129 << shift) + azp;
-        int64_t b = mul ? (num + (int64_t)mul - 1) / (int64_t)mul : 0;
-        fast = b <= 2147483646ll;  // inputs span all of int32 here: the clamp must not bind below saturation
-        fast = fast && ((num + (int64_t)mul + azp + ((int64_t)1 << 31)) >> shift) < 2147483647ll;
+        int64_t b = 0;
+        if (!hi) {
+            const int64_t num = ((int64_t)129 << shift) + azp;
+            b = mul ? (num + (int64_t)mul - 1) / (int64_t)mul : 0;
+            fast = b <= 2147483646ll;  // inputs span all of int32 here: the clamp must not bind below saturation
+            fast = fast && ((num + (int64_t)mul + azp + ((int64_t)1 << 31)) >> shift) < 2147483647ll;
+        }
         int64_t t;
         if (mul == 0) t = zp < 0 ? 2147483647ll : -2147483648ll;
         else { const int64_t nz = -zp, m = (int64_t)mul; t = nz >= 0 ? (nz + m - 1) / m : -((-nz) / m); }
+        if (hi && t > 2147483647ll) fast = false;  // no input clamp on this path: x == INT32_MAX must still compare right
         t = t > 2147483647ll ? 2147483647ll : (t < -2147483648ll ? -2147483648ll : t);
         B = (int32_t)b; thr = (int32_t)t;
     }
     // `fast` and `has_slope` are grid-uniform: one branch-free loop body per case, so that the 16 independent element
     // chains of a thread interleave (a per-element fast/slow branch serialises them)
     if (fast) {
-        if (has_slope) requant_scalar_fast_loop<true>(in, total16, out, slope, B, thr, (int32_t)mul, c0, shift);
-        else requant_scalar_fast_loop<false>(in, total16, out, slope, B, thr, (int32_t)mul, c0, shift);
+        if (hi) {
+            if (has_slope) requant_scalar_fast_loop<true, true>(in, total16, out, slope, B, thr, (int32_t)mul, c0, shift);
+            else requant_scalar_fast_loop<false, true>(in, total16, out, slope, B, thr, (int32_t)mul, c0, shift);
+        } else {
+            if (has_slope) requant_scalar_fast_loop<true, false>(in, total16, out, slope, B, thr, (int32_t)mul, c0, shift);
+            else requant_scalar_fast_loop<false, false>(in, total16, out, slope, B, thr, (int32_t)mul, c0, shift);
+        }
         return;
     }
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total16; i += (int64_t)gridDim.x * blockDim.x) {

@@ -222,13 +222,32 @@ def test_epilogue_ranges_fast_and_wide_paths(ops):
         got = ops.linear(dev(a), dev(w), ep).cpu().numpy()
         assert got.dtype == np_t and (got == want).all(), (trial, shift, mul_hi, bias_hi, int(zp[0]), slope)
         cases += 1
+    # shifts 32..62 (the high-word fast path: the int32-producing layers and most linears of a converted model sit at
+    # 36-39): same sweep, zero points on both sides of the 2^60 precondition
+    for trial in range(60):
+        out_t, np_t = [(ops.OUT_I8, np.int8), (ops.OUT_I16, np.int16), (ops.OUT_I32, np.int32)][trial % 3]
+        shift = int(rng.integers(32, 63))
+        mul_hi = [1 << 20, (1 << 30) + 12345, (1 << 31) - 1, (1 << 32) - 1][int(rng.integers(0, 4))]
+        mul = rng.integers(mul_hi >> 2, mul_hi, n, endpoint=True).astype(np.uint32)
+        if trial % 7 == 0:
+            mul[::5] = 0
+        bias_hi = [1000, 1 << 20, 1 << 29, (1 << 31) - 1][int(rng.integers(0, 4))]
+        bias = rng.integers(-bias_hi, bias_hi, n, endpoint=True).astype(np.int32)
+        zs = min(shift, 57)
+        zp = np.array([[0, 0, 1, -1, 3 << zs, -(5 << zs), (1 << 40) + 12345, -(1 << 45), 1 << 60, -(1 << 60) - 1][int(rng.integers(0, 10))]], np.int64)
+        slope = [None, None, 0, 1 << 25, int(0.2 * (1 << 25)), -(1 << 23), 3 << 25][int(rng.integers(0, 7))]
+        slope = None if slope is None else np.array([slope], np.int32)
+        want = K.requant(acc0, mul, zp, shift, np_t, bias=bias, slope=slope)
+        ep = ops.make_epilogue(dev(mul), dev(zp), shift, out_t, bias=dev(bias), slope=None if slope is None else dev(slope))
+        got = ops.linear(dev(a), dev(w), ep).cpu().numpy()
+        assert got.dtype == np_t and (got == want).all(), ('hi', trial, shift, mul_hi, bias_hi, int(zp[0]), slope)
     # occupancy row bias with entries large enough to leave the proven range (per-chunk fall-back) + residual / post PReLU
     table = rng.integers(-(1 << 31), (1 << 31) - 1, (256, n), endpoint=True).astype(np.int32)
     table[:128] >>= 9
     idx = rng.integers(0, 256, m).astype(np.uint8)
     mul = rng.integers(1 << 10, 1 << 22, n).astype(np.uint32)
     bias = rng.integers(-(1 << 28), 1 << 28, n).astype(np.int32)
-    for out_t, np_t, shift in [(ops.OUT_I8, np.int8, 20), (ops.OUT_I32, np.int32, 9)]:
+    for out_t, np_t, shift in [(ops.OUT_I8, np.int8, 20), (ops.OUT_I32, np.int32, 9), (ops.OUT_I8, np.int8, 38), (ops.OUT_I32, np.int32, 37)]:
         for zpv in (0, 77777):
             zp = np.array([zpv], np.int64)
             slope = np.array([int(0.3 * (1 << 25))], np.int32)
@@ -250,16 +269,17 @@ def test_epilogue_ranges_fast_and_wide_paths(ops):
     # stand-alone requant with one multiplier (RequantFxpToScaledInt8, cuda_ops.py:478-507): full int32 inputs
     x = rng.integers(-(1 << 31), (1 << 31) - 1, (513, 64), endpoint=True).astype(np.int32)
     x[0, :8] = [-(1 << 31), (1 << 31) - 1, 0, -1, 1, -(1 << 31) + 1, 1 << 30, -(1 << 30)]
-    for shift in (0, 1, 7, 23, 31, 36):
-        for mulv in (0, 1, 3, 12345, (1 << 22) + 5, (1 << 31) - 1, (1 << 31) + 7):
-            for zpv in (0, -1, 5 << shift, -(1 << 40)):
+    for shift in (0, 1, 7, 23, 31, 32, 36, 48, 62):
+        for mulv in (0, 1, 3, 12345, (1 << 22) + 5, (1 << 30) + 99, (1 << 31) - 1, (1 << 31) + 7):
+            for zpv in (0, -1, 5 << min(shift, 57), -(1 << 40), (1 << 60) - 1, -(3 << 58)):
                 mul1, zp = np.array([mulv], np.uint32), np.array([zpv], np.int64)
                 want = K.requant(x, np.full(64, mulv, np.uint32), zp, shift, np.int8)
                 got = ops.requant(dev(x), ops.make_epilogue(dev(mul1), dev(zp), shift, ops.OUT_I8)).cpu().numpy()
                 assert (got == want).all(), (shift, mulv, zpv)
     # ... and with the PReLU in front (prelu_requant_to_int8, bias_prelu_requant.cu:6-37): slopes inside and outside [0, 1]
     for slope_v in (0, 1 << 25, int(0.3 * (1 << 25)), -(1 << 22), 3 << 25):
-        for shift, mulv, zpv in ((7, 12345, 0), (23, (1 << 22) + 5, -77), (31, 3, 5 << 31), (36, (1 << 31) + 7, 0)):
+        for shift, mulv, zpv in ((7, 12345, 0), (23, (1 << 22) + 5, -77), (31, 3, 5 << 31), (36, (1 << 31) + 7, 0),
+                                 (32, 3, -(5 << 33)), (48, (1 << 30) + 12345, 1 << 47), (48, (1 << 30) - 7, -(1 << 52) - 3), (62, (1 << 29) + 3, 0)):
             mul1, zp, sl = np.array([mulv], np.uint32), np.array([zpv], np.int64), np.array([slope_v], np.int32)
             want = K.requant(x, np.full(64, mulv, np.uint32), zp, shift, np.int8, slope=sl)
             got = ops.requant(dev(x), ops.make_epilogue(dev(mul1), dev(zp), shift, ops.OUT_I8, slope=dev(sl))).cpu().numpy()
