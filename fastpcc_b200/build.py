@@ -32,7 +32,8 @@ def build(force=False, verbose=False):
     for src in SOURCES:
         obj = osp.join(OUT_DIR, 'obj', src.replace('.cu', '.o'))
         objs.append(obj)
-        cmd = [nvcc] + NVCC_FLAGS + ['-Xptxas', '-v', '-c', osp.join(CSRC, src), '-o', obj]
+        # FPCC_NVCC_EXTRA: build-time experiment knobs, e.g. "-DFPCC_PAIRS_PRODUCER_WARPS=2" (use with force=True / -f)
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get('FPCC_NVCC_EXTRA', '').split() + ['-Xptxas', '-v', '-c', osp.join(CSRC, src), '-o', obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for src, p in procs:

@@ -473,6 +473,16 @@ __device__ __forceinline__ void epi_chunk_f(const uint32_t (&acc)[EC], const int
 // Fewer epilogue warps leave more issue slots (and registers: 128 / 96 / 80 per thread) to everyone else; the
 // gather-heavy conv prefers 12, the epilogue-bound linears 16.
 constexpr int EPI_WARPS_CONV = 12, EPI_WARPS_PAIRS = 16;
+// Gather-producer warps.  The conv needs a thread per output row (4 warps: per-row neighbour prefetch in registers).
+// The linears can run on 2 (each lane then issues 16 instead of 8 copies per stage): 16 + 2 + 2 = 20 warps put 5 warps
+// on every SM sub-partition, which lifts the register budget from 80 to 96 per thread (22 warps: 6 on one sub-partition,
+// 16384 / 192 = 85 -> 80).  Build-time experiment knob (-DFPCC_PAIRS_PRODUCER_WARPS=2); the default keeps 4.
+#ifndef FPCC_PAIRS_PRODUCER_WARPS
+#define FPCC_PAIRS_PRODUCER_WARPS 4
+#endif
+template <int MODE>
+constexpr int prod_warps() { return MODE == 1 ? FPCC_PAIRS_PRODUCER_WARPS : 4; }
+static_assert(FPCC_PAIRS_PRODUCER_WARPS == 4 || FPCC_PAIRS_PRODUCER_WARPS == 2, "producer warps: 2 or 4");
 
 struct PMeta {  // per-tile metadata, double buffered
     uint32_t kmask;
@@ -505,10 +515,11 @@ __device__ __forceinline__ void pairs_tile_lookup(const TcArgs &a, int tile_m, P
 // KIND: 0 = int8 x int8 -> int32 (kind::i8, integer requant epilogue), 1 = fp16, 2 = bf16 (kind::f16, fp32
 // accumulation, floating-point epilogue).  a.K is the contraction length in BYTES in every case.
 template <int MODE, int STAGES, int KIND, int EW>
-__global__ void __launch_bounds__((EW + 6) * 32, 1) igemm_tc_persistent(TcArgs a, const __grid_constant__ CUtensorMap tmap_w,
+__global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_tc_persistent(TcArgs a, const __grid_constant__ CUtensorMap tmap_w,
                                                                     EpiParams ep, FEpi fe, void *__restrict__ out, int tiles_m,
                                                                     int tiles_n) {
-    constexpr int P_EPI_WARPS = EW, P_PROD_WARP0 = EW, P_TMA_WARP = EW + 4, P_MMA_WARP = EW + 5, P_THREADS = (EW + 6) * 32;
+    constexpr int PW = prod_warps<MODE>(), PT = PW * 32;  // producer warps / threads
+    constexpr int P_EPI_WARPS = EW, P_PROD_WARP0 = EW, P_TMA_WARP = EW + PW, P_MMA_WARP = EW + PW + 1, P_THREADS = (EW + PW + 2) * 32;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int b_bytes = a.n_tile * TC_KB;
@@ -533,11 +544,11 @@ __global__ void __launch_bounds__((EW + 6) * 32, 1) igemm_tc_persistent(TcArgs a
 
     if (warp == P_MMA_WARP && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full[s], TC_M + 1);
+            mbar_init(&full[s], PT + 1);
             mbar_init(&empty[s], 1);
         }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(&meta_full[b], TC_M);
+            mbar_init(&meta_full[b], PT);
             mbar_init(&tmem_full[b], 1);
             mbar_init(&tmem_empty[b], P_EPI_WARPS);
         }
@@ -569,7 +580,7 @@ __global__ void __launch_bounds__((EW + 6) * 32, 1) igemm_tc_persistent(TcArgs a
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    if (warp >= P_PROD_WARP0 && warp < P_PROD_WARP0 + 4) {
+    if (warp >= P_PROD_WARP0 && warp < P_PROD_WARP0 + PW) {
         // ================= metadata + gather producers =================
         const int r = tid - P_PROD_WARP0 * 32;
         int it = 0;       // running pipeline step across tiles
@@ -592,7 +603,7 @@ __global__ void __launch_bounds__((EW + 6) * 32, 1) igemm_tc_persistent(TcArgs a
             int32_t *rows = rows_s + slot * rows_k * TC_M;
             mbar_wait(&tmem_empty[slot], ((j >> 1) & 1) ^ 1);  // slot's previous tile (j-2) fully consumed
             if (r == 0) meta[slot].kmask = 0;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(PT) : "memory");
             if (MODE == 0) {
                 const int m = tile_m * TC_M + r;
                 uint32_t mine = 0;
@@ -615,11 +626,14 @@ __global__ void __launch_bounds__((EW + 6) * 32, 1) igemm_tc_persistent(TcArgs a
                 if (lane == 0 && mine) atomicOr(&meta[slot].kmask, mine);
             } else {
                 if (r == 0) { pairs_tile_lookup(a, tile_m, &meta[slot]); }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                const int p = meta[slot].begin + r;
-                const bool ok = meta[slot].begin >= 0 && p < meta[slot].end;
-                rows[r] = ok ? (a.in_idx ? __ldg(&a.in_idx[p]) : p) : -1;
-                rows[TC_M + r] = ok ? (a.out_idx ? __ldg(&a.out_idx[p]) : p) : -1;
+                asm volatile("bar.sync 1, %0;" ::"n"(PT) : "memory");
+#pragma unroll
+                for (int rr = r; rr < TC_M; rr += PT) {
+                    const int p = meta[slot].begin + rr;
+                    const bool ok = meta[slot].begin >= 0 && p < meta[slot].end;
+                    rows[rr] = ok ? (a.in_idx ? __ldg(&a.in_idx[p]) : p) : -1;
+                    rows[TC_M + rr] = ok ? (a.out_idx ? __ldg(&a.out_idx[p]) : p) : -1;
+                }
                 if (r == 0) meta[slot].kmask = meta[slot].begin >= 0 && meta[slot].begin < meta[slot].end ? 1u : 0u;
             }
             __threadfence_block();
@@ -635,21 +649,24 @@ __global__ void __launch_bounds__((EW + 6) * 32, 1) igemm_tc_persistent(TcArgs a
                 // 8 consecutive lanes fetch the 8 16-byte pieces of ONE row (a full 128-byte line), 4 rows per
                 // instruction: 4 L1 wavefronts per LDGSTS instead of 32 with one row per lane.
                 // This lane serves rows base..base+7 (two 16-byte shared loads fetch their source rows).
-                const int base = (r & ~31) + (lane >> 3) * 8;
-                const uint32_t rk = smem_u32(rows + (MODE == 0 ? k : 0) * TC_M + base);
-                const int4 s0 = lds128(rk), s1 = lds128(rk + 16);
-                const int32_t srcs[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
                 const int piece = lane & 7;
                 const bool k_ok = kc * TC_KB + piece * 16 < a.K;
                 const uint32_t dst0 = smem_u32(sA + stage * a_bytes);
-                if (!(a.dbg & 1)) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int32_t src = srcs[i];
-                        const int row = base + i;
-                        const bool ok = src >= 0 && k_ok;
-                        const int8_t *gsrc = a.A + (ok ? (int64_t)src * a.K + kc * TC_KB + piece * 16 : 0);
-                        cp_async16(dst0 + row * TC_KB + ((piece ^ (row & 7)) << 4), gsrc, ok ? 16u : 0u);
+                for (int h = 0; h < TC_M / PT; ++h) {  // one pass with a producer thread per row, two with half as many
+                    const int base = (r & ~31) + (lane >> 3) * 8 + h * PT;
+                    const uint32_t rk = smem_u32(rows + (MODE == 0 ? k : 0) * TC_M + base);
+                    const int4 s0 = lds128(rk), s1 = lds128(rk + 16);
+                    const int32_t srcs[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                    if (!(a.dbg & 1)) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int32_t src = srcs[i];
+                            const int row = base + i;
+                            const bool ok = src >= 0 && k_ok;
+                            const int8_t *gsrc = a.A + (ok ? (int64_t)src * a.K + kc * TC_KB + piece * 16 : 0);
+                            cp_async16(dst0 + row * TC_KB + ((piece ^ (row & 7)) << 4), gsrc, ok ? 16u : 0u);
+                        }
                     }
                 }
                 // The stage's full barrier is signalled by the copy engine itself once this thread's copies have
@@ -926,7 +943,7 @@ static int launch_stages(const TcArgs &a, const CUtensorMap &tmap, const EpiPara
         FPCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX));
         configured = true;
     }
-    kern<<<grid, (EW + 6) * 32, smem, s>>>(a, tmap, ep, fe, out, tiles_m, n_blocks_n);
+    kern<<<grid, (EW + prod_warps<MODE>() + 2) * 32, smem, s>>>(a, tmap, ep, fe, out, tiles_m, n_blocks_n);
     FPCC_LAUNCH_CHECK();
     return FPCC_OK;
 }
