@@ -627,6 +627,12 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
             } else {
                 if (r == 0) { pairs_tile_lookup(a, tile_m, &meta[slot]); }
                 asm volatile("bar.sync 1, %0;" ::"n"(PT) : "memory");
+#if FPCC_PAIRS_PRODUCER_WARPS == 4  // the default build keeps the measured code verbatim (ptxas scheduling is sensitive here)
+                const int p = meta[slot].begin + r;
+                const bool ok = meta[slot].begin >= 0 && p < meta[slot].end;
+                rows[r] = ok ? (a.in_idx ? __ldg(&a.in_idx[p]) : p) : -1;
+                rows[TC_M + r] = ok ? (a.out_idx ? __ldg(&a.out_idx[p]) : p) : -1;
+#else
 #pragma unroll
                 for (int rr = r; rr < TC_M; rr += PT) {
                     const int p = meta[slot].begin + rr;
@@ -634,6 +640,7 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
                     rows[rr] = ok ? (a.in_idx ? __ldg(&a.in_idx[p]) : p) : -1;
                     rows[TC_M + rr] = ok ? (a.out_idx ? __ldg(&a.out_idx[p]) : p) : -1;
                 }
+#endif
                 if (r == 0) meta[slot].kmask = meta[slot].begin >= 0 && meta[slot].begin < meta[slot].end ? 1u : 0u;
             }
             __threadfence_block();
@@ -649,11 +656,30 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
                 // 8 consecutive lanes fetch the 8 16-byte pieces of ONE row (a full 128-byte line), 4 rows per
                 // instruction: 4 L1 wavefronts per LDGSTS instead of 32 with one row per lane.
                 // This lane serves rows base..base+7 (two 16-byte shared loads fetch their source rows).
+#if FPCC_PAIRS_PRODUCER_WARPS == 4
+                const int base = (r & ~31) + (lane >> 3) * 8;
+                const uint32_t rk = smem_u32(rows + (MODE == 0 ? k : 0) * TC_M + base);
+                const int4 s0 = lds128(rk), s1 = lds128(rk + 16);
+                const int32_t srcs[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                const int piece = lane & 7;
+                const bool k_ok = kc * TC_KB + piece * 16 < a.K;
+                const uint32_t dst0 = smem_u32(sA + stage * a_bytes);
+                if (!(a.dbg & 1)) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int32_t src = srcs[i];
+                        const int row = base + i;
+                        const bool ok = src >= 0 && k_ok;
+                        const int8_t *gsrc = a.A + (ok ? (int64_t)src * a.K + kc * TC_KB + piece * 16 : 0);
+                        cp_async16(dst0 + row * TC_KB + ((piece ^ (row & 7)) << 4), gsrc, ok ? 16u : 0u);
+                    }
+                }
+#else
                 const int piece = lane & 7;
                 const bool k_ok = kc * TC_KB + piece * 16 < a.K;
                 const uint32_t dst0 = smem_u32(sA + stage * a_bytes);
 #pragma unroll
-                for (int h = 0; h < TC_M / PT; ++h) {  // one pass with a producer thread per row, two with half as many
+                for (int h = 0; h < TC_M / PT; ++h) {  // two passes with half as many producer threads as rows
                     const int base = (r & ~31) + (lane >> 3) * 8 + h * PT;
                     const uint32_t rk = smem_u32(rows + (MODE == 0 ? k : 0) * TC_M + base);
                     const int4 s0 = lds128(rk), s1 = lds128(rk + 16);
@@ -669,6 +695,7 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
                         }
                     }
                 }
+#endif
                 // The stage's full barrier is signalled by the copy engine itself once this thread's copies have
                 // landed (no commit/wait lag in the producer): all STAGES stages can be in flight or queued.
                 asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full[stage])) : "memory");
