@@ -27,7 +27,10 @@ keys, vals = ops.hash_build(C)
 table = ops.kmap_lookup(keys, vals, C, (3, 3, 3), (1, 1, 1))
 pairs = int(torch.count_nonzero(table).item())
 ep = ops.make_epilogue(mul, zp, 24, ops.OUT_I8, bias=bias, slope=slope)
-ep32 = ops.make_epilogue(mul, zp, 6, ops.OUT_I32, bias=bias, slope=slope)
+ep32 = ops.make_epilogue(mul, zp, 6, ops.OUT_I32, bias=bias, slope=slope)  # overflows int32: every chunk falls back to the 64-bit epilogue
+# the regime of a PTQ-converted model's int32 (Q8.23) producing layers: multipliers near 2^30, shift 37 (high-word fast path)
+mul_r = torch.from_numpy(rng.integers(1 << 29, 1 << 30, ch).astype(np.int64)).to(torch.uint32).cuda()
+ep32r = ops.make_epilogue(mul_r, zp, 37, ops.OUT_I32, bias=bias, slope=slope)
 
 
 def t(fn, reps=5):
@@ -52,6 +55,8 @@ for dbg in (sys.argv[4].split(',') if len(sys.argv) > 4 else ['0']):
     print(f'[dbg {dbg}] linear n={n} {ch}->{ch}: {ms:.3f} ms  {2.0 * n * ch * ch / ms / 1e9:.1f} TOP/s')
     ms = t(lambda: ops.linear(f, w2, ep32))
     print(f'[dbg {dbg}] linear int32 out n={n} {ch}->{ch}: {ms:.3f} ms  {2.0 * n * ch * ch / ms / 1e9:.1f} TOP/s  {n * ch * 5 / ms / 1e6:.0f} GB/s')
+    ms = t(lambda: ops.linear(f, w2, ep32r))
+    print(f'[dbg {dbg}] linear int32 out (shift 37, converted-model regime) n={n} {ch}->{ch}: {ms:.3f} ms  {2.0 * n * ch * ch / ms / 1e9:.1f} TOP/s  {n * ch * 5 / ms / 1e6:.0f} GB/s')
 os.environ['FPCC_TC_DEBUG'] = '0'
 ms = t(lambda: ops.group_rows(table))
 tp, perm = ops.group_rows(table)
