@@ -81,7 +81,10 @@ _LIB = None
 
 
 def so_path():
-    return _build.SO
+    # FPCC_LIB_PATH: an experiment build of the SAME library (build.build_variant) for A/B timing; there is still no
+    # fallback of any kind: the named file must exist and export every declared symbol
+    import os
+    return os.environ.get('FPCC_LIB_PATH') or _build.SO
 
 
 def load(build_if_missing=True):

@@ -50,5 +50,32 @@ def build(force=False, verbose=False):
     return SO
 
 
+def build_variant(name, extra_flags):
+    """Experiment builds for A/B runs in ONE GPU call: the same sources with extra nvcc flags (e.g.
+    ['-DFPCC_PAIRS_PRODUCER_WARPS=2', '-DFPCC_EPI_TILE_DISPATCH=1']) into _C/variants/<name>/libfastpcc_b200.so,
+    selected at run time with FPCC_LIB_PATH (fastpcc_b200/_lib.py).  The default library is untouched."""
+    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+    out_dir = osp.join(OUT_DIR, 'variants', name)
+    os.makedirs(osp.join(out_dir, 'obj'), exist_ok=True)
+    procs, objs = [], []
+    for src in SOURCES:
+        obj = osp.join(out_dir, 'obj', src.replace('.cu', '.o'))
+        objs.append(obj)
+        cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + ['-Xptxas', '-v', '-c', osp.join(CSRC, src), '-o', obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log = []
+    for src, p in procs:
+        out, _ = p.communicate()
+        log.append(f'==== {src}\n{out}')
+        if p.returncode != 0:
+            sys.stderr.write(out)
+            raise RuntimeError(f'nvcc failed on {src}')
+    with open(osp.join(out_dir, 'ptxas.log'), 'w') as f:
+        f.write('\n'.join(log))
+    so = osp.join(out_dir, 'libfastpcc_b200.so')
+    subprocess.run([nvcc, '-shared', '-o', so] + objs, check=True)
+    return so
+
+
 if __name__ == '__main__':
     print(build(force='-f' in sys.argv, verbose='-v' in sys.argv))

@@ -419,6 +419,80 @@ __device__ __forceinline__ void epi_dispatch(const uint32_t (&acc)[EC], const Ep
     }
 }
 
+#ifndef FPCC_EPI_TILE_DISPATCH
+#define FPCC_EPI_TILE_DISPATCH 0
+#endif
+#if FPCC_EPI_TILE_DISPATCH
+// Build-time experiment (-DFPCC_EPI_TILE_DISPATCH=1, parity green on B200): all chunks of one tile row for one (output
+// type, PReLU, row-bias) case.  The case is chosen ONCE per tile (the per-chunk dispatch costs ~90 instructions of
+// uniform branches, parameter loads and pointer formation per 16 columns), the contexts and the row pointers are
+// formed once, and the row-bias table row is looked up once per tile.  At the 80-register cap of the 22-warp linear
+// kernel the hoisted values spill and the linears slow down; meant for the 96-register layouts.
+struct EpiTile {
+    uint32_t tacc;             // TMEM address of this warp's lane quarter, column 0 of the tile
+    int c_begin, c_end;        // this warp's columns
+    int n0, N, dbg, shift, k24;
+    bool have_acc, row_ok, has_post, fast, out_al;
+    int64_t m, zp;
+    int32_t slope, post;
+    const int4 *chan4_s;
+    const int32_t *thr_s;
+};
+
+template <int OUT, bool SLOPE, bool ROWBIAS>
+__device__ __forceinline__ void epi_tile(const EpiTile &t, const EpiParams &ep, void *out) {
+    constexpr int esz = OUT == FPCC_OUT_I8 ? 1 : (OUT == FPCC_OUT_I16 ? 2 : 4);
+    EpiCtx cx;
+    cx.chan = nullptr;
+    cx.slope = t.slope; cx.post = t.post; cx.zp = t.zp; cx.shift = t.shift;
+    cx.half = t.shift > 0 ? (int64_t)1 << (t.shift - 1) : 0; cx.sgn = t.shift > 0;
+    cx.has_post = t.has_post; cx.dbg = t.dbg;
+    FastCtx fx;
+    fx.slope = t.slope; fx.post = t.post;
+    fx.shift = min(t.shift, 32); fx.shift_hi = max(t.shift - 32, 0);
+    const int64_t c0v = t.zp + cx.half;
+    fx.c0_lo = (uint32_t)c0v; fx.c0_hi = (uint32_t)((uint64_t)c0v >> 32);
+    fx.c_pos = c0v; fx.c_neg = c0v - 1; fx.k24 = (int64_t)t.k24;
+    fx.ovf_add = t.shift > 0 && t.shift <= 31 ? 1u << (t.shift - 1) : 0u;
+    fx.ovf_lim_m1 = t.shift <= 31 ? (1u << t.shift) - 1u : 0xffffffffu;
+    const int64_t row0 = t.row_ok ? t.m * t.N + t.n0 : 0;
+    const int32_t *rb_row = (ROWBIAS && t.row_ok) ? ep.row_bias + (int64_t)__ldg(&ep.row_idx[t.m]) * t.N + t.n0 : nullptr;
+    const int32_t *res_row = ep.residual ? ep.residual + row0 : nullptr;
+    char *orow = (char *)out + row0 * esz;
+    const bool vec = t.out_al && (t.N & 15) == 0;
+    const bool zp0 = t.zp == 0;
+    for (int c0 = t.c_begin; c0 < t.c_end; c0 += EC) {
+        uint32_t acc[EC];
+        if (t.have_acc) {
+            tmem_ld16(t.tacc + (uint32_t)c0, acc);  // .sync.aligned: every lane, also those without a row
+        } else {
+#pragma unroll
+            for (int q = 0; q < EC; ++q) acc[q] = 0;
+        }
+        const int nb = t.n0 + c0;
+        if (!t.row_ok || nb >= t.N) continue;
+        if (t.dbg & 4) { if (c0 == 0) ((int32_t *)out)[t.m] = (int32_t)acc[0]; continue; }
+        cx.chan4 = t.chan4_s + c0;
+        cx.row_bias = ROWBIAS ? rb_row + c0 : nullptr;
+        cx.residual = res_row ? res_row + c0 : nullptr;
+        cx.nvalid = min(EC, t.N - nb);
+        fx.chan = smem_u32(t.chan4_s + c0); fx.thr = smem_u32(t.thr_s + c0);
+        epi_one<OUT, SLOPE, ROWBIAS>(acc, cx, fx, orow + c0 * esz, vec, t.fast, zp0);
+    }
+}
+
+template <int OUT>
+__device__ __forceinline__ void epi_tile_dispatch(const EpiTile &t, const EpiParams &ep, void *out, bool slope, bool rb) {
+    if (slope) {
+        if (rb) epi_tile<OUT, true, true>(t, ep, out);
+        else epi_tile<OUT, true, false>(t, ep, out);
+    } else {
+        if (rb) epi_tile<OUT, false, true>(t, ep, out);
+        else epi_tile<OUT, false, false>(t, ep, out);
+    }
+}
+#endif
+
 // ---- floating-point epilogue (kind::f16 path): v = acc + bias; act; [+ residual; post act]; cast -------------
 // act codes: 0 none, 1 relu, 2 leaky-relu / PReLU with one slope.  out_type: 0 fp16, 1 bf16, 2 fp32.
 struct FEpi {
@@ -797,6 +871,18 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
             mbar_wait(&tmem_full[slot], (j >> 1) & 1);
             tc_fence_after();
             const uint32_t tacc = tmem_base + (uint32_t)(slot * a.tmem_cols) + ((uint32_t)(quarter * 32) << 16);
+#if FPCC_EPI_TILE_DISPATCH
+            if (KIND == 0) {
+                EpiTile et;
+                et.tacc = tacc; et.c_begin = c_begin; et.c_end = c_end; et.n0 = n0; et.N = a.N; et.dbg = a.dbg; et.shift = shift;
+                et.k24 = a.k24; et.have_acc = have_acc; et.row_ok = row_ok; et.has_post = has_post; et.fast = fast; et.out_al = out_al;
+                et.m = m; et.zp = zp; et.slope = slope; et.post = post; et.chan4_s = chan4_s; et.thr_s = thr_s;
+                const bool rb = ep.row_bias != nullptr;
+                if (ep.out_type == FPCC_OUT_I8) epi_tile_dispatch<FPCC_OUT_I8>(et, ep, out, has_slope, rb);
+                else if (ep.out_type == FPCC_OUT_I32) epi_tile_dispatch<FPCC_OUT_I32>(et, ep, out, has_slope, rb);
+                else epi_tile_dispatch<FPCC_OUT_I16>(et, ep, out, has_slope, rb);
+            } else
+#endif
             for (int c0 = c_begin; c0 < c_end; c0 += EC) {
                 uint32_t acc[EC];
                 if (have_acc) {
