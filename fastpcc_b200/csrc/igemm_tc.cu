@@ -297,8 +297,7 @@ __device__ __forceinline__ bool fast_uniform_ok(const EpiParams &ep, int out_typ
     const int shift = ep.shift;
     // upper limits: fast_channel's saturation bound (hi_t + 2) << shift must stay inside int64 (I8 / I16); I32 has no bound
     const int shift_max = out_type == FPCC_OUT_I32 ? 62 : (out_type == FPCC_OUT_I8 ? 54 : 46);
-    // shift == 0 has no "-1 for negatives" (round half away only exists for shift > 0): the 64-bit path takes it
-    if (shift > shift_max || shift < 1 || kk > 65536) return false;
+    if (shift > shift_max || shift < (out_type == FPCC_OUT_I32 ? 1 : 0) || kk > 65536) return false;
     const int64_t c0 = zp + (shift > 0 ? (int64_t)1 << (shift - 1) : 0);
     if ((shift <= 31 && (uint32_t)c0 == 0u) || zp > ((int64_t)1 << 60) || zp < -((int64_t)1 << 60)) return false;
     if (ep.slope) { const int32_t sl = ep.slope[0]; if (sl < 0 || sl > (1 << 25)) return false; }
