@@ -172,6 +172,12 @@ __device__ __forceinline__ void store_words(char *optr, const uint32_t (&w)[WORD
         if (t * 16 < nbytes) reinterpret_cast<uint4 *>(optr)[t] = make_uint4(w[4 * t], w[4 * t + 1], w[4 * t + 2], w[4 * t + 3]);
 }
 
+// Build-time experiment (-DFPCC_EPI_PAIR_STORES=1, not yet run on a GPU): int32 outputs are 64 contiguous bytes per lane
+// and chunk, written as four STG.128 that each touch 32 HALF sectors (SM->L2 write bytes are 2x the output).
+// Lane pairs exchange two of their four 16-byte pieces by SHFL so that every STG.128 writes whole 32-byte sectors.
+#ifndef FPCC_EPI_PAIR_STORES
+#define FPCC_EPI_PAIR_STORES 0
+#endif
 struct EpiCtx {
     const int2 *chan;          // smem (bias, mul) pairs of this chunk (unused when chan4 is set)
     const int4 *chan4;         // smem (bias, mul, B, -B) of this chunk
@@ -183,6 +189,9 @@ struct EpiCtx {
     bool has_post;
     int nvalid;
     int dbg;                   // experiments: 128 compute but do not store, 256 store the raw accumulator
+#if FPCC_EPI_PAIR_STORES
+    char *optr_pair;           // I32 outputs: the lane ^ 1 partner's output pointer for this chunk, NULL = plain stores
+#endif
 };
 
 __device__ __forceinline__ int32_t sat_s8(int64_t r) { int32_t o; asm("cvt.sat.s8.s64 %0, %1;" : "=r"(o) : "l"(r)); return o; }
@@ -372,6 +381,28 @@ __device__ __forceinline__ void epi_store_chunk(int32_t (&o)[EC], const EpiCtx &
             for (int t = 0; t < EC / 2; ++t) w[t] = (uint32_t)(o[2 * t] & 0xffff) | ((uint32_t)o[2 * t + 1] << 16);
             store_words<EC / 2>((char *)optr, w, cx.nvalid * 2);
         } else {
+#if FPCC_EPI_PAIR_STORES
+            if (cx.optr_pair) {  // warp-uniform: every lane has a row and a whole chunk
+                const bool odd = (threadIdx.x & 1) != 0;
+                uint4 q[4], rcv[2];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) q[t] = make_uint4((uint32_t)o[4 * t], (uint32_t)o[4 * t + 1], (uint32_t)o[4 * t + 2], (uint32_t)o[4 * t + 3]);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {  // even lanes send pieces 1 and 3, odd lanes pieces 0 and 2
+                    const uint4 snd = odd ? q[2 * h] : q[2 * h + 1];
+                    rcv[h].x = __shfl_xor_sync(0xffffffffu, snd.x, 1); rcv[h].y = __shfl_xor_sync(0xffffffffu, snd.y, 1);
+                    rcv[h].z = __shfl_xor_sync(0xffffffffu, snd.z, 1); rcv[h].w = __shfl_xor_sync(0xffffffffu, snd.w, 1);
+                }
+                // store 1 / 3: the EVEN lane's row (bytes 0-31 / 32-63), store 2 / 4: the ODD lane's row
+                char *pa = (odd ? cx.optr_pair : (char *)optr) + (odd ? 16 : 0);
+                char *pb = (odd ? (char *)optr : cx.optr_pair) + (odd ? 16 : 0);
+                *reinterpret_cast<uint4 *>(pa) = odd ? rcv[0] : q[0];
+                *reinterpret_cast<uint4 *>(pb) = odd ? q[1] : rcv[0];
+                *reinterpret_cast<uint4 *>(pa + 32) = odd ? rcv[1] : q[2];
+                *reinterpret_cast<uint4 *>(pb + 32) = odd ? q[3] : rcv[1];
+                return;
+            }
+#endif
             uint32_t w[EC];
 #pragma unroll
             for (int t = 0; t < EC; ++t) w[t] = (uint32_t)o[t];
@@ -446,6 +477,9 @@ __device__ __forceinline__ void epi_tile(const EpiTile &t, const EpiParams &ep, 
     cx.slope = t.slope; cx.post = t.post; cx.zp = t.zp; cx.shift = t.shift;
     cx.half = t.shift > 0 ? (int64_t)1 << (t.shift - 1) : 0; cx.sgn = t.shift > 0;
     cx.has_post = t.has_post; cx.dbg = t.dbg;
+#if FPCC_EPI_PAIR_STORES
+    cx.optr_pair = nullptr;  // pairing is wired into the per-chunk loop only
+#endif
     FastCtx fx;
     fx.slope = t.slope; fx.post = t.post;
     fx.shift = min(t.shift, 32); fx.shift_hi = max(t.shift - 32, 0);
@@ -867,6 +901,10 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
             const int64_t mt = (int64_t)tile_m * TC_M + r;  // MODE 0: column of the neighbour table
             const bool row_ok = MODE == 0 ? (mt < a.n_out) : (rows[TC_M + r] >= 0);
             const int64_t m = MODE == 0 ? ((a.row_perm && row_ok) ? (int64_t)__ldg(&a.row_perm[mt]) : mt) : (int64_t)rows[TC_M + r];
+#if FPCC_EPI_PAIR_STORES
+            const bool pair_ok = KIND == 0 && ep.out_type == FPCC_OUT_I32 && out_al && (a.N & 15) == 0 && __all_sync(0xffffffffu, row_ok);
+            const int64_t m_pair = __shfl_xor_sync(0xffffffffu, m, 1);
+#endif
             mbar_wait(&tmem_full[slot], (j >> 1) & 1);
             tc_fence_after();
             const uint32_t tacc = tmem_base + (uint32_t)(slot * a.tmem_cols) + ((uint32_t)(quarter * 32) << 16);
@@ -909,6 +947,9 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
                 cx.residual = ep.residual ? ep.residual + m * a.N + nb : nullptr;
                 cx.has_post = has_post; cx.dbg = a.dbg;
                 cx.nvalid = min(EC, a.N - nb);
+#if FPCC_EPI_PAIR_STORES
+                cx.optr_pair = (pair_ok && cx.nvalid == EC) ? (char *)out + (m_pair * a.N + nb) * 4 : nullptr;
+#endif
                 FastCtx fx;
                 fx.chan = smem_u32(chan4_s + c0); fx.thr = smem_u32(thr_s + c0); fx.slope = slope; fx.post = post;
                 fx.shift = min(shift, 32); fx.shift_hi = max(shift - 32, 0);
