@@ -264,14 +264,23 @@ def main():
             hbm[k] = {'gb_per_step': round(v['bytes'] / 1e9, 3), 'achieved_gbs': round(gbs, 1), 'frac': round(gbs / hbm_peak, 3)}
 
     cpu = None
+    parity = None
     if rank == 0 and not args.no_cpu_baseline:
         from oracle.lossl_coord_int import Model as OracleModel
         om = OracleModel(sd, **CFG)
         sample = frames_host[0][:: args.cpu_stride]
         t = time.perf_counter()
-        rec = om.decompress(om.compress(sample))
+        want = om.compress(sample)
+        rec = om.decompress(want)
         dt = time.perf_counter() - t
         assert rec.shape[0] == sample.shape[0]
+        # parity on the benchmarked configuration (C=256 default topology): the bytes of the CUDA codec against the
+        # oracle's on the same sample, alone and inside a batch coded by concurrent groups
+        x = torch.from_numpy(sample).to(dev)
+        got = model.compress(x)
+        batch = model.compress_batch([frames_dev[1], x, frames_dev[2]], n_groups=3)
+        dec = model.decompress(got)
+        parity = bool(got == want and batch[1] == want and np.array_equal(dec.cpu().numpy(), rec))
         cpu = {'value': sample.shape[0] / dt / 1e6, 'unit': 'Mpts/s', 'cores': os.cpu_count(), 'kind': 'port',
                'sample': f'frame 0 subsampled 1:{args.cpu_stride} ({sample.shape[0]} pts), compress+decompress once, numpy/BLAS oracle'}
 
@@ -282,7 +291,9 @@ def main():
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int8', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'frames_per_step_per_gpu': args.frames, 'concurrent_groups': G, 'points_per_step': pts_all,
                        'l2': 'flushed between timed iterations (256 MB write)', 'weights': 'seeded random int8 (seed 7)',
-                       'roundtrip_lossless': bool(lossless)},
+                       'roundtrip_lossless': bool(lossless), 'parity_sample': parity,
+                       'parity_note': 'bitstream of the CUDA codec == bitstream of the CPU oracle (pinned to the reference Python, '
+                                      'tests/golden) on the cpu_baseline sample, single and inside a 3-group batch; decoded points equal'},
             'clocks': clocks,
             'e2e': {'value': pts_all / (ms_e2e * 1e-3) / 1e6, 'unit': 'Mpts/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': ms_e2e},
@@ -295,5 +306,34 @@ def main():
         dist.destroy_process_group()
 
 
+def _guarded_main():
+    """A failing rank prints its own traceback as its last stderr lines, a one-line JSON {"error": ...} on stdout and a
+    copy under gpurun_out/ (torchrun's failure summary otherwise hides it); `record` also puts it into that summary."""
+    import traceback
+    try:
+        from torch.distributed.elastic.multiprocessing.errors import record
+        fn = record(main)
+    except Exception:
+        fn = main
+    try:
+        fn()
+    except SystemExit:
+        raise
+    except BaseException as e:
+        rank = os.environ.get('RANK', '0')
+        tb = traceback.format_exc()
+        try:
+            os.makedirs(osp.join(ROOT, 'gpurun_out'), exist_ok=True)
+            with open(osp.join(ROOT, 'gpurun_out', f'bench_rank{rank}.err'), 'w') as f:
+                f.write(tb)
+        except OSError:
+            pass
+        sys.stdout.flush()
+        sys.stderr.write(f'\n[bench] rank {rank} FAILED:\n{tb}\n')
+        sys.stderr.flush()
+        print(json.dumps({'error': f'rank {rank}: {type(e).__name__}: {e}'[:2000]}), flush=True)
+        os._exit(1)
+
+
 if __name__ == '__main__':
-    main()
+    _guarded_main()

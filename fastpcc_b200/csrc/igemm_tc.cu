@@ -1105,7 +1105,11 @@ template <int MODE, int KIND>
 static int launch_tc(TcArgs &a, const void *W, int64_t w_rows, int tiles_m, const EpiParams &ep, const FEpi &fe, void *out,
                      cudaStream_t s) {
     int n_blocks_n = pick_tile(a.N, &a.n_tile, &a.tmem_cols);
+#ifdef FPCC_TC_DEBUG  // experiment builds only (build.build_variant(..., ['-DFPCC_TC_DEBUG'])): a release library ignores the variable
     { const char *e = getenv("FPCC_TC_DEBUG"); a.dbg = e ? atoi(e) : 0; }
+#else
+    a.dbg = 0;
+#endif
     a.k24 = (1 << 24) - 1;
     CUtensorMap tmap;
     int rc = weight_tensor_map((const int8_t *)W, w_rows, a.K, a.n_tile, &tmap);

@@ -114,7 +114,8 @@ __global__ void __launch_bounds__(256) requant_scalar_i8_kernel(const int4 *__re
     const int64_t c0 = zp + half;
     const int64_t azp = zp < 0 ? -zp : zp;
     const bool hi = shift >= 32 && shift <= 62;
-    bool fast = (hi || (shift <= 31 && (uint32_t)c0 != 0u)) && mul < (1u << 31) && azp < ((int64_t)1 << 60) &&
+    // mul == 0: the sign of v*mul + zp does not depend on v, which "v < thr" cannot express for v == INT32_MAX
+    bool fast = (hi || (shift <= 31 && (uint32_t)c0 != 0u)) && mul != 0u && mul < (1u << 31) && azp < ((int64_t)1 << 60) &&
                 (!has_slope || (slope >= 0 && slope <= (1 << 25)));
     int32_t B = 0, thr = 0;
     if (fast) {

@@ -74,10 +74,20 @@ class KernelMap:
         return self.as_pair_lists()[i]
 
 
-def _publish_ready():
-    """Derived parameter tensors are cached on the module and may be picked up by another thread on another CUDA stream:
-    finish the kernels that fill them before the cache entry becomes visible (once per parameter version)."""
-    torch.cuda.current_stream().synchronize()
+def _cached(mod, attr, key, make):
+    """Derived parameter tensors cached on a module are picked up by other threads on other CUDA streams (concurrent
+    coding groups): ONE thread builds them under ops.cache_lock, the kernels that fill them finish before the entry
+    becomes visible, and an entry is only replaced when the parameters it was derived from changed (ops.cache_lock)."""
+    cache = getattr(mod, attr, None)
+    if cache is not None and cache[0] == key:
+        return cache
+    with ops.cache_lock:
+        cache = getattr(mod, attr, None)
+        if cache is None or cache[0] != key:
+            cache = (key,) + tuple(make())
+            ops.publish_ready()
+            setattr(mod, attr, cache)
+    return cache
 
 
 def _as_kernel_map(in_out_maps, n_out, kernel_volume, idx_omit_map, device):
@@ -319,14 +329,12 @@ class SparseConvIn8Out8(_AffineIn8):
                 in_out_maps, hashmap_kv = build_kernel_map(in_coords, out_coords, self.kernel_size, self.stride, hashmap_kv)
             kmap = _as_kernel_map(in_out_maps, out_coords.shape[0], kv, -1, in_feats.device)
             kp = max(32, (kv * self.in_ch + 15) // 16 * 16)
-            cache = getattr(self, '_patch_weight', None)
-            key = (self.weight._version, self.weight.data_ptr(), kp)
-            if cache is None or cache[0] != key:
+            def make():
                 wf = torch.zeros((self.out_ch, kp), dtype=torch.int8, device=self.weight.device)
                 wf[:, :kv * self.in_ch] = self.weight.permute(1, 0, 2).reshape(self.out_ch, kv * self.in_ch)
-                cache = (key, wf)
-                _publish_ready()  # other CUDA streams (concurrent coding groups) may read the cached tensors next
-                self._patch_weight = cache
+                return (wf,)
+
+            cache = _cached(self, '_patch_weight', (self.weight._version, self.weight.data_ptr(), kp), make)
             patches = ops.gather_patches(in_feats, kmap.table, kp)
             return ops.linear(patches, cache[1], ep), hashmap_kv, kmap
         return sparse_conv_in8w8out32(
@@ -492,8 +500,7 @@ class LinearIn8W8(_AffineIn8):
     def _padded_channels(self):
         key = (self.weight._version, self.bias._version, self.requant_mul._version, self.int_zero_point_out._version,
                self.weight.data_ptr())
-        cache = getattr(self, '_pad_cache', None)
-        if cache is None or cache[0] != key:
+        def make():
             n_pad = (self.out_ch + 15) // 16 * 16
             pad = n_pad - self.out_ch
             w = torch.nn.functional.pad(self.weight, (0, 0, 0, pad)).contiguous()
@@ -507,9 +514,9 @@ class LinearIn8W8(_AffineIn8):
                 shift -= SharedFxpShift
             ep = ops.make_epilogue(mul, self.int_zero_point_out, shift, out_type, bias=bias,
                                    slope=self.slope if self.with_prelu else None)
-            cache = (key, w, ep)
-            _publish_ready()  # other CUDA streams (concurrent coding groups) may read the cached tensors next
-            self._pad_cache = cache
+            return w, ep
+
+        cache = _cached(self, '_pad_cache', key, make)
         return cache[1], cache[2]
 
     def forward_with_bits(self, input: torch.Tensor, occ: torch.Tensor, q0: int, q1: int) -> torch.Tensor:
@@ -519,16 +526,14 @@ class LinearIn8W8(_AffineIn8):
         contraction keeps K = C (identical integers, no concat, tensor-core friendly K)."""
         C = self.in_ch - 8
         key = (q0, q1, self.weight._version, self.weight.data_ptr())
-        cache = getattr(self, '_bits_cache', None)
-        if cache is None or cache[0] != key:
+        def make():
             w = self.weight
             pat = ((torch.arange(256, device=w.device)[:, None] >> torch.arange(7, -1, -1, device=w.device)[None]) & 1).double()
             q = pat * float(q1) + (1.0 - pat) * float(q0)                       # [256, 8]
             table = (q @ w[:, C:].double().T).round().to(torch.int32).contiguous()  # exact: |values| < 2^53
-            cache = (key, w[:, :C].contiguous(), table)
-            _publish_ready()  # other CUDA streams (concurrent coding groups) may read the cached tensors next
-            self._bits_cache = cache
-        _, w_main, table = cache
+            return w[:, :C].contiguous(), table
+
+        _, w_main, table = _cached(self, '_bits_cache', key, make)
         return ops.linear(input, w_main, self.epilogue(True, row_bias=(table, occ)))
 
 

@@ -425,9 +425,14 @@ class Model(nn.Module):
         V = self.MAX_CDF
         bot = levels[L].C
         frame_of = bot[:, 0].long().repeat_interleave(3)
-        bottom = bot[:, 1:].reshape(-1)                                    # int32 [3*n_bottom]
+        bottom_raw = bot[:, 1:].reshape(-1)                                # int32 [3*n_bottom]
+        # the stream stores len(cdf) - 2 under a 128-entry table (model.py:371 asserts len(cdf) - 2 <= 128): a coarser
+        # bottom level than that cannot be coded.  Index with the clamped value (no device-side assert that would poison
+        # the context of the other coding groups) and raise on the host at the next read-back.
+        bottom_max = bottom_raw.max() if bottom_raw.numel() else torch.zeros((), dtype=torch.int32, device=dev)
+        bottom = bottom_raw.clamp(max=V - 1)
         counts = torch.zeros((B, V), dtype=torch.int64, device=dev)
-        counts.view(-1).index_add_(0, frame_of * V + bottom.clamp(max=V - 1).long(), torch.ones_like(bottom, dtype=torch.int64))
+        counts.view(-1).index_add_(0, frame_of * V + bottom.long(), torch.ones_like(bottom, dtype=torch.int64))
         n_sym = counts.sum(1)                                              # 3 * bottom points of the frame
         ar = torch.arange(V, device=dev)
         n_cdf = ((counts > 0) * (ar + 1)).amax(1).clamp(min=2)            # bincount(minlength=2) length
@@ -484,7 +489,11 @@ class Model(nn.Module):
             ranges[base[fr] + torch.arange(lv.n, device=dev) - rows[fr]] = rng
             base = base + (rows[1:] - rows[:-1])
         rng_off = torch.cat([start, (start[-1] + per_frame[-1])[None]]).contiguous()
-        cap = (2 * int(per_frame.max().item()) + 64 + 3) & ~3  # <= 2 bytes per entry + the 4-byte state header
+        longest, bmax = torch.stack([per_frame.max(), bottom_max.to(per_frame.dtype)]).tolist()
+        if bmax > V - 1:
+            raise ValueError(f'bottom-level coordinate {bmax} exceeds {V - 1}: the per-frame CDF side info holds at most '
+                             f'{V} entries (reference model.py:371); use a larger max_stride or fewer skip_top_scales_num')
+        cap = (2 * int(longest) + 64 + 3) & ~3  # <= 2 bytes per entry + the 4-byte state header
         tr.mark('assemble')
         out, out_len = ops.rans_encode(ranges, rng_off, cap)
         lens = out_len.tolist()

@@ -4,6 +4,7 @@ PyTorch is plumbing here: device memory, the current CUDA stream, and a few inde
 computation on the hot path is a kernel of libfastpcc_b200.so; nothing falls back to torch or the CPU.
 """
 import ctypes as C
+import threading
 
 import torch
 
@@ -130,15 +131,32 @@ def make_epilogue(requant_mul, zero_point, shift, out_type, bias=None, slope=Non
     return e
 
 
+# Derived tensors that are cached and then read by every thread / CUDA stream (concurrent coding groups) follow ONE
+# rule: they are created under `cache_lock` by exactly one thread, their producing stream is synchronised BEFORE the
+# cache entry becomes visible, and a valid entry is never replaced.  (Replacing an entry frees a tensor that another
+# stream's pending kernels may still read: the caching allocator only orders reuse on the allocating stream.)
+cache_lock = threading.RLock()
+
+
+def publish_ready(device=None):
+    torch.cuda.current_stream(device).synchronize()
+
+
 _identity = {}
 
 
 def identity_epilogue(device):
     """acc*1 + 0 >> 0 -> int32: returns the raw accumulator (sparse_conv_in8w8out32's contract)."""
-    key = device.index
-    if key not in _identity:
-        _identity[key] = (torch.ones(1, dtype=torch.int32).view(torch.uint32).to(device), torch.zeros(1, dtype=torch.int64, device=device))
-    mul, zp = _identity[key]
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    ent = _identity.get(key)
+    if ent is None:
+        with cache_lock:
+            ent = _identity.get(key)
+            if ent is None:
+                ent = (torch.ones(1, dtype=torch.int32).view(torch.uint32).to(device), torch.zeros(1, dtype=torch.int64, device=device))
+                publish_ready(device)
+                _identity[key] = ent
+    mul, zp = ent
     return make_epilogue(mul, zp, 0, OUT_I32)
 
 
@@ -281,12 +299,11 @@ def prelu_i32(inp, slope):
     return out
 
 
-_POPC8 = None
+_POPC8 = {}
 
 
 def kmap_from_parent(coarse_table, coarse_occ, parent, slot):
     """3x3x3 same-stride neighbour table of a level from its parent level's table (see fpcc_kmap_from_parent)."""
-    global _POPC8
     _need(coarse_table, torch.int32, 'coarse table', 2)
     _need(coarse_occ, torch.uint8, 'coarse occupancy', 1)
     _need(parent, torch.int32, 'parent', 1)
@@ -294,11 +311,15 @@ def kmap_from_parent(coarse_table, coarse_occ, parent, slot):
     if coarse_table.shape[0] != 27 or coarse_table.shape[1] != coarse_occ.shape[0] or parent.shape[0] != slot.shape[0]:
         raise RuntimeError('kmap_from_parent: shape mismatch')
     dev = coarse_table.device
-    if _POPC8 is None or _POPC8.device != dev:
-        lut = torch.tensor([bin(v).count('1') for v in range(256)], dtype=torch.int32, device=dev)
-        torch.cuda.current_stream(dev).synchronize()  # shared by every stream from here on (concurrent coding groups)
-        _POPC8 = lut
-    cnt = _POPC8[coarse_occ.long()]
+    lut = _POPC8.get(dev.index)
+    if lut is None:
+        with cache_lock:
+            lut = _POPC8.get(dev.index)
+            if lut is None:
+                lut = torch.tensor([bin(v).count('1') for v in range(256)], dtype=torch.int32, device=dev)
+                publish_ready(dev)  # shared by every stream from here on (concurrent coding groups)
+                _POPC8[dev.index] = lut
+    cnt = lut[coarse_occ.long()]
     base = (torch.cumsum(cnt, 0, dtype=torch.int32) - cnt).contiguous()
     n_c, n_f = coarse_occ.shape[0], parent.shape[0]
     table = torch.empty((27, n_f), dtype=torch.int32, device=dev)

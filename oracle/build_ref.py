@@ -58,6 +58,33 @@ def build(verbose=False):
              extra_include_paths=[osp.join(REF_ROOT, i) for i in spec['includes']],
              extra_cflags=spec['cflags'], extra_ldflags=spec['ldflags'],
              build_directory=bdir, verbose=verbose)
+    stage_python()
+    return True
+
+
+PYREF_ZIP = osp.join(OUT, 'pyref.zip')
+_PY_TREES = ('lib', 'models', 'scripts')
+
+
+def stage_python(force=False):
+    """Archive the reference's .py files (lib/, models/) into oracle/_ref/pyref.zip so that the drop-in test
+    (tests/test_gpu_dropin.py: the UNMODIFIED reference model.py + cuda_ops.py running on this repo's extension
+    shim) can run on the GPU box, where /root/reference does not exist.  Same status as a `pip install --target` of
+    the reference: git-ignored, travels with the snapshot, never committed, extracted only into a temporary directory."""
+    if not osp.isdir(osp.join(REF_ROOT, 'models')):
+        return False
+    if osp.isfile(PYREF_ZIP) and not force:
+        return True
+    import zipfile
+    os.makedirs(OUT, exist_ok=True)
+    with zipfile.ZipFile(PYREF_ZIP, 'w', zipfile.ZIP_DEFLATED) as z:
+        for tree in _PY_TREES:
+            for root, dirs, files in os.walk(osp.join(REF_ROOT, tree)):
+                dirs[:] = [d for d in dirs if d not in ('build', '__pycache__')]
+                for f in files:
+                    if f.endswith('.py'):
+                        full = osp.join(root, f)
+                        z.write(full, osp.relpath(full, REF_ROOT))
     return True
 
 

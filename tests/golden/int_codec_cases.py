@@ -17,6 +17,15 @@ CASES = [
          cfg=dict(channels=64, max_stride_wo_recurrent=32, max_stride=128, fea_stride=16, skip_top_scales_num=1)),
     dict(name='c16_lidar', seed=1000, n=0, bits=16,
          cfg=dict(channels=16, max_stride_wo_recurrent=2048, max_stride=8192, fea_stride=16)),
+    # the benchmarked width: channels >= 256 is the only configuration that takes the SparseConvPReLUIn8W8Out32 embed
+    # branch of the 3- and 4-step predictors (reference model.py:130), and the tcgen05 kernels run whole 256-column tiles
+    dict(name='c256_fea16', seed=5, n=2500, bits=9,
+         cfg=dict(channels=256, max_stride_wo_recurrent=32, max_stride=128, fea_stride=16)),
+    # BASELINE configs[1]/[2] topology (model_config.py:10-14 defaults / kitti_ford_ch128.yaml) on a 1:16 LiDAR frame
+    dict(name='c128_lidar', seed=1001, n=0, bits=16,
+         cfg=dict(channels=128, max_stride_wo_recurrent=2048, max_stride=8192, fea_stride=16)),
+    dict(name='c256_lidar', seed=1002, n=0, bits=16,
+         cfg=dict(channels=256, max_stride_wo_recurrent=2048, max_stride=8192, fea_stride=16)),
 ]
 
 

@@ -120,84 +120,21 @@ def _make_ext():
 
 
 # ----------------------------------------------------------------------------------------------
-# import the reference with the absent third-party modules stubbed
+# import the reference with the absent third-party modules stubbed (shared with tests/test_gpu_dropin.py)
 # ----------------------------------------------------------------------------------------------
+from tests import ref_import  # noqa: E402
+
 
 def import_reference_model():
-    ts = types.ModuleType('torchsparse')
-    tsn = types.ModuleType('torchsparse.nn')
-
-    class SparseTensor:
-        def __init__(self, feats, coords, stride=(1, 1, 1), spatial_range=None):
-            self.F, self.C, self.spatial_range = feats, coords, spatial_range
-            self.stride = tuple(stride) if isinstance(stride, (tuple, list)) else (stride,) * 3
-            self._caches = types.SimpleNamespace(cmaps={}, kmaps={}, hashmaps={})
-
-    class Conv3d(nn.Module):
-        pass
-
-    ts.SparseTensor, ts.nn, tsn.Conv3d = SparseTensor, tsn, Conv3d
-    sys.modules['torchsparse'], sys.modules['torchsparse.nn'] = ts, tsn
-    for name in ('plyfile', 'open3d', 'cv2'):
-        if name not in sys.modules:
-            try:
-                importlib.import_module(name)
-            except ImportError:
-                m = types.ModuleType(name)
-                m.PlyData = m.PlyElement = object
-                sys.modules[name] = m
-
-    # compiled-extension loaders: hand back what is prebuilt from the reference's own C++ (range coder) or the
-    # CPU stand-in; nothing is compiled into /root/reference (read-only).
     simple_rans = build_ref.load_ref('simple_rans_ext_cpp')
     assert simple_rans is not None, 'run python oracle/build_ref.py first'
-    import torch.utils.cpp_extension as cpp_ext
-
-    def fake_load(name, *a, **kw):
-        if name == 'simple_rans_ext_cpp':
-            return simple_rans
-        if name == 'rans_ext_cpp':
-            return build_ref.load_ref('rans_ext_cpp')
-        return types.ModuleType(name)  # CUDA-only helpers (morton3d, knn...) never reached on the CPU branch
-    cpp_ext.load = fake_load
-
-    build_mod = types.ModuleType('lib.int_sparse_conv.build')
-    build_mod.int_sparse_conv_ext = _make_ext()
-    sys.modules['lib.int_sparse_conv.build'] = build_mod
-
-    # lossy_coord_v3/__init__ pulls in the whole v3 model (torchsparse internals); only its rans_coder
-    # sub-package is needed: register the package without executing its __init__.
-    pkg = types.ModuleType('models.convolutional.lossy_coord_v3')
-    pkg.__path__ = [osp.join(REF, 'models/convolutional/lossy_coord_v3')]
-    sys.modules['models.convolutional.lossy_coord_v3'] = pkg
-
-    torch.cuda.synchronize = lambda *a, **k: None
-    for _ in range(20):
-        try:
-            return importlib.import_module('models.convolutional.lossl_coord_int.model')
-        except ModuleNotFoundError as e:  # optional third-party imports of unrelated helpers
-            if e.name.split('.')[0] in ('lib', 'models'):
-                raise
-            sys.modules[e.name] = types.ModuleType(e.name)
-    raise RuntimeError('could not import the reference model')
+    return ref_import.import_reference_model(REF, _make_ext(), simple_rans=simple_rans, rans=build_ref.load_ref('rans_ext_cpp'),
+                                             stub_cuda_sync=True)
 
 
 def build_reference_model(ref, cfg):
-    c = ref.Config()
-    for k, v in cfg.items():
-        setattr(c, k, v)
-    m = ref.Model(c, torch.device('cpu'))
     sd_np = synth.make_lossl_int_state_dict(seed=7, **{k: v for k, v in cfg.items() if k != 'skip_top_scales_num'})
-    sd = {}
-    for k, v in sd_np.items():
-        t = torch.from_numpy(np.ascontiguousarray(v.view(np.int32) if v.dtype == np.uint32 else v))
-        sd[k] = t.view(torch.uint32) if v.dtype == np.uint32 else t
-    own = m.state_dict()
-    missing = [k for k in own if k not in sd and not k.split('.')[-1].startswith(('scale_', 'zero_point_'))]
-    assert not missing, missing
-    m.load_state_dict(sd, strict=False)
-    m.eval()
-    return m
+    return ref_import.build_reference_model(ref, cfg, sd_np)
 
 
 def main():

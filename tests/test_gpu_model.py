@@ -94,6 +94,75 @@ def test_concurrent_groups_on_a_fresh_model():
         assert all(torch.equal(a, b) for a, b in zip(rec, rec1))
 
 
+def _drop_caches(model):
+    """forget every lazily derived tensor (module caches and the process-wide ones) as a fresh process would"""
+    from fastpcc_b200 import ops
+    for mod in model.modules():
+        for attr in ('_patch_weight', '_pad_cache', '_bits_cache', '_bit_levels', '_shift_cache', '_unit_range'):
+            if hasattr(mod, attr):
+                delattr(mod, attr)
+    ops._POPC8.clear()
+    ops._identity.clear()
+
+
+@pytest.mark.parametrize('omp1', [False, True])
+def test_concurrent_groups_first_use_under_host_contention(omp1):
+    """Round-1 multi-GPU failure mode: under torchrun (OMP_NUM_THREADS=1, N processes on the same cores) a rank died in
+    its first steps.  The first step of every coding group builds the shared derived tensors; with the host threads
+    delayed at random that must still give the single-group bytes.  8 busy-loop threads hog the GIL and the cores
+    while fresh caches are raced by 3 groups, 12 times."""
+    import threading
+    cfg = dict(channels=64, max_stride_wo_recurrent=32, max_stride=128, fea_stride=16)
+    rng = np.random.default_rng(12)
+    frames = []
+    for i in range(9):
+        xyz = synth.surface_cloud(50 + i, bits=9, n_target=2500 + 200 * i) + rng.integers(0, 50, 3).astype(np.int32)
+        frames.append(torch.from_numpy(synth.with_batch(xyz)).cuda())
+    m, _ = _make(cfg)
+    want = m.compress_batch(frames)
+    rec1 = m.decompress_batch(want)
+    old_threads = torch.get_num_threads()
+    if omp1:
+        torch.set_num_threads(1)
+    stop = threading.Event()
+
+    def hog():
+        x = 0
+        while not stop.is_set():
+            x = (x * 1103515245 + 12345) & 0x7fffffff
+
+    hogs = [threading.Thread(target=hog, daemon=True) for _ in range(8)]
+    for h in hogs:
+        h.start()
+    try:
+        for trial in range(12):
+            _drop_caches(m)
+            got = m.compress_batch(frames, n_groups=3)
+            assert got == want, trial
+            _drop_caches(m)
+            rec = m.decompress_batch(got, n_groups=3)
+            assert all(torch.equal(a, b) for a, b in zip(rec, rec1)), trial
+    finally:
+        stop.set()
+        for h in hogs:
+            h.join()
+        torch.set_num_threads(old_threads)
+
+
+def test_bottom_level_too_wide_raises_on_the_host():
+    """A bottom level wider than the 130-entry side-info table is a clean host error (reference: AssertionError at
+    model.py:371), not a device-side index assert."""
+    cfg = dict(channels=16, max_stride_wo_recurrent=16, max_stride=64, fea_stride=4, skip_top_scales_num=3)
+    from fastpcc_b200.lossl_coord_int import Config, Model
+    sd = synth.make_lossl_int_state_dict(seed=7, **{k: v for k, v in cfg.items() if k != 'skip_top_scales_num'})
+    m = Model(Config(**cfg), device='cuda').load_numpy_state_dict(sd).cuda()
+    xyz = synth.surface_cloud(3, bits=11, n_target=3000)  # 11-bit grid, 3 levels coded: bottom coordinates up to 255
+    with pytest.raises(ValueError):
+        m.compress(torch.from_numpy(synth.with_batch(xyz)).cuda())
+    ok = synth.surface_cloud(3, bits=9, n_target=3000)
+    assert len(m.compress(torch.from_numpy(synth.with_batch(ok)).cuda())) > 8  # the context is still healthy
+
+
 def _golden():
     import json
     import os.path as osp
