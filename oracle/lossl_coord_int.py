@@ -363,7 +363,8 @@ class Model:
         off = np.array([int.from_bytes(data[2 * i: 2 * i + 2], 'little') for i in range(3)], dtype=np.int32)
         nb = int.from_bytes(data[6:8], 'little')
         dec = RansDecoder()
-        dec.flush(data[8:])
+        payload = data[8:]  # the reference's decoder keeps a pointer into these bytes: hold them until decoding is done
+        dec.flush(payload)
         # rans_decode_fea(decode_rounded_min=False), model.py:377-393
         clen = np.empty(1, dtype=np.uint16)
         dec.decode(self.cdf2, clen)
