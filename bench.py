@@ -80,11 +80,16 @@ class ClockSampler:
                 'samples': len(sm), 'power_w_max': max(float(s[2]) for s in samples)}
 
 
-def make_frames(n, rank):
+def make_frames(n, rank, world=1):
+    """This rank's frames of the job: the job is `world * n` independent scans (unit u = scan of seed 1000 + u); the units
+    are dealt to the ranks by fastpcc_b200.sharding (size-balanced assignment, no data-path collective) and every rank
+    generates only its own."""
     from concurrent.futures import ThreadPoolExecutor
-    from fastpcc_b200 import synth
-    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:  # numpy releases the GIL in the heavy parts
-        return list(pool.map(lambda i: synth.with_batch(synth.lidar_frame(1000 + rank * 1000 + i)), range(n)))
+    from fastpcc_b200 import sharding, synth
+    units = sharding.local_indices([1] * (world * n), rank=rank, world=world)
+    workers = max(1, min(8, (os.cpu_count() or 1) // max(1, world)))  # numpy releases the GIL in the heavy parts
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        return list(pool.map(lambda u: synth.with_batch(synth.lidar_frame(1000 + u)), units))
 
 
 def cpu_arm_model(cores):
@@ -183,7 +188,7 @@ def main():
 
     sd = synth.make_lossl_int_state_dict(seed=7, **CFG)
     model = Model(Config(**CFG), device=dev).load_numpy_state_dict(sd).to(dev)
-    frames_host = make_frames(args.frames, rank)
+    frames_host = make_frames(args.frames, rank, world)
     pinned = [torch.from_numpy(f).pin_memory() for f in frames_host]
     frames_dev = [p.to(dev) for p in pinned]
     n_pts = sum(f.shape[0] for f in frames_host)

@@ -24,22 +24,25 @@ def assign(sizes: Sequence[int], world: int) -> List[List[int]]:
     return out
 
 
-def local_indices(sizes: Sequence[int], rank: Optional[int] = None, world: Optional[int] = None) -> List[int]:
+def local_indices(sizes: Sequence[int], rank: Optional[int] = None, world: Optional[int] = None, group=None) -> List[int]:
+    """Unit indices of this rank.  `rank` / `world` default to the position in `group` (the default group if None)."""
     if world is None:
-        world = dist.get_world_size() if dist.is_initialized() else 1
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
     if rank is None:
-        rank = dist.get_rank() if dist.is_initialized() else 0
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
     return assign(sizes, world)[rank]
 
 
 def gather_ordered(local: Dict[int, bytes], n_total: int, dst: int = 0, group=None) -> Optional[List[bytes]]:
-    """Collects {unit index: bytes} from every rank on `dst`, returned in unit order (None elsewhere)."""
+    """Collects {unit index: bytes} from every rank on `dst`, returned in unit order (None elsewhere).
+    `dst` is a rank WITHIN `group` (the default group if None); it is translated to the global rank gather_object takes."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         assert len(local) == n_total
         return [local[i] for i in range(n_total)]
     rank = dist.get_rank(group)
     bucket = [None] * dist.get_world_size(group) if rank == dst else None
-    dist.gather_object(local, bucket, dst=dst, group=group)
+    global_dst = dist.get_global_rank(group, dst) if group is not None else dst
+    dist.gather_object(local, bucket, dst=global_dst, group=group)
     if rank != dst:
         return None
     merged: Dict[int, bytes] = {}
@@ -55,7 +58,7 @@ def compress_sharded(compress_batch: Callable[[list], List[bytes]], units: list,
                      dst: int = 0, group=None) -> Optional[List[bytes]]:
     """Every rank codes its share of `units` with `compress_batch` (e.g. Model.compress_batch); rank `dst` gets
     all bitstreams in the original order."""
-    mine = local_indices(sizes)
+    mine = local_indices(sizes, group=group)
     coded = compress_batch([units[i] for i in mine]) if mine else []
     return gather_ordered(dict(zip(mine, coded)), len(units), dst=dst, group=group)
 

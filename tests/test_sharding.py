@@ -41,6 +41,16 @@ def _worker(rank, world, port, q):
         out = sharding.compress_sharded(fake_compress, units, sizes)
         mine = sharding.local_indices(sizes)
         assert [units[i] for i in mine] == seen
+        # the same through an explicit group with the LAST group rank as destination: assignment and gather must agree
+        # on the position inside the group, and `dst` is a group rank (advisor finding of round 1)
+        grp = dist.new_group(ranks=[0, 1])
+        seen.clear()
+        out_g = sharding.compress_sharded(fake_compress, units, sizes, dst=1, group=grp)
+        assert [units[i] for i in sharding.local_indices(sizes, group=grp)] == seen
+        if dist.get_rank(grp) == 1:
+            assert out_g is not None and [o[1:4] for o in out_g] == [u[:3] for u in units]
+        else:
+            assert out_g is None
         if rank == 0:
             q.put(out)
         else:
