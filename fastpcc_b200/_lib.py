@@ -15,7 +15,7 @@ class Epilogue(C.Structure):
     """fpcc_epilogue (include/fastpcc_b200.h)"""
     _fields_ = [('bias', _vp), ('slope', _vp), ('requant_mul', _vp), ('zero_point', _vp),
                 ('shift', C.c_int32), ('out_type', C.c_int32), ('mul_is_scalar', C.c_int32),
-                ('residual', _vp), ('post_slope', _vp), ('row_bias', _vp), ('row_idx', _vp)]
+                ('residual', _vp), ('post_slope', _vp), ('row_bias', _vp), ('row_idx', _vp), ('row_bias_bound', C.c_int32)]
 
 
 _EP = C.POINTER(Epilogue)

@@ -83,13 +83,14 @@ struct EpiParams {  // device-side copy of fpcc_epilogue with scalars resolved t
     const int32_t *post_slope;
     const int32_t *row_bias;
     const uint8_t *row_idx;
+    int32_t row_bias_bound;
 };
 static inline EpiParams to_params(const fpcc_epilogue *e) {
     EpiParams p;
     p.bias = e->bias; p.slope = e->slope; p.mul = e->requant_mul; p.zp = e->zero_point;
     p.shift = e->shift; p.out_type = e->out_type; p.mul_is_scalar = e->mul_is_scalar;
     p.residual = e->residual; p.post_slope = e->post_slope;
-    p.row_bias = e->row_bias; p.row_idx = e->row_idx;
+    p.row_bias = e->row_bias; p.row_idx = e->row_idx; p.row_bias_bound = e->row_bias_bound;
     return p;
 }
 int check_epilogue(const fpcc_epilogue *e, bool allow_residual);

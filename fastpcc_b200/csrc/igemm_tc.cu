@@ -145,9 +145,6 @@ struct TcArgs {
     // MODE_PAIRS
     const int32_t *in_idx, *out_idx, *offsets;
     int n_groups, n_pairs, bias_per_group;
-    int k24;  // (1 << 24) - 1, see FastCtx
-    int dbg;  // FPCC_TC_DEBUG bitmask (experiments only): 1 skip A loads, 2 skip B loads, 4 skip epilogue math, 8 skip MMA,
-              // 16 force the 64-bit epilogue
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -159,9 +156,15 @@ struct TcArgs {
 //   warps 8-11  gather producers (one output row per thread) + per-tile metadata (source rows, offset mask)
 //   warp 12     weight producer (TMA)          warp 13   TMEM owner + MMA issuer
 // ---------------------------------------------------------------------------------------------
-// Epilogue of one 32-column chunk of one output row.  Values stay in registers; the body is specialised at compile
-// time on the output type, the PReLU and the occupancy row-bias so that the 32x unrolled arithmetic carries no
-// per-element selects: ~22 (no PReLU) / ~32 (PReLU) integer instructions per element, all 64-bit exact.
+// ---------------------------------------------------------------------------------------------
+// Integer epilogue.  Two implementations of the reference's arithmetic (bias_prelu_requant.cu:6-37, prelu.cu:6-21,
+// cuda_ops.py:82-92):
+//   * lean_tile   32-bit registers, ~5 (no PReLU) / ~8.5 (PReLU) instructions per element, taken when the CTA-uniform
+//                 and per-channel preconditions proven at staging time hold (every layer of a PTQ-converted model);
+//   * epi_chunk   exact 64-bit arithmetic for everything else (odd shifts, huge multipliers, slopes outside [0, 1],
+//                 int16 outputs, unaligned rows ...).
+// Both give the same integers wherever the lean preconditions hold (tests/test_gpu_ops.py sweeps both).
+// ---------------------------------------------------------------------------------------------
 constexpr int EC = 16;  // accumulator columns per epilogue step (one tcgen05.ld.32x32b.x16)
 
 // 16-byte vector stores of the packed words of one chunk (nbytes is a multiple of 16)
@@ -172,70 +175,45 @@ __device__ __forceinline__ void store_words(char *optr, const uint32_t (&w)[WORD
         if (t * 16 < nbytes) reinterpret_cast<uint4 *>(optr)[t] = make_uint4(w[4 * t], w[4 * t + 1], w[4 * t + 2], w[4 * t + 3]);
 }
 
-// Build-time experiment (-DFPCC_EPI_PAIR_STORES=1, not yet run on a GPU): int32 outputs are 64 contiguous bytes per lane
-// and chunk, written as four STG.128 that each touch 32 HALF sectors (SM->L2 write bytes are 2x the output).
-// Lane pairs exchange two of their four 16-byte pieces by SHFL so that every STG.128 writes whole 32-byte sectors.
-#ifndef FPCC_EPI_PAIR_STORES
-#define FPCC_EPI_PAIR_STORES 0
-#endif
 struct EpiCtx {
-    const int2 *chan;          // smem (bias, mul) pairs of this chunk (unused when chan4 is set)
-    const int4 *chan4;         // smem (bias, mul, B, -B) of this chunk
+    const int4 *chan4;         // smem (bias, mul, thr, -) of this chunk
     int32_t slope, post;
     int64_t zp, half;          // half = 2^(shift-1) (0 when shift == 0)
     int shift, sgn;            // sgn = 1 when shift > 0 (round-half-away correction for negatives)
-    const int32_t *row_bias;   // 32 entries of the occupancy-indexed bias row (ROWBIAS)
-    const int32_t *residual;   // 32 entries, or NULL
+    const int32_t *row_bias;   // entries of the occupancy-indexed bias row of this chunk (ROWBIAS)
+    const int32_t *residual;   // entries of this chunk, or NULL
     bool has_post;
     int nvalid;
-    int dbg;                   // experiments: 128 compute but do not store, 256 store the raw accumulator
-#if FPCC_EPI_PAIR_STORES
-    char *optr_pair;           // I32 outputs: the lane ^ 1 partner's output pointer for this chunk, NULL = plain stores
-#endif
 };
 
 __device__ __forceinline__ int32_t sat_s8(int64_t r) { int32_t o; asm("cvt.sat.s8.s64 %0, %1;" : "=r"(o) : "l"(r)); return o; }
 __device__ __forceinline__ int32_t sat_s16(int64_t r) { int32_t o; asm("cvt.sat.s16.s64 %0, %1;" : "=r"(o) : "l"(r)); return o; }
 __device__ __forceinline__ int32_t sat_s32(int64_t r) { int32_t o; asm("cvt.sat.s32.s64 %0, %1;" : "=r"(o) : "l"(r)); return o; }
 
+// exact value of one element before the narrowing store (all 64-bit)
+template <int OUT>
+__device__ __forceinline__ int32_t epi_exact(int32_t a32, int32_t bias, uint32_t mul, bool has_slope, int32_t slope, int64_t zp,
+                                             int64_t half, int sgn, int shift) {
+    int64_t v = (int64_t)a32 + (int64_t)bias;
+    if (has_slope) {  // Q6.25 PReLU on negatives, round half away (bias_prelu_requant.cu:17-22)
+        int64_t t = v * (int64_t)slope;
+        t = (t + ((1ll << 24) - (int64_t)((uint64_t)t >> 63))) >> 25;
+        v = v < 0 ? t : v;
+    }
+    int64_t r = v * (int64_t)mul + zp;
+    r = (r + (half - (int64_t)(((uint64_t)r >> 63) & (uint64_t)sgn))) >> shift;
+    return OUT == FPCC_OUT_I8 ? sat_s8(r) : (OUT == FPCC_OUT_I16 ? sat_s16(r) : sat_s32(r));
+}
+
 template <int OUT, bool SLOPE, bool ROWBIAS>
 __device__ __forceinline__ void epi_chunk(const uint32_t (&acc)[EC], const EpiCtx &cx, int32_t (&o)[EC]) {
 #pragma unroll
     for (int q = 0; q < EC; ++q) {
-        const int32_t bias = cx.chan4 ? cx.chan4[q].x : cx.chan[q].x;
-        const uint32_t mul = (uint32_t)(cx.chan4 ? cx.chan4[q].y : cx.chan[q].y);
         int32_t a32 = (int32_t)acc[q];
         if (ROWBIAS) a32 = (int32_t)((uint32_t)a32 + (uint32_t)__ldg(&cx.row_bias[q < cx.nvalid ? q : 0]));
-        int64_t v = (int64_t)a32 + (int64_t)bias;
-        if (SLOPE) {  // Q6.25 PReLU on negatives, round half away (bias_prelu_requant.cu:17-22)
-            int64_t t = v * (int64_t)cx.slope;
-            t = (t + ((1ll << 24) - (int64_t)((uint64_t)t >> 63))) >> 25;
-            v = v < 0 ? t : v;
-        }
-        int64_t r = v * (int64_t)mul + cx.zp;
-        r = (r + (cx.half - (int64_t)(((uint64_t)r >> 63) & (uint64_t)cx.sgn))) >> cx.shift;
-        o[q] = OUT == FPCC_OUT_I8 ? sat_s8(r) : (OUT == FPCC_OUT_I16 ? sat_s16(r) : sat_s32(r));
+        o[q] = epi_exact<OUT>(a32, cx.chan4[q].x, (uint32_t)cx.chan4[q].y, SLOPE, cx.slope, cx.zp, cx.half, cx.sgn, cx.shift);
     }
 }
-
-// ---- 32-bit fast path -------------------------------------------------------------------------------------
-// The same results as epi_chunk with ~11 (no PReLU) / ~15 (PReLU) 32-bit instructions per element.  It is taken
-// when the CTA-uniform preconditions checked at staging time hold (fast_ok below); a chunk whose values leave the
-// proven ranges falls back to epi_chunk.  Per channel, staged in shared memory:
-//   x bias   y mul (< 2^31)   z B   w -B,  thr[c]
-//   B:   |v| >= B  =>  the requantised value saturates the output type, so clamping v to [-B, B] first changes
-//        nothing and makes v*mul + zp fit comfortably in 64 bits with a quotient that fits 32 bits (I8 / I16);
-//   thr: v*mul + zp < 0  <=>  v < thr  (the "-1 for negatives" of round-half-away; thr == 0 when zp == 0).
-struct FastCtx {
-    uint32_t chan;   // shared-space addresses (explicit ld.shared: the compiler cannot prove the space of a struct member)
-    uint32_t thr;
-    int32_t slope, post;
-    uint32_t c0_lo, c0_hi;   // zp + 2^(shift-1)
-    int64_t c_pos, c_neg;    // the same constant and constant - 1 as ready-made 64-bit addends of IMAD.WIDE
-    int64_t k24;             // 2^24 - 1 (kernel argument, so that it stays a register-pair addend)
-    int shift, shift_hi;        // min(shift, 32), max(shift - 32, 0)
-    uint32_t ovf_add, ovf_lim_m1;  // I32: result fits iff (hi + ovf_add) <= ovf_lim_m1 (unsigned)
-};
 
 __device__ __forceinline__ int64_t mad_wide(int32_t a, int32_t b, int64_t c) {  // one IMAD.WIDE
     int64_t d;
@@ -247,97 +225,20 @@ __device__ __forceinline__ int4 lds128(uint32_t addr) {
     asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ int32_t lds32(uint32_t addr) {
-    int32_t v;
-    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
+__device__ __forceinline__ int64_t pack64(uint32_t lo, uint32_t hi) {
+    int64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+    return d;
 }
-__device__ __forceinline__ int32_t prelu_fast(int32_t v, int32_t slope, int64_t k24 = (1 << 24) - 1) {  // 0 <= slope <= 2^25: |result| <= |v|
-    const int64_t p = mad_wide(v, slope, k24);  // v < 0 => product <= 0 => the -1 applies
-    const int32_t pv = (int32_t)__funnelshift_r((uint32_t)p, (uint32_t)((uint64_t)p >> 32), 25);
-    return v < 0 ? pv : v;
-}
-
-// Shifts 32..62 (the int32 / Q8.23 producing layers and most linears of a PTQ-converted model sit at 36-39) take the
-// same code: the clamped funnel shift by min(shift, 32) yields the HIGH word of the 64-bit sum, which a second
-// arithmetic shift by shift - 32 (0 below 32) turns into the quotient.  That quotient always fits int32, so for these
-// shifts the I32 overflow test is switched off (ovf_lim_m1 = 2^32 - 1); the saturation clamp of I8 / I16 stays valid
-// for any shift; |v*mul| < 2^62, |zp| <= 2^60, half <= 2^61 keep the sum inside int64.
-template <int OUT, bool SLOPE, bool ROWBIAS, bool ZP0>
-__device__ __forceinline__ bool epi_chunk_fast(const uint32_t (&acc)[EC], const FastCtx &fx, const int32_t *row_bias,
-                                               int nvalid, int32_t (&o)[EC]) {
-    bool bad = false;
-    // occupancy-indexed bias row: every lane reads its own table row, so a 4-byte load per element costs 32 L1
-    // wavefronts each; one 16-byte load per four elements when the chunk is whole and aligned
-    const bool rb_vec = ROWBIAS && nvalid == EC && ((uintptr_t)row_bias & 15) == 0;
-    int4 rb4 = make_int4(0, 0, 0, 0);
-#pragma unroll
-    for (int q = 0; q < EC; ++q) {
-        const int4 ch = lds128(fx.chan + q * 16);
-        int32_t v = (int32_t)acc[q];
-        if (ROWBIAS) {
-            int32_t rbv;
-            if (rb_vec) {
-                if ((q & 3) == 0) rb4 = __ldg(reinterpret_cast<const int4 *>(row_bias) + (q >> 2));
-                rbv = (q & 3) == 0 ? rb4.x : ((q & 3) == 1 ? rb4.y : ((q & 3) == 2 ? rb4.z : rb4.w));
-            } else {
-                rbv = __ldg(&row_bias[q < nvalid ? q : 0]);
-            }
-            v = (int32_t)((uint32_t)v + (uint32_t)rbv);
-            bad |= (uint32_t)v + (1u << 30) > (1u << 31);  // keeps v + bias inside int32
-        }
-        v += ch.x;
-        if (SLOPE) v = prelu_fast(v, fx.slope, fx.k24);
-        if (OUT != FPCC_OUT_I32) v = max(min(v, ch.z), ch.w);
-        // t = v*mul + zp + half - [v*mul + zp < 0]: one of two predicated IMAD.WIDE with the addend already formed
-        const int32_t thr = ZP0 ? 0 : lds32(fx.thr + q * 4);
-        const int64_t t = mad_wide(v, ch.y, v < thr ? fx.c_neg : fx.c_pos);
-        const uint32_t lo = (uint32_t)t, hi = (uint32_t)((uint64_t)t >> 32);
-        int32_t r = (int32_t)__funnelshift_rc(lo, hi, fx.shift) >> fx.shift_hi;  // fx.shift = min(shift, 32), shift_hi = max(shift - 32, 0)
-        if (OUT == FPCC_OUT_I16) r = max(min(r, 32767), -32768);
-        if (OUT == FPCC_OUT_I32) bad |= hi + fx.ovf_add > fx.ovf_lim_m1;
-        o[q] = r;  // I8: saturated by the packing conversion (or the scalar store path)
-    }
-    return !bad;
-}
-
-// CTA-uniform part of the fast-path preconditions
-__device__ __forceinline__ bool fast_uniform_ok(const EpiParams &ep, int out_type, int64_t zp, int64_t kk) {
-    const int shift = ep.shift;
-    // upper limits: fast_channel's saturation bound (hi_t + 2) << shift must stay inside int64 (I8 / I16); I32 has no bound
-    const int shift_max = out_type == FPCC_OUT_I32 ? 62 : (out_type == FPCC_OUT_I8 ? 54 : 46);
-    if (shift > shift_max || shift < (out_type == FPCC_OUT_I32 ? 1 : 0) || kk > 65536) return false;
-    const int64_t c0 = zp + (shift > 0 ? (int64_t)1 << (shift - 1) : 0);
-    if ((shift <= 31 && (uint32_t)c0 == 0u) || zp > ((int64_t)1 << 60) || zp < -((int64_t)1 << 60)) return false;
-    if (ep.slope) { const int32_t sl = ep.slope[0]; if (sl < 0 || sl > (1 << 25)) return false; }
-    if (ep.post_slope) { const int32_t sl = ep.post_slope[0]; if (sl < 0 || sl > (1 << 25)) return false; }
-    return true;
-}
-
-// Per-channel constants of the fast path; returns false when this channel cannot take it.
-__device__ __forceinline__ bool fast_channel(int32_t bias, uint32_t mul, int64_t zp, int shift, int out_type, int4 *ch, int32_t *thr) {
-    bool ok = mul < (1u << 31) && bias <= (1 << 29) && bias >= -(1 << 29);
-    const int64_t azp = zp < 0 ? -zp : zp;
-    int64_t B = 0;
-    if (out_type != FPCC_OUT_I32) {
-        const int64_t hi_t = out_type == FPCC_OUT_I8 ? 127 : 32767;
-        const int64_t num = ((hi_t + 2) << shift) + azp;
-        B = mul ? (num + (int64_t)mul - 1) / (int64_t)mul : 0;
-        if (B > 2147483646ll) B = 2147483646ll;
-        // |v*mul + zp + half| <= num + mul + |zp| + half must shift down into 32 bits
-        ok = ok && ((num + (int64_t)mul + azp + ((int64_t)1 << 31)) >> shift) < 2147483647ll;
-    }
-    int64_t t;
-    if (mul == 0) t = zp < 0 ? 2147483647ll : -2147483648ll;
-    else { const int64_t nz = -zp, m = (int64_t)mul; t = nz >= 0 ? (nz + m - 1) / m : -((-nz) / m); }
-    t = t > 2147483647ll ? 2147483647ll : (t < -2147483648ll ? -2147483648ll : t);
-    *ch = make_int4(bias, (int32_t)mul, (int32_t)B, (int32_t)-B);
-    *thr = (int32_t)t;
-    return ok;
+// Q6.25 PReLU for 0 <= slope <= 2^25 (|result| <= |v|): rha(v*slope, 25) == (v*slope + 2^24 - 1) >> 25 for v < 0 (the product
+// is <= 0 there); for v >= 0 the same expression is <= v, so the PReLU is a plain max.
+__device__ __forceinline__ int32_t prelu_unit(int32_t v, int32_t slope, int64_t k24) {
+    const int64_t p = mad_wide(v, slope, k24);
+    return max(v, (int32_t)__funnelshift_r((uint32_t)p, (uint32_t)((uint64_t)p >> 32), 25));
 }
 
 template <int OUT>
-__device__ __forceinline__ void epi_store_chunk(int32_t (&o)[EC], const EpiCtx &cx, void *optr, bool vec, bool fast_post) {
+__device__ __forceinline__ void epi_store_chunk(int32_t (&o)[EC], const EpiCtx &cx, void *optr, bool vec) {
     if (OUT == FPCC_OUT_I32 && cx.residual) {
         if (vec) {
             const int4 *rp = reinterpret_cast<const int4 *>(cx.residual);
@@ -354,16 +255,10 @@ __device__ __forceinline__ void epi_store_chunk(int32_t (&o)[EC], const EpiCtx &
             for (int q = 0; q < EC; ++q) o[q] = (int32_t)((uint32_t)o[q] + (uint32_t)__ldg(&cx.residual[q < cx.nvalid ? q : 0]));
         }
         if (cx.has_post) {
-            if (fast_post) {
 #pragma unroll
-                for (int q = 0; q < EC; ++q) o[q] = prelu_fast(o[q], cx.post);
-            } else {
-#pragma unroll
-                for (int q = 0; q < EC; ++q) o[q] = sat_s32(prelu_q25((int64_t)o[q], cx.post));
-            }
+            for (int q = 0; q < EC; ++q) o[q] = sat_s32(prelu_q25((int64_t)o[q], cx.post));
         }
     }
-    if ((cx.dbg & 128) && o[0] != 0x7fffffff) return;
     if (vec) {  // nvalid == EC here (N is a multiple of 16)
         if (OUT == FPCC_OUT_I8) {
             uint32_t w[EC / 4];
@@ -381,28 +276,6 @@ __device__ __forceinline__ void epi_store_chunk(int32_t (&o)[EC], const EpiCtx &
             for (int t = 0; t < EC / 2; ++t) w[t] = (uint32_t)(o[2 * t] & 0xffff) | ((uint32_t)o[2 * t + 1] << 16);
             store_words<EC / 2>((char *)optr, w, cx.nvalid * 2);
         } else {
-#if FPCC_EPI_PAIR_STORES
-            if (cx.optr_pair) {  // warp-uniform: every lane has a row and a whole chunk
-                const bool odd = (threadIdx.x & 1) != 0;
-                uint4 q[4], rcv[2];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) q[t] = make_uint4((uint32_t)o[4 * t], (uint32_t)o[4 * t + 1], (uint32_t)o[4 * t + 2], (uint32_t)o[4 * t + 3]);
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {  // even lanes send pieces 1 and 3, odd lanes pieces 0 and 2
-                    const uint4 snd = odd ? q[2 * h] : q[2 * h + 1];
-                    rcv[h].x = __shfl_xor_sync(0xffffffffu, snd.x, 1); rcv[h].y = __shfl_xor_sync(0xffffffffu, snd.y, 1);
-                    rcv[h].z = __shfl_xor_sync(0xffffffffu, snd.z, 1); rcv[h].w = __shfl_xor_sync(0xffffffffu, snd.w, 1);
-                }
-                // store 1 / 3: the EVEN lane's row (bytes 0-31 / 32-63), store 2 / 4: the ODD lane's row
-                char *pa = (odd ? cx.optr_pair : (char *)optr) + (odd ? 16 : 0);
-                char *pb = (odd ? (char *)optr : cx.optr_pair) + (odd ? 16 : 0);
-                *reinterpret_cast<uint4 *>(pa) = odd ? rcv[0] : q[0];
-                *reinterpret_cast<uint4 *>(pb) = odd ? q[1] : rcv[0];
-                *reinterpret_cast<uint4 *>(pa + 32) = odd ? rcv[1] : q[2];
-                *reinterpret_cast<uint4 *>(pb + 32) = odd ? q[3] : rcv[1];
-                return;
-            }
-#endif
             uint32_t w[EC];
 #pragma unroll
             for (int t = 0; t < EC; ++t) w[t] = (uint32_t)o[t];
@@ -420,111 +293,252 @@ __device__ __forceinline__ void epi_store_chunk(int32_t (&o)[EC], const EpiCtx &
     }
 }
 
-template <int OUT, bool SLOPE, bool ROWBIAS>
-__device__ __forceinline__ void epi_one(const uint32_t (&acc)[EC], const EpiCtx &cx, const FastCtx &fx, void *optr, bool vec,
-                                        bool fast, bool zp0) {
-    int32_t o[EC];
-    bool done = false;
-    if (cx.dbg & 256) {
-#pragma unroll
-        for (int q = 0; q < EC; ++q) o[q] = (int32_t)acc[q];
-        done = true;
-    } else if (fast) {
-        done = zp0 ? epi_chunk_fast<OUT, SLOPE, ROWBIAS, true>(acc, fx, cx.row_bias, cx.nvalid, o)
-                   : epi_chunk_fast<OUT, SLOPE, ROWBIAS, false>(acc, fx, cx.row_bias, cx.nvalid, o);
-    }
-    if (!done) epi_chunk<OUT, SLOPE, ROWBIAS>(acc, cx, o);
-    epi_store_chunk<OUT>(o, cx, optr, vec, fast);
-}
-
 template <int OUT>
-__device__ __forceinline__ void epi_dispatch(const uint32_t (&acc)[EC], const EpiCtx &cx, const FastCtx &fx, void *optr, bool vec,
-                                             bool slope, bool rb, bool fast, bool zp0) {
+__device__ __forceinline__ void epi_dispatch(const uint32_t (&acc)[EC], const EpiCtx &cx, void *optr, bool vec, bool slope, bool rb) {
+    int32_t o[EC];
     if (slope) {
-        if (rb) epi_one<OUT, true, true>(acc, cx, fx, optr, vec, fast, zp0);
-        else epi_one<OUT, true, false>(acc, cx, fx, optr, vec, fast, zp0);
+        if (rb) epi_chunk<OUT, true, true>(acc, cx, o);
+        else epi_chunk<OUT, true, false>(acc, cx, o);
     } else {
-        if (rb) epi_one<OUT, false, true>(acc, cx, fx, optr, vec, fast, zp0);
-        else epi_one<OUT, false, false>(acc, cx, fx, optr, vec, fast, zp0);
+        if (rb) epi_chunk<OUT, false, true>(acc, cx, o);
+        else epi_chunk<OUT, false, false>(acc, cx, o);
     }
+    epi_store_chunk<OUT>(o, cx, optr, vec);
 }
 
-#ifndef FPCC_EPI_TILE_DISPATCH
-#define FPCC_EPI_TILE_DISPATCH 0
-#endif
-#if FPCC_EPI_TILE_DISPATCH
-// Build-time experiment (-DFPCC_EPI_TILE_DISPATCH=1, parity green on B200): all chunks of one tile row for one (output
-// type, PReLU, row-bias) case.  The case is chosen ONCE per tile (the per-chunk dispatch costs ~90 instructions of
-// uniform branches, parameter loads and pointer formation per 16 columns), the contexts and the row pointers are
-// formed once, and the row-bias table row is looked up once per tile.  At the 80-register cap of the 22-warp linear
-// kernel the hoisted values spill and the linears slow down; meant for the 96-register layouts.
-struct EpiTile {
-    uint32_t tacc;             // TMEM address of this warp's lane quarter, column 0 of the tile
-    int c_begin, c_end;        // this warp's columns
-    int n0, N, dbg, shift, k24;
-    bool have_acc, row_ok, has_post, fast, out_al;
-    int64_t m, zp;
+// ---- lean path --------------------------------------------------------------------------------------------------
+// t' = v*mul + c0 - [v*mul + zp < 0],  c0 = zp + 2^(shift-1),  result = t' >> shift  (one IMAD.WIDE + one shift).
+// How the "-1 for negatives" reaches the 64-bit addend depends on the CTA-uniform case (sign mode):
+//   SGN_LO0     zp == 0, shift <= 32: c0 = 2^(shift-1) fits the low word and is >= 1, so c0 - 1 never borrows:
+//               lo = c0_lo + (v >> 31) (one LEA.HI.SX32), hi = 0.
+//   SGN_HI0     zp == 0, shift >= 33: c0_lo == 0:  lo = sx, hi = c0_hi + sx  with sx = v >> 31.
+//   SGN_THR_*   zp != 0 (asymmetric activations feeding a Linear): the sign of v*mul + zp is v < thr[c] with the staged
+//               per-channel threshold ceil(-zp / mul); c0_lo != 0 is required so that c0 - 1 stays in the low word.
+// *_LO: shift <= 32 (clamped funnel shift of the pair), *_HI: shift >= 32 (arithmetic shift of the high word).
+// The accumulator bound |acc| <= K*kvol*127*128 is static, |bias| <= 2^29 and the row-bias bound are checked, so v and
+// v*mul + c0 stay inside int32 / int64; a per-channel check proves that the shifted value fits 32 bits for int8 outputs;
+// int32 outputs with shift < 32 test the high word per element and redo a chunk exactly when one value saturates.
+enum { SGN_LO0 = 0, SGN_HI0 = 1, SGN_THR_LO = 2, SGN_THR_HI = 3, SGN_NONE = -1 };
+
+struct LeanU {
     int32_t slope, post;
-    const int4 *chan4_s;
-    const int32_t *thr_s;
+    uint32_t c0_lo, c0_hi;
+    int shift;
+    uint32_t ovf_add, ovf_lim;   // I32, shift < 32: the result fits iff (hi + ovf_add) <= ovf_lim (unsigned)
+    int64_t k24;                 // 2^24 - 1, read back from shared memory: ptxas splits an immediate or uniform 64-bit addend of
+                                 // IMAD.WIDE into IADD3 + IMAD.X; a vector register pair stays the instruction's C operand
 };
 
-template <int OUT, bool SLOPE, bool ROWBIAS>
-__device__ __forceinline__ void epi_tile(const EpiTile &t, const EpiParams &ep, void *out) {
-    constexpr int esz = OUT == FPCC_OUT_I8 ? 1 : (OUT == FPCC_OUT_I16 ? 2 : 4);
-    EpiCtx cx;
-    cx.chan = nullptr;
-    cx.slope = t.slope; cx.post = t.post; cx.zp = t.zp; cx.shift = t.shift;
-    cx.half = t.shift > 0 ? (int64_t)1 << (t.shift - 1) : 0; cx.sgn = t.shift > 0;
-    cx.has_post = t.has_post; cx.dbg = t.dbg;
-#if FPCC_EPI_PAIR_STORES
-    cx.optr_pair = nullptr;  // pairing is wired into the per-chunk loop only
-#endif
-    FastCtx fx;
-    fx.slope = t.slope; fx.post = t.post;
-    fx.shift = min(t.shift, 32); fx.shift_hi = max(t.shift - 32, 0);
-    const int64_t c0v = t.zp + cx.half;
-    fx.c0_lo = (uint32_t)c0v; fx.c0_hi = (uint32_t)((uint64_t)c0v >> 32);
-    fx.c_pos = c0v; fx.c_neg = c0v - 1; fx.k24 = (int64_t)t.k24;
-    fx.ovf_add = t.shift > 0 && t.shift <= 31 ? 1u << (t.shift - 1) : 0u;
-    fx.ovf_lim_m1 = t.shift <= 31 ? (1u << t.shift) - 1u : 0xffffffffu;
-    const int64_t row0 = t.row_ok ? t.m * t.N + t.n0 : 0;
-    const int32_t *rb_row = (ROWBIAS && t.row_ok) ? ep.row_bias + (int64_t)__ldg(&ep.row_idx[t.m]) * t.N + t.n0 : nullptr;
-    const int32_t *res_row = ep.residual ? ep.residual + row0 : nullptr;
-    char *orow = (char *)out + row0 * esz;
-    const bool vec = t.out_al && (t.N & 15) == 0;
-    const bool zp0 = t.zp == 0;
-    for (int c0 = t.c_begin; c0 < t.c_end; c0 += EC) {
+__device__ __forceinline__ int lean_mode(const EpiParams &ep, int64_t zp, int64_t kk, int32_t rb_bound, int64_t *vmax_out) {
+    const int shift = ep.shift;
+    if (ep.out_type != FPCC_OUT_I8 && ep.out_type != FPCC_OUT_I32) return SGN_NONE;
+    if (shift < 1 || shift > 62) return SGN_NONE;
+    if (ep.slope) { const int32_t sl = ep.slope[0]; if (sl < 0 || sl > (1 << 25)) return SGN_NONE; }
+    if (ep.post_slope) { const int32_t sl = ep.post_slope[0]; if (sl < 0 || sl > (1 << 25)) return SGN_NONE; }
+    if (ep.row_bias && (rb_bound <= 0 || ((uintptr_t)ep.row_bias & 15) != 0)) return SGN_NONE;
+    if (ep.residual && ((uintptr_t)ep.residual & 15) != 0) return SGN_NONE;
+    const int64_t vmax = kk * 16256 + ((int64_t)1 << 29) + (ep.row_bias ? (int64_t)rb_bound : 0);
+    if (vmax > 2147483646ll) return SGN_NONE;
+    *vmax_out = vmax;
+    if (zp == 0) return shift <= 32 ? SGN_LO0 : SGN_HI0;
+    if (zp > ((int64_t)1 << 60) || zp < -((int64_t)1 << 60)) return SGN_NONE;
+    const int64_t c0 = zp + ((int64_t)1 << (shift - 1));
+    if ((uint32_t)c0 == 0u) return SGN_NONE;
+    return shift < 32 ? SGN_THR_LO : SGN_THR_HI;
+}
+
+// Stages (bias, mul, thr) of one channel; returns false when the channel cannot take the lean path.
+__device__ __forceinline__ bool stage_channel(int32_t bias, uint32_t mul, int64_t zp, int shift, int out_type, int64_t vmax, int4 *ch) {
+    bool ok = mul < (1u << 31) && bias <= (1 << 29) && bias >= -(1 << 29);
+    if (out_type == FPCC_OUT_I8 || shift >= 32) {  // the shifted value must fit 32 bits (int32 outputs with shift < 32 test per element)
+        const int64_t azp = zp < 0 ? -zp : zp;
+        const int64_t top = vmax * (int64_t)(mul & 0x7fffffffu) + azp + ((int64_t)1 << (shift - (shift > 0)));
+        ok = ok && (top >> shift) < 2147483647ll;
+    }
+    int64_t t;
+    if (mul == 0) t = zp < 0 ? 2147483647ll : -2147483648ll;
+    else { const int64_t nz = -zp, m = (int64_t)mul; t = nz >= 0 ? (nz + m - 1) / m : -((-nz) / m); }
+    t = t > 2147483647ll ? 2147483647ll : (t < -2147483648ll ? -2147483648ll : t);
+    *ch = make_int4(bias, (int32_t)mul, (int32_t)t, 0);
+    return ok;
+}
+
+template <int OUT, bool SLOPE, int SGN>
+__device__ __forceinline__ bool lean_chunk(const uint32_t (&acc)[EC], uint32_t chan_addr, const LeanU &u, int32_t (&o)[EC]) {
+    bool bad = false;
+#pragma unroll
+    for (int q = 0; q < EC; ++q) {
+        const int4 ch = lds128(chan_addr + q * 16);
+        int32_t v = (int32_t)acc[q] + ch.x;
+        if (SLOPE) v = prelu_unit(v, u.slope, u.k24);
+        int64_t add;
+        if (SGN == SGN_LO0) {
+            add = (int64_t)(uint64_t)(u.c0_lo + (uint32_t)(v >> 31));
+        } else if (SGN == SGN_HI0) {
+            const uint32_t sx = (uint32_t)(v >> 31);
+            add = pack64(sx, u.c0_hi + sx);
+        } else {
+            add = pack64(v < ch.z ? u.c0_lo - 1u : u.c0_lo, u.c0_hi);
+        }
+        const int64_t t = mad_wide(v, ch.y, add);
+        const uint32_t lo = (uint32_t)t, hi = (uint32_t)((uint64_t)t >> 32);
+        int32_t r;
+        if (SGN == SGN_LO0 || SGN == SGN_THR_LO) {
+            r = (int32_t)__funnelshift_rc(lo, hi, u.shift);
+            if (OUT == FPCC_OUT_I32) bad |= hi + u.ovf_add > u.ovf_lim;
+        } else {
+            r = (int32_t)hi >> (u.shift - 32);
+        }
+        o[q] = r;  // I8: saturated by the packing conversion
+    }
+    return !bad;
+}
+
+struct LeanTile {
+    uint32_t tacc;              // TMEM address of this warp's lane quarter, column 0 of the tile
+    uint32_t chan_addr;         // shared-space address of the staged channel constants of column 0
+    int c_begin, c_end, ncols;  // this warp's columns; valid columns of the tile (N - n0)
+    bool have_acc, row_ok;
+    char *orow;                 // output row (column n0), NULL rows are not stored
+    char *orow_pair;            // int32 outputs: the lane ^ 1 partner's output row when the whole warp has rows, else NULL
+    const int32_t *rb_row;      // occupancy bias row (column n0) or NULL
+    const int32_t *res_row;     // residual row (column n0) or NULL
+    bool has_post;
+};
+
+__device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t &r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Exact recomputation of one chunk, one column at a time straight from TMEM (rare: an int32 output saturated).
+// Executed by the whole warp (tcgen05.ld is warp-collective); rows without an output skip the store.
+template <int OUT, bool SLOPE>
+__device__ __forceinline__ void lean_redo_chunk(const LeanTile &lt, const LeanU &u, int c0, int64_t zp) {
+    const int64_t half = (int64_t)1 << (u.shift - 1);
+#pragma unroll 1
+    for (int q = 0; q < EC; ++q) {
+        uint32_t a = 0;
+        __syncwarp();  // tcgen05.ld is .sync.aligned: the lanes that skipped the previous column's store rejoin here
+        if (lt.have_acc) tmem_ld1(lt.tacc + (uint32_t)(c0 + q), a);
+        if (lt.row_ok) {
+            const int4 ch = lds128(lt.chan_addr + (uint32_t)(c0 + q) * 16);
+            int32_t a32 = (int32_t)a;
+            if (lt.rb_row) a32 = (int32_t)((uint32_t)a32 + (uint32_t)__ldg(lt.rb_row + c0 + q));
+            int32_t r = epi_exact<OUT>(a32, ch.x, (uint32_t)ch.y, SLOPE, u.slope, zp, half, 1, u.shift);
+            if (OUT == FPCC_OUT_I32) {
+                if (lt.res_row) {
+                    r = (int32_t)((uint32_t)r + (uint32_t)__ldg(lt.res_row + c0 + q));
+                    if (lt.has_post) r = sat_s32(prelu_q25((int64_t)r, u.post));
+                }
+                ((int32_t *)lt.orow)[c0 + q] = r;
+            } else {
+                ((int8_t *)lt.orow)[c0 + q] = (int8_t)r;
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// All chunks of one tile row.  The case (output type, PReLU, sign mode) is chosen once per tile by the caller; row
+// pointers and constants are formed once.  Requires 16-byte aligned rows and N % 16 == 0 (whole chunks).
+template <int OUT, bool SLOPE, int SGN>
+__device__ __forceinline__ void lean_tile(const LeanTile &lt, const LeanU &u, int64_t zp) {
+    constexpr int esz = OUT == FPCC_OUT_I8 ? 1 : 4;
+    for (int c0 = lt.c_begin; c0 < lt.c_end; c0 += EC) {
         uint32_t acc[EC];
-        if (t.have_acc) {
-            tmem_ld16(t.tacc + (uint32_t)c0, acc);  // .sync.aligned: every lane, also those without a row
+        __syncwarp();  // lanes without an output row skipped the previous chunk's stores
+        if (lt.have_acc) {
+            tmem_ld16(lt.tacc + (uint32_t)c0, acc);  // .sync.aligned: every lane, also those without a row
         } else {
 #pragma unroll
             for (int q = 0; q < EC; ++q) acc[q] = 0;
         }
-        const int nb = t.n0 + c0;
-        if (!t.row_ok || nb >= t.N) continue;
-        if (t.dbg & 4) { if (c0 == 0) ((int32_t *)out)[t.m] = (int32_t)acc[0]; continue; }
-        cx.chan4 = t.chan4_s + c0;
-        cx.row_bias = ROWBIAS ? rb_row + c0 : nullptr;
-        cx.residual = res_row ? res_row + c0 : nullptr;
-        cx.nvalid = min(EC, t.N - nb);
-        fx.chan = smem_u32(t.chan4_s + c0); fx.thr = smem_u32(t.thr_s + c0);
-        epi_one<OUT, SLOPE, ROWBIAS>(acc, cx, fx, orow + c0 * esz, vec, t.fast, zp0);
+        if (c0 >= lt.ncols) continue;  // warp-uniform
+        if (lt.rb_row) {               // warp-uniform; every lane has its own table row
+            const int4 *rp = reinterpret_cast<const int4 *>(lt.rb_row + c0);
+#pragma unroll
+            for (int t = 0; t < EC / 4; ++t) {
+                const int4 rv = lt.row_ok ? __ldg(rp + t) : make_int4(0, 0, 0, 0);
+                acc[4 * t] += (uint32_t)rv.x; acc[4 * t + 1] += (uint32_t)rv.y; acc[4 * t + 2] += (uint32_t)rv.z; acc[4 * t + 3] += (uint32_t)rv.w;
+            }
+        }
+        int32_t o[EC];
+        const bool good = lean_chunk<OUT, SLOPE, SGN>(acc, lt.chan_addr + (uint32_t)c0 * 16, u, o);
+        if (OUT == FPCC_OUT_I32 && (SGN == SGN_LO0 || SGN == SGN_THR_LO)) {
+            if (__any_sync(0xffffffffu, !good)) {  // warp-uniform, rare
+                lean_redo_chunk<OUT, SLOPE>(lt, u, c0, zp);
+                continue;
+            }
+        }
+        if (!lt.row_ok && !(OUT == FPCC_OUT_I32 && lt.orow_pair)) continue;
+        if (OUT == FPCC_OUT_I32) {
+            if (lt.res_row) {
+                const int4 *rp = reinterpret_cast<const int4 *>(lt.res_row + c0);
+#pragma unroll
+                for (int t = 0; t < EC / 4; ++t) {
+                    const int4 rv = __ldg(rp + t);
+                    o[4 * t] = (int32_t)((uint32_t)o[4 * t] + (uint32_t)rv.x);  // int32 add wraps
+                    o[4 * t + 1] = (int32_t)((uint32_t)o[4 * t + 1] + (uint32_t)rv.y);
+                    o[4 * t + 2] = (int32_t)((uint32_t)o[4 * t + 2] + (uint32_t)rv.z);
+                    o[4 * t + 3] = (int32_t)((uint32_t)o[4 * t + 3] + (uint32_t)rv.w);
+                }
+                if (lt.has_post) {
+#pragma unroll
+                    for (int q = 0; q < EC; ++q) o[q] = prelu_unit(o[q], u.post, u.k24);
+                }
+            }
+            if (lt.orow_pair) {
+                // Row-per-lane STG.128 touches 32 HALF sectors per instruction (SM->L2 write bytes = 2x the output).  Lane
+                // pairs swap two of their four 16-byte pieces so that every STG.128 writes whole 32-byte sectors:
+                // even lanes send pieces 1 and 3, odd lanes pieces 0 and 2.
+                const bool odd = (threadIdx.x & 1) != 0;
+                uint4 rcv[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int qs = 4 * (2 * h);  // first word of piece 2h
+                    rcv[h].x = __shfl_xor_sync(0xffffffffu, (uint32_t)(odd ? o[qs] : o[qs + 4]), 1);
+                    rcv[h].y = __shfl_xor_sync(0xffffffffu, (uint32_t)(odd ? o[qs + 1] : o[qs + 5]), 1);
+                    rcv[h].z = __shfl_xor_sync(0xffffffffu, (uint32_t)(odd ? o[qs + 2] : o[qs + 6]), 1);
+                    rcv[h].w = __shfl_xor_sync(0xffffffffu, (uint32_t)(odd ? o[qs + 3] : o[qs + 7]), 1);
+                }
+                // stores 1 / 3: the EVEN lane's row (bytes 0-31 / 32-63 of the chunk), stores 2 / 4: the ODD lane's row
+                char *pa = (odd ? lt.orow_pair : lt.orow) + (size_t)c0 * esz + (odd ? 16 : 0);
+                char *pb = (odd ? lt.orow : lt.orow_pair) + (size_t)c0 * esz + (odd ? 16 : 0);
+                const uint4 own0 = odd ? make_uint4((uint32_t)o[4], (uint32_t)o[5], (uint32_t)o[6], (uint32_t)o[7])
+                                       : make_uint4((uint32_t)o[0], (uint32_t)o[1], (uint32_t)o[2], (uint32_t)o[3]);
+                const uint4 own1 = odd ? make_uint4((uint32_t)o[12], (uint32_t)o[13], (uint32_t)o[14], (uint32_t)o[15])
+                                       : make_uint4((uint32_t)o[8], (uint32_t)o[9], (uint32_t)o[10], (uint32_t)o[11]);
+                *reinterpret_cast<uint4 *>(pa) = odd ? rcv[0] : own0;
+                *reinterpret_cast<uint4 *>(pb) = odd ? own0 : rcv[0];
+                *reinterpret_cast<uint4 *>(pa + 32) = odd ? rcv[1] : own1;
+                *reinterpret_cast<uint4 *>(pb + 32) = odd ? own1 : rcv[1];
+            } else {
+                uint4 *op = reinterpret_cast<uint4 *>(lt.orow + (size_t)c0 * esz);
+#pragma unroll
+                for (int t = 0; t < EC / 4; ++t) op[t] = make_uint4((uint32_t)o[4 * t], (uint32_t)o[4 * t + 1], (uint32_t)o[4 * t + 2], (uint32_t)o[4 * t + 3]);
+            }
+        } else {
+            uint32_t w[EC / 4];
+#pragma unroll
+            for (int t = 0; t < EC / 4; ++t) {
+                const int q = t * 4;
+                uint32_t up;  // saturating pack: d = c[15:0] << 16 | sat8(a) << 8 | sat8(b)
+                asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(up) : "r"(o[q + 3]), "r"(o[q + 2]), "r"(0));
+                asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(w[t]) : "r"(o[q + 1]), "r"(o[q]), "r"(up));
+            }
+            *reinterpret_cast<uint4 *>(lt.orow + (size_t)c0 * esz) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
     }
 }
 
-template <int OUT>
-__device__ __forceinline__ void epi_tile_dispatch(const EpiTile &t, const EpiParams &ep, void *out, bool slope, bool rb) {
-    if (slope) {
-        if (rb) epi_tile<OUT, true, true>(t, ep, out);
-        else epi_tile<OUT, true, false>(t, ep, out);
-    } else {
-        if (rb) epi_tile<OUT, false, true>(t, ep, out);
-        else epi_tile<OUT, false, false>(t, ep, out);
-    }
+template <int OUT, bool SLOPE>
+__device__ __forceinline__ void lean_tile_sgn(const LeanTile &lt, const LeanU &u, int64_t zp, int sgn) {
+    if (sgn == SGN_HI0) lean_tile<OUT, SLOPE, SGN_HI0>(lt, u, zp);
+    else if (sgn == SGN_LO0) lean_tile<OUT, SLOPE, SGN_LO0>(lt, u, zp);
+    else if (sgn == SGN_THR_HI) lean_tile<OUT, SLOPE, SGN_THR_HI>(lt, u, zp);
+    else lean_tile<OUT, SLOPE, SGN_THR_LO>(lt, u, zp);
 }
-#endif
 
 // ---- floating-point epilogue (kind::f16 path): v = acc + bias; act; [+ residual; post act]; cast -------------
 // act codes: 0 none, 1 relu, 2 leaky-relu / PReLU with one slope.  out_type: 0 fp16, 1 bf16, 2 fp32.
@@ -637,13 +651,13 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
     int32_t *rows_s = (int32_t *)(sB + (size_t)STAGES * b_bytes);  // [2 slots][rows_k][128]
     int4 *chan4_s = (int4 *)(rows_s + 2 * rows_k * TC_M);         // [n_tile] (bias, mul, B, -B) of the current channel block
     int2 *chan_s = (int2 *)chan4_s;                               // float kinds: (bias bits, 0)
-    int32_t *thr_s = (int32_t *)(chan4_s + a.n_tile);             // [n_tile] sign threshold of the fast epilogue
+    int32_t *thr_s = (int32_t *)(chan4_s + a.n_tile);             // [n_tile] spare; words 0-1 hold the PReLU rounding addend (LeanU::k24)
     uint64_t *bars = (uint64_t *)(thr_s + a.n_tile);
     uint64_t *full = bars, *empty = bars + STAGES;
     uint64_t *meta_full = bars + 2 * STAGES, *tmem_full = meta_full + 2, *tmem_empty = tmem_full + 2;
     PMeta *meta = (PMeta *)(tmem_empty + 2);
     uint32_t *tmem_ptr = (uint32_t *)(meta + 2);
-    uint32_t *fast_off = tmem_ptr + 1;  // set once a staged channel block fails the fast-epilogue preconditions
+    uint32_t *lean_off = tmem_ptr + 1;  // set once a staged channel block fails the lean-epilogue preconditions
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_chunks = (a.K + TC_KB - 1) / TC_KB;
@@ -669,15 +683,16 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
     // per-channel epilogue constants of a single channel block are staged once (grouped weights reload per tile)
     const bool chan_static = tiles_n == 1 && !(MODE == 1 && a.bias_per_group);
     const int64_t zp_all = KIND == 0 ? ep.zp[0] : 0;
-    const bool fast_uni = KIND == 0 && !(a.dbg & 16) && fast_uniform_ok(ep, ep.out_type, zp_all, (int64_t)a.K * (MODE == 0 ? a.kvol : 1));
-    if (tid == 0) *fast_off = fast_uni ? 0u : 1u;
+    int64_t vmax = 0;
+    const int sgn_mode = KIND == 0 ? lean_mode(ep, zp_all, (int64_t)a.K * (MODE == 0 ? a.kvol : 1), ep.row_bias_bound, &vmax) : SGN_NONE;
+    if (tid == 0) { *lean_off = sgn_mode != SGN_NONE ? 0u : 1u; thr_s[0] = (1 << 24) - 1; thr_s[1] = 0; }
     __syncthreads();
     if (chan_static)
         for (int c = tid; c < a.n_tile; c += P_THREADS) {
             if (KIND == 0) {
                 const int32_t b = c < a.N && ep.bias ? ep.bias[c] : 0;
                 const uint32_t mu = c < a.N ? ep.mul[ep.mul_is_scalar ? 0 : c] : 0u;
-                if (!fast_channel(b, mu, zp_all, ep.shift, ep.out_type, &chan4_s[c], &thr_s[c]) && fast_uni) atomicOr(fast_off, 1u);
+                if (!stage_channel(b, mu, zp_all, ep.shift, ep.out_type, vmax, &chan4_s[c]) && sgn_mode != SGN_NONE) atomicOr(lean_off, 1u);
             } else {
                 chan_s[c] = make_int2(c < a.N && fe.bias ? __float_as_int(fe.bias[c]) : 0, 0);
             }
@@ -771,7 +786,7 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
                 const int piece = lane & 7;
                 const bool k_ok = kc * TC_KB + piece * 16 < a.K;
                 const uint32_t dst0 = smem_u32(sA + stage * a_bytes);
-                if (!(a.dbg & 1)) {
+                {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int32_t src = srcs[i];
@@ -791,7 +806,7 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
                     const uint32_t rk = smem_u32(rows + (MODE == 0 ? k : 0) * TC_M + base);
                     const int4 s0 = lds128(rk), s1 = lds128(rk + 16);
                     const int32_t srcs[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-                    if (!(a.dbg & 1)) {
+                    {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int32_t src = srcs[i];
@@ -824,7 +839,6 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
                     if (++kc == n_chunks) { kc = 0; k = __ffs(rem) - 1; rem &= rem - 1; }
                     const int stage = it % STAGES;
                     mbar_wait(&empty[stage], ((it / STAGES) & 1) ^ 1);
-                    if (a.dbg & 2) { mbar_arrive(&full[stage]); continue; }
                     mbar_expect_tx(&full[stage], (uint32_t)b_bytes);
                     const int wrow = (MODE == 0 ? k : group) * a.N + n0;
                     tma_load_2d(smem_u32(sB + (size_t)stage * b_bytes), &tmap_w, &full[stage], kc * TC_KB, wrow);
@@ -850,7 +864,7 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
                     tc_fence_after();
                     const uint64_t ad = umma_desc_sw128(smem_u32(sA + stage * a_bytes));
                     const uint64_t bd = umma_desc_sw128(smem_u32(sB + (size_t)stage * b_bytes));
-                    if (!(a.dbg & 8)) {
+                    {
 #pragma unroll
                         for (int q = 0; q < TC_KB / 32; ++q) {  // 32 bytes of K per instruction for both kinds
                             if (KIND == 0) umma_i8(tacc, ad + 2 * q, bd + 2 * q, idesc, (uint32_t)(i > 0 || q > 0));
@@ -874,6 +888,14 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
         const int cols_grp = (((a.n_tile + P_EPI_WARPS / 4 - 1) / (P_EPI_WARPS / 4) + EC - 1) / EC) * EC;  // columns per group, multiple of EC
         const int c_begin = min(a.n_tile, group * cols_grp), c_end = min(a.n_tile, c_begin + cols_grp);
         const bool out_al = ((uintptr_t)out & 15) == 0;
+        LeanU lu;
+        {
+            const int64_t c0v = zp + (shift > 0 ? (int64_t)1 << (shift - 1) : 0);
+            lu.slope = slope; lu.post = post; lu.shift = shift; { const uint32_t ka = smem_u32(thr_s); int32_t k_lo, k_hi; asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(k_lo), "=r"(k_hi) : "r"(ka)); lu.k24 = pack64((uint32_t)k_lo, (uint32_t)k_hi); }
+            lu.c0_lo = (uint32_t)c0v; lu.c0_hi = (uint32_t)((uint64_t)c0v >> 32);
+            lu.ovf_add = shift > 0 && shift <= 31 ? 1u << (shift - 1) : 0u;
+            lu.ovf_lim = shift <= 31 ? (1u << shift) - 1u : 0xffffffffu;
+        }
         int j = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
             const int slot = j & 1;
@@ -889,39 +911,46 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
                     if (KIND == 0) {
                         const int32_t b = ep.bias ? __ldg(&ep.bias[pc]) : 0;
                         const uint32_t mu = __ldg(&ep.mul[ep.mul_is_scalar ? 0 : pc]);
-                        if (!fast_channel(b, mu, zp_all, ep.shift, ep.out_type, &chan4_s[t], &thr_s[t]) && fast_uni) atomicOr(fast_off, 1u);
+                        if (!stage_channel(b, mu, zp_all, ep.shift, ep.out_type, vmax, &chan4_s[t]) && sgn_mode != SGN_NONE) atomicOr(lean_off, 1u);
                     } else {
                         chan_s[t] = make_int2(fe.bias ? __float_as_int(__ldg(&fe.bias[pc])) : 0, 0);
                     }
                 }
                 asm volatile("bar.sync 2, %0;" ::"n"(P_EPI_WARPS * 32) : "memory");
             }
-            const bool fast = KIND == 0 && *(volatile uint32_t *)fast_off == 0u;
             const int32_t *rows = rows_s + slot * rows_k * TC_M;
             const int64_t mt = (int64_t)tile_m * TC_M + r;  // MODE 0: column of the neighbour table
             const bool row_ok = MODE == 0 ? (mt < a.n_out) : (rows[TC_M + r] >= 0);
             const int64_t m = MODE == 0 ? ((a.row_perm && row_ok) ? (int64_t)__ldg(&a.row_perm[mt]) : mt) : (int64_t)rows[TC_M + r];
-#if FPCC_EPI_PAIR_STORES
-            const bool pair_ok = KIND == 0 && ep.out_type == FPCC_OUT_I32 && out_al && (a.N & 15) == 0 && __all_sync(0xffffffffu, row_ok);
-            const int64_t m_pair = __shfl_xor_sync(0xffffffffu, m, 1);
-#endif
             mbar_wait(&tmem_full[slot], (j >> 1) & 1);
             tc_fence_after();
             const uint32_t tacc = tmem_base + (uint32_t)(slot * a.tmem_cols) + ((uint32_t)(quarter * 32) << 16);
-#if FPCC_EPI_TILE_DISPATCH
-            if (KIND == 0) {
-                EpiTile et;
-                et.tacc = tacc; et.c_begin = c_begin; et.c_end = c_end; et.n0 = n0; et.N = a.N; et.dbg = a.dbg; et.shift = shift;
-                et.k24 = a.k24; et.have_acc = have_acc; et.row_ok = row_ok; et.has_post = has_post; et.fast = fast; et.out_al = out_al;
-                et.m = m; et.zp = zp; et.slope = slope; et.post = post; et.chan4_s = chan4_s; et.thr_s = thr_s;
-                const bool rb = ep.row_bias != nullptr;
-                if (ep.out_type == FPCC_OUT_I8) epi_tile_dispatch<FPCC_OUT_I8>(et, ep, out, has_slope, rb);
-                else if (ep.out_type == FPCC_OUT_I32) epi_tile_dispatch<FPCC_OUT_I32>(et, ep, out, has_slope, rb);
-                else epi_tile_dispatch<FPCC_OUT_I16>(et, ep, out, has_slope, rb);
+            const bool lean = KIND == 0 && out_al && (a.N & 15) == 0 && *(volatile uint32_t *)lean_off == 0u;
+            if (KIND == 0 && lean) {
+                LeanTile lt;
+                lt.tacc = tacc; lt.chan_addr = smem_u32(chan4_s); lt.c_begin = c_begin; lt.c_end = c_end; lt.ncols = a.N - n0;
+                lt.have_acc = have_acc; lt.row_ok = row_ok; lt.has_post = has_post;
+                const int64_t row0 = row_ok ? m * a.N + n0 : 0;
+                lt.orow = (char *)out + row0 * (ep.out_type == FPCC_OUT_I8 ? 1 : 4);
+                lt.orow_pair = nullptr;
+                if (ep.out_type == FPCC_OUT_I32) {  // warp-uniform: pair stores need a row in every lane
+                    const unsigned long long mine = (unsigned long long)(uintptr_t)lt.orow;
+                    const unsigned long long other = __shfl_xor_sync(0xffffffffu, mine, 1);
+                    if (__all_sync(0xffffffffu, row_ok)) lt.orow_pair = (char *)(uintptr_t)other;
+                }
+                lt.rb_row = ep.row_bias ? ep.row_bias + (row_ok ? (int64_t)__ldg(&ep.row_idx[m]) * a.N + n0 : 0) : nullptr;
+                lt.res_row = ep.residual ? ep.residual + row0 : nullptr;
+                if (ep.out_type == FPCC_OUT_I8) {
+                    if (has_slope) lean_tile_sgn<FPCC_OUT_I8, true>(lt, lu, zp, sgn_mode);
+                    else lean_tile_sgn<FPCC_OUT_I8, false>(lt, lu, zp, sgn_mode);
+                } else {
+                    if (has_slope) lean_tile_sgn<FPCC_OUT_I32, true>(lt, lu, zp, sgn_mode);
+                    else lean_tile_sgn<FPCC_OUT_I32, false>(lt, lu, zp, sgn_mode);
+                }
             } else
-#endif
             for (int c0 = c_begin; c0 < c_end; c0 += EC) {
                 uint32_t acc[EC];
+                __syncwarp();
                 if (have_acc) {
                     tmem_ld16(tacc + (uint32_t)c0, acc);
                 } else {
@@ -930,7 +959,6 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
                 }
                 const int nb = n0 + c0;
                 if (!row_ok || nb >= a.N) continue;
-                if (a.dbg & 4) { if (c0 == 0) ((int32_t *)out)[m] = (int32_t)acc[0]; continue; }
                 if (KIND != 0) {
                     const int esz = fe.out_type == 2 ? 4 : 2;
                     const int nvalid = min(EC, a.N - nb);
@@ -940,30 +968,19 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
                     continue;
                 }
                 EpiCtx cx;
-                cx.chan = nullptr; cx.chan4 = chan4_s + c0;
+                cx.chan4 = chan4_s + c0;
                 cx.slope = slope; cx.post = post; cx.zp = zp; cx.shift = shift;
                 cx.half = shift > 0 ? (int64_t)1 << (shift - 1) : 0; cx.sgn = shift > 0;
                 cx.row_bias = ep.row_bias ? ep.row_bias + (int64_t)__ldg(&ep.row_idx[m]) * a.N + nb : nullptr;
                 cx.residual = ep.residual ? ep.residual + m * a.N + nb : nullptr;
-                cx.has_post = has_post; cx.dbg = a.dbg;
+                cx.has_post = has_post;
                 cx.nvalid = min(EC, a.N - nb);
-#if FPCC_EPI_PAIR_STORES
-                cx.optr_pair = (pair_ok && cx.nvalid == EC) ? (char *)out + (m_pair * a.N + nb) * 4 : nullptr;
-#endif
-                FastCtx fx;
-                fx.chan = smem_u32(chan4_s + c0); fx.thr = smem_u32(thr_s + c0); fx.slope = slope; fx.post = post;
-                fx.shift = min(shift, 32); fx.shift_hi = max(shift - 32, 0);
-                const int64_t c0v = zp + cx.half;
-                fx.c0_lo = (uint32_t)c0v; fx.c0_hi = (uint32_t)((uint64_t)c0v >> 32);
-                fx.c_pos = c0v; fx.c_neg = c0v - 1; fx.k24 = (int64_t)a.k24;
-                fx.ovf_add = shift > 0 && shift <= 31 ? 1u << (shift - 1) : 0u;
-                fx.ovf_lim_m1 = shift <= 31 ? (1u << shift) - 1u : 0xffffffffu;
                 void *optr = (char *)out + (m * a.N + nb) * (ep.out_type == FPCC_OUT_I8 ? 1 : (ep.out_type == FPCC_OUT_I16 ? 2 : 4));
                 const bool vec = out_al && (a.N & 15) == 0;
                 const bool rb = ep.row_bias != nullptr;
-                if (ep.out_type == FPCC_OUT_I8) epi_dispatch<FPCC_OUT_I8>(acc, cx, fx, optr, vec, has_slope, rb, fast, zp == 0);
-                else if (ep.out_type == FPCC_OUT_I32) epi_dispatch<FPCC_OUT_I32>(acc, cx, fx, optr, vec, has_slope, rb, fast, zp == 0);
-                else epi_dispatch<FPCC_OUT_I16>(acc, cx, fx, optr, vec, has_slope, rb, fast, zp == 0);
+                if (ep.out_type == FPCC_OUT_I8) epi_dispatch<FPCC_OUT_I8>(acc, cx, optr, vec, has_slope, rb);
+                else if (ep.out_type == FPCC_OUT_I32) epi_dispatch<FPCC_OUT_I32>(acc, cx, optr, vec, has_slope, rb);
+                else epi_dispatch<FPCC_OUT_I16>(acc, cx, optr, vec, has_slope, rb);
             }
             tc_fence_before();
             __syncwarp();
@@ -1105,12 +1122,6 @@ template <int MODE, int KIND>
 static int launch_tc(TcArgs &a, const void *W, int64_t w_rows, int tiles_m, const EpiParams &ep, const FEpi &fe, void *out,
                      cudaStream_t s) {
     int n_blocks_n = pick_tile(a.N, &a.n_tile, &a.tmem_cols);
-#ifdef FPCC_TC_DEBUG  // experiment builds only (build.build_variant(..., ['-DFPCC_TC_DEBUG'])): a release library ignores the variable
-    { const char *e = getenv("FPCC_TC_DEBUG"); a.dbg = e ? atoi(e) : 0; }
-#else
-    a.dbg = 0;
-#endif
-    a.k24 = (1 << 24) - 1;
     CUtensorMap tmap;
     int rc = weight_tensor_map((const int8_t *)W, w_rows, a.K, a.n_tile, &tmap);
     if (rc) return rc;

@@ -531,10 +531,10 @@ class LinearIn8W8(_AffineIn8):
             pat = ((torch.arange(256, device=w.device)[:, None] >> torch.arange(7, -1, -1, device=w.device)[None]) & 1).double()
             q = pat * float(q1) + (1.0 - pat) * float(q0)                       # [256, 8]
             table = (q @ w[:, C:].double().T).round().to(torch.int32).contiguous()  # exact: |values| < 2^53
-            return w[:, :C].contiguous(), table
+            return w[:, :C].contiguous(), table, int(table.abs().max().item())
 
-        _, w_main, table = _cached(self, '_bits_cache', key, make)
-        return ops.linear(input, w_main, self.epilogue(True, row_bias=(table, occ)))
+        _, w_main, table, bound = _cached(self, '_bits_cache', key, make)
+        return ops.linear(input, w_main, self.epilogue(True, row_bias=(table, occ, bound)))
 
 
 class LinearIn8W8Out8(LinearIn8W8):

@@ -124,9 +124,10 @@ def make_epilogue(requant_mul, zero_point, shift, out_type, bias=None, slope=Non
     e.residual = _p(_need(residual, torch.int32, 'residual')) if residual is not None else None
     e.post_slope = _p(_need(post_slope, torch.int32, 'post_slope')) if post_slope is not None else None
     if row_bias is not None:
-        table, idx = row_bias
+        table, idx = row_bias[:2]
         e.row_bias = _p(_need(table, torch.int32, 'row_bias table', 2))
         e.row_idx = _p(_need(idx, torch.uint8, 'row_bias index', 1))
+        e.row_bias_bound = int(row_bias[2]) if len(row_bias) > 2 else 0  # max |table entry| when the caller knows it
     e._keep = (bias, slope, requant_mul, zero_point, residual, post_slope, row_bias)
     return e
 

@@ -213,6 +213,8 @@ typedef struct {
     const int32_t *post_slope;   /* device [1] Q6.25 or NULL                        */
     const int32_t *row_bias;     /* fused kernels: [256, ch] table or NULL: v += row_bias[row_idx[row]][ch] */
     const uint8_t *row_idx;      /* [rows] table row of every output row            */
+    int32_t row_bias_bound;      /* max |entry| of the row_bias table if the caller knows it, else 0: lets the fused
+                                  * kernels prove that acc + row_bias + bias stays inside int32 (32-bit epilogue)  */
 } fpcc_epilogue;
 
 /* replaces the 12 requant entry points of binding.cu:118-129 */

@@ -1,5 +1,5 @@
 """Micro-benchmark of the fused sparse-conv / linear kernels on one LiDAR pyramid level (also the ncu target).
-usage: python tests/bench_conv.py [stride_log2=4] [channels=256] [frames=1]"""
+usage: python tools/bench_conv.py [stride_log2=4] [channels=256] [frames=1]"""
 import sys
 import os.path as osp
 import numpy as np
@@ -43,21 +43,39 @@ def t(fn, reps=5):
     return e0.elapsed_time(e1) / reps
 
 
-import os
 alg = 2.0 * pairs * ch * ch
 mma = 2.0 * ((n + 127) // 128 * 128) * 27 * ch * ch
 w2 = torch.from_numpy(rng.integers(-127, 128, (ch, ch)).astype(np.int8)).cuda()
-for dbg in (sys.argv[4].split(',') if len(sys.argv) > 4 else ['0']):
-    os.environ['FPCC_TC_DEBUG'] = dbg  # experiment knobs of igemm_tc.cu (0 = the real kernel)
-    ms = t(lambda: ops.spconv(f, w, table, ep))
-    print(f'[dbg {dbg}] conv  stride 2^{lvl} n={n} C={ch} pairs/pt={pairs / n:.2f}: {ms:.3f} ms  algorithmic {alg / ms / 1e9:.1f} TOP/s  executed {mma / ms / 1e9:.1f} TOP/s')
-    ms = t(lambda: ops.linear(f, w2, ep))
-    print(f'[dbg {dbg}] linear n={n} {ch}->{ch}: {ms:.3f} ms  {2.0 * n * ch * ch / ms / 1e9:.1f} TOP/s')
-    ms = t(lambda: ops.linear(f, w2, ep32))
-    print(f'[dbg {dbg}] linear int32 out n={n} {ch}->{ch}: {ms:.3f} ms  {2.0 * n * ch * ch / ms / 1e9:.1f} TOP/s  {n * ch * 5 / ms / 1e6:.0f} GB/s')
-    ms = t(lambda: ops.linear(f, w2, ep32r))
-    print(f'[dbg {dbg}] linear int32 out (shift 37, converted-model regime) n={n} {ch}->{ch}: {ms:.3f} ms  {2.0 * n * ch * ch / ms / 1e9:.1f} TOP/s  {n * ch * 5 / ms / 1e6:.0f} GB/s')
-os.environ['FPCC_TC_DEBUG'] = '0'
+occ = torch.from_numpy(rng.integers(1, 256, n).astype(np.uint8)).cuda()
+rb_table = torch.from_numpy(rng.integers(-100000, 100000, (256, ch)).astype(np.int32)).cuda()
+res = torch.from_numpy(rng.integers(-(1 << 28), 1 << 28, (n, ch)).astype(np.int32)).cuda()
+# regimes of a PTQ-converted model (fastpcc_b200/synth.py): int8-producing layers shift 28..39, int32 (Q8.23) producing
+# layers shift - 23 = 5..16, multipliers just below 2^(32 - guard bits)
+mul_hi = torch.from_numpy(rng.integers(1 << 29, 1 << 30, ch).astype(np.int64)).to(torch.uint32).cuda()
+mul_lo = torch.from_numpy(rng.integers(1 << 20, 1 << 21, ch).astype(np.int64)).to(torch.uint32).cuda()
+cases = {
+    'i8  shift 24 prelu         ': ops.make_epilogue(mul, zp, 24, ops.OUT_I8, bias=bias, slope=slope),
+    'i8  shift 38 prelu         ': ops.make_epilogue(mul_hi, zp, 38, ops.OUT_I8, bias=bias, slope=slope),
+    'i8  shift 38               ': ops.make_epilogue(mul_hi, zp, 38, ops.OUT_I8, bias=bias),
+    'i8  shift 38 prelu rowbias ': ops.make_epilogue(mul_hi, zp, 38, ops.OUT_I8, bias=bias, slope=slope, row_bias=(rb_table, occ, 100000)),
+    'i32 shift 12               ': ops.make_epilogue(mul_lo, zp, 12, ops.OUT_I32, bias=bias),
+    'i32 shift 12 prelu rowbias ': ops.make_epilogue(mul_lo, zp, 12, ops.OUT_I32, bias=bias, slope=slope, row_bias=(rb_table, occ, 100000)),
+    'i32 shift 37 prelu         ': ops.make_epilogue(mul_hi, zp, 37, ops.OUT_I32, bias=bias, slope=slope),
+    'i32 shift 6 (saturating)   ': ops.make_epilogue(mul, zp, 6, ops.OUT_I32, bias=bias, slope=slope),
+}
+ms = t(lambda: ops.spconv(f, w, table, ep))
+print(f'conv  stride 2^{lvl} n={n} C={ch} pairs/pt={pairs / n:.2f}: {ms:.3f} ms  algorithmic {alg / ms / 1e9:.1f} TOP/s  executed {mma / ms / 1e9:.1f} TOP/s')
+for name, e in cases.items():
+    ms = t(lambda: ops.linear(f, w2, e))
+    esz = 1 if e.out_type == ops.OUT_I8 else 4
+    print(f'linear {name} n={n} {ch}->{ch}: {ms:.3f} ms  {2.0 * n * ch * ch / ms / 1e9:7.1f} TOP/s  {n * ch * (1 + esz) / ms / 1e6:6.0f} GB/s')
+tp0, perm0 = ops.group_rows(table)
+epr = ops.make_epilogue(mul_lo, zp, 12, ops.OUT_I32, bias=bias, residual=res, post_slope=slope)
+ms = t(lambda: ops.spconv(f, w, tp0, epr, row_perm=perm0))
+print(f'conv grouped, i32 out + residual + post PReLU (ResBlock conv2): {ms:.3f} ms  algorithmic {alg / ms / 1e9:.1f} TOP/s')
+eph = ops.make_epilogue(mul_hi, zp, 38, ops.OUT_I8, bias=bias, slope=slope)
+ms = t(lambda: ops.spconv(f, w, tp0, eph, row_perm=perm0))
+print(f'conv grouped, i8 out shift 38 prelu (ResBlock conv_prelu): {ms:.3f} ms  algorithmic {alg / ms / 1e9:.1f} TOP/s')
 ms = t(lambda: ops.group_rows(table))
 tp, perm = ops.group_rows(table)
 print(f'group_rows n={n}: {ms:.3f} ms')

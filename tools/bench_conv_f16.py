@@ -1,5 +1,5 @@
 """Micro-benchmark of the fp16/bf16 fused sparse conv on a dense object surface (BASELINE configs[3]-like:
-~800k occupied voxels of a 10-bit surface, C=128, 3x3x3).  usage: python tests/bench_conv_f16.py [n=800000] [channels=128]"""
+~800k occupied voxels of a 10-bit surface, C=128, 3x3x3).  usage: python tools/bench_conv_f16.py [n=800000] [channels=128]"""
 import sys
 import os.path as osp
 import numpy as np

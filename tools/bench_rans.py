@@ -1,5 +1,5 @@
 """Micro-benchmark of the GPU range coder kernels (one or many streams); also the ncu target for them.
-usage: python tests/bench_rans.py [n_symbols] [n_streams]"""
+usage: python tools/bench_rans.py [n_symbols] [n_streams]"""
 import sys
 import os.path as osp
 import numpy as np

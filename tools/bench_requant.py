@@ -1,5 +1,5 @@
 """Micro-benchmark of the layer-to-layer requant (Q8.23 int32 -> scaled int8, optional fused PReLU): GB/s of
-algorithmic traffic (5 B/elem).  usage: PYTHONPATH=. python tests/bench_requant.py [rows] [channels] [prelu=0|1]"""
+algorithmic traffic (5 B/elem).  usage: PYTHONPATH=. python tools/bench_requant.py [rows] [channels] [prelu=0|1]"""
 import sys
 
 import torch

@@ -1,6 +1,6 @@
 """Diagnostic for the open question in DESIGN 3.5 (not collected by pytest): shift 0 with a non-zero zero point and
 non-saturating negatives, through the fused linear epilogue and the stand-alone requant; prints every mismatch with
-got / want instead of asserting.  usage: python tests/diag_shift0.py"""
+got / want instead of asserting.  usage: python tools/diag_shift0.py"""
 import os.path as osp
 import sys
 

@@ -1,4 +1,4 @@
-"""Per-call device times of one compress + decompress batch (diagnostics).  usage: python tests/profile_calls.py [frames=8]"""
+"""Per-call device times of one compress + decompress batch (diagnostics).  usage: python tools/profile_calls.py [frames=8]"""
 import sys
 import os.path as osp
 import torch

@@ -1,5 +1,5 @@
 """Whole-GPU kernel time table (ours + torch's own kernels) of one compress + decompress batch via torch.profiler.
-usage: python tests/profile_torch.py [frames=32]"""
+usage: python tools/profile_torch.py [frames=32]"""
 import sys
 import os.path as osp
 import torch
