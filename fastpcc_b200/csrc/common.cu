@@ -40,6 +40,13 @@ int check_epilogue(const fpcc_epilogue *e, bool allow_residual) {
     }
     FPCC_REQUIRE((e->row_bias == nullptr) == (e->row_idx == nullptr), "epilogue: row_bias and row_idx go together");
     FPCC_REQUIRE(e->row_bias == nullptr || allow_residual, "epilogue: row_bias is only supported by the fused kernels");
+    if (e->post_requant_mul) {
+        FPCC_REQUIRE(allow_residual, "epilogue: the fused second stage is only supported by the fused kernels");
+        FPCC_REQUIRE(e->out_type == FPCC_OUT_I32 && e->post_zero_point != nullptr, "epilogue: second stage needs an int32 first stage and a zero point");
+        FPCC_REQUIRE(e->post_shift >= 0 && e->post_shift < 63, "epilogue: post_shift %d out of range", e->post_shift);
+    } else {
+        FPCC_REQUIRE(e->post_requant_slope == nullptr, "epilogue: post_requant_slope without post_requant_mul");
+    }
     return FPCC_OK;
 }
 

@@ -84,6 +84,10 @@ struct EpiParams {  // device-side copy of fpcc_epilogue with scalars resolved t
     const int32_t *row_bias;
     const uint8_t *row_idx;
     int32_t row_bias_bound;
+    const uint32_t *post_mul;     // fused second stage (fpcc_epilogue::post_requant_mul ...), NULL = off
+    const int64_t *post_zp;
+    int32_t post_shift;
+    const int32_t *post_slope2;
 };
 static inline EpiParams to_params(const fpcc_epilogue *e) {
     EpiParams p;
@@ -91,6 +95,7 @@ static inline EpiParams to_params(const fpcc_epilogue *e) {
     p.shift = e->shift; p.out_type = e->out_type; p.mul_is_scalar = e->mul_is_scalar;
     p.residual = e->residual; p.post_slope = e->post_slope;
     p.row_bias = e->row_bias; p.row_idx = e->row_idx; p.row_bias_bound = e->row_bias_bound;
+    p.post_mul = e->post_requant_mul; p.post_zp = e->post_zero_point; p.post_shift = e->post_shift; p.post_slope2 = e->post_requant_slope;
     return p;
 }
 int check_epilogue(const fpcc_epilogue *e, bool allow_residual);

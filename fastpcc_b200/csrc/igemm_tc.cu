@@ -205,6 +205,31 @@ __device__ __forceinline__ int32_t epi_exact(int32_t a32, int32_t bias, uint32_t
     return OUT == FPCC_OUT_I8 ? sat_s8(r) : (OUT == FPCC_OUT_I16 ? sat_s16(r) : sat_s32(r));
 }
 
+// Second stage, exact: the consumer's PReLUIn32Out32 (prelu.cu:6-21, saturating) + RequantFxpToScaledInt8
+// (requant.cu:7-26) applied to a finished int32 value.
+struct Post2 {
+    bool on, has_slope;
+    int32_t slope;
+    uint32_t mul;
+    int64_t zp;
+    int shift;
+};
+__device__ __forceinline__ Post2 load_post2(const EpiParams &ep) {
+    Post2 p2;
+    p2.on = ep.post_mul != nullptr;
+    p2.has_slope = p2.on && ep.post_slope2 != nullptr;
+    p2.slope = p2.has_slope ? ep.post_slope2[0] : 0;
+    p2.mul = p2.on ? ep.post_mul[0] : 0u;
+    p2.zp = p2.on ? ep.post_zp[0] : 0;
+    p2.shift = p2.on ? ep.post_shift : 0;
+    return p2;
+}
+__device__ __forceinline__ int32_t post2_exact(int32_t y, const Post2 &p2) {
+    int64_t v = (int64_t)y;
+    if (p2.has_slope) v = (int64_t)sat_s32(prelu_q25(v, p2.slope));
+    return sat_s8(rha_shift(v * (int64_t)p2.mul + p2.zp, p2.shift));
+}
+
 template <int OUT, bool SLOPE, bool ROWBIAS>
 __device__ __forceinline__ void epi_chunk(const uint32_t (&acc)[EC], const EpiCtx &cx, int32_t (&o)[EC]) {
 #pragma unroll
@@ -238,7 +263,7 @@ __device__ __forceinline__ int32_t prelu_unit(int32_t v, int32_t slope, int64_t 
 }
 
 template <int OUT>
-__device__ __forceinline__ void epi_store_chunk(int32_t (&o)[EC], const EpiCtx &cx, void *optr, bool vec) {
+__device__ __forceinline__ void epi_store_chunk(int32_t (&o)[EC], const EpiCtx &cx, void *optr, bool vec, const Post2 &p2) {
     if (OUT == FPCC_OUT_I32 && cx.residual) {
         if (vec) {
             const int4 *rp = reinterpret_cast<const int4 *>(cx.residual);
@@ -259,8 +284,12 @@ __device__ __forceinline__ void epi_store_chunk(int32_t (&o)[EC], const EpiCtx &
             for (int q = 0; q < EC; ++q) o[q] = sat_s32(prelu_q25((int64_t)o[q], cx.post));
         }
     }
+    if (OUT == FPCC_OUT_I32 && p2.on) {  // the int32 result feeds the fused second stage; int8 rows are stored
+#pragma unroll
+        for (int q = 0; q < EC; ++q) o[q] = post2_exact(o[q], p2);
+    }
     if (vec) {  // nvalid == EC here (N is a multiple of 16)
-        if (OUT == FPCC_OUT_I8) {
+        if (OUT == FPCC_OUT_I8 || (OUT == FPCC_OUT_I32 && p2.on)) {
             uint32_t w[EC / 4];
 #pragma unroll
             for (int t = 0; t < EC / 4; ++t) {
@@ -285,7 +314,7 @@ __device__ __forceinline__ void epi_store_chunk(int32_t (&o)[EC], const EpiCtx &
 #pragma unroll
         for (int q = 0; q < EC; ++q) {
             if (q < cx.nvalid) {
-                if (OUT == FPCC_OUT_I8) ((int8_t *)optr)[q] = (int8_t)max(min(o[q], 127), -128);
+                if (OUT == FPCC_OUT_I8 || (OUT == FPCC_OUT_I32 && p2.on)) ((int8_t *)optr)[q] = (int8_t)max(min(o[q], 127), -128);
                 else if (OUT == FPCC_OUT_I16) ((int16_t *)optr)[q] = (int16_t)o[q];
                 else ((int32_t *)optr)[q] = o[q];
             }
@@ -294,7 +323,8 @@ __device__ __forceinline__ void epi_store_chunk(int32_t (&o)[EC], const EpiCtx &
 }
 
 template <int OUT>
-__device__ __forceinline__ void epi_dispatch(const uint32_t (&acc)[EC], const EpiCtx &cx, void *optr, bool vec, bool slope, bool rb) {
+__device__ __forceinline__ void epi_dispatch(const uint32_t (&acc)[EC], const EpiCtx &cx, void *optr, bool vec, bool slope, bool rb,
+                                             const Post2 &p2) {
     int32_t o[EC];
     if (slope) {
         if (rb) epi_chunk<OUT, true, true>(acc, cx, o);
@@ -303,7 +333,7 @@ __device__ __forceinline__ void epi_dispatch(const uint32_t (&acc)[EC], const Ep
         if (rb) epi_chunk<OUT, false, true>(acc, cx, o);
         else epi_chunk<OUT, false, false>(acc, cx, o);
     }
-    epi_store_chunk<OUT>(o, cx, optr, vec);
+    epi_store_chunk<OUT>(o, cx, optr, vec, p2);
 }
 
 // ---- lean path --------------------------------------------------------------------------------------------------
@@ -325,6 +355,8 @@ struct LeanU {
     uint32_t c0_lo, c0_hi;
     int shift;
     uint32_t ovf_add, ovf_lim;   // I32, shift < 32: the result fits iff (hi + ovf_add) <= ovf_lim (unsigned)
+    uint32_t post2_addr;         // shared-space address of the staged second-stage constants (POST2 instantiations only):
+                                 // words {mul2, thr2, slope2, shift2 - 32, c02 lo, c02 hi},  c02 = zp2 + 2^(shift2 - 1)
     int64_t k24;                 // 2^24 - 1, read back from shared memory: ptxas splits an immediate or uniform 64-bit addend of
                                  // IMAD.WIDE into IADD3 + IMAD.X; a vector register pair stays the instruction's C operand
 };
@@ -340,6 +372,15 @@ __device__ __forceinline__ int lean_mode(const EpiParams &ep, int64_t zp, int64_
     const int64_t vmax = kk * 16256 + ((int64_t)1 << 29) + (ep.row_bias ? (int64_t)rb_bound : 0);
     if (vmax > 2147483646ll) return SGN_NONE;
     *vmax_out = vmax;
+    if (ep.post_mul) {  // fused second stage: int32 first stage in a *_LO mode, shift2 >= 32, threshold representable
+        if (ep.out_type != FPCC_OUT_I32 || shift >= 32) return SGN_NONE;
+        const uint32_t m2 = ep.post_mul[0];
+        const int64_t z2 = ep.post_zp[0];
+        if (ep.post_shift < 32 || ep.post_shift > 62 || m2 == 0u || m2 >= (1u << 31) || z2 > ((int64_t)1 << 60) || z2 < -((int64_t)1 << 60)) return SGN_NONE;
+        if (ep.post_slope2) { const int32_t sl = ep.post_slope2[0]; if (sl < 0 || sl > (1 << 25)) return SGN_NONE; }
+        const int64_t nz = -z2, m = (int64_t)m2, t2 = nz >= 0 ? (nz + m - 1) / m : -((-nz) / m);
+        if (t2 > 2147483647ll) return SGN_NONE;  // y == INT32_MAX must still compare right
+    }
     if (zp == 0) return shift <= 32 ? SGN_LO0 : SGN_HI0;
     if (zp > ((int64_t)1 << 60) || zp < -((int64_t)1 << 60)) return SGN_NONE;
     const int64_t c0 = zp + ((int64_t)1 << (shift - 1));
@@ -400,7 +441,6 @@ struct LeanTile {
     int c_begin, c_end, ncols;  // this warp's columns; valid columns of the tile (N - n0)
     bool have_acc, row_ok;
     char *orow;                 // output row (column n0), NULL rows are not stored
-    char *orow_pair;            // int32 outputs: the lane ^ 1 partner's output row when the whole warp has rows, else NULL
     const int32_t *rb_row;      // occupancy bias row (column n0) or NULL
     const int32_t *res_row;     // residual row (column n0) or NULL
     bool has_post;
@@ -414,8 +454,9 @@ __device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t &r) {
 // Exact recomputation of one chunk, one column at a time straight from TMEM (rare: an int32 output saturated).
 // Executed by the whole warp (tcgen05.ld is warp-collective); rows without an output skip the store.
 template <int OUT, bool SLOPE>
-__device__ __forceinline__ void lean_redo_chunk(const LeanTile &lt, const LeanU &u, int c0, int64_t zp) {
+__device__ __forceinline__ void lean_redo_chunk(const LeanTile &lt, const LeanU &u, int c0, int64_t zp, const EpiParams &ep) {
     const int64_t half = (int64_t)1 << (u.shift - 1);
+    const Post2 p2 = load_post2(ep);
 #pragma unroll 1
     for (int q = 0; q < EC; ++q) {
         uint32_t a = 0;
@@ -431,7 +472,8 @@ __device__ __forceinline__ void lean_redo_chunk(const LeanTile &lt, const LeanU 
                     r = (int32_t)((uint32_t)r + (uint32_t)__ldg(lt.res_row + c0 + q));
                     if (lt.has_post) r = sat_s32(prelu_q25((int64_t)r, u.post));
                 }
-                ((int32_t *)lt.orow)[c0 + q] = r;
+                if (p2.on) ((int8_t *)lt.orow)[c0 + q] = (int8_t)post2_exact(r, p2);
+                else ((int32_t *)lt.orow)[c0 + q] = r;
             } else {
                 ((int8_t *)lt.orow)[c0 + q] = (int8_t)r;
             }
@@ -442,9 +484,11 @@ __device__ __forceinline__ void lean_redo_chunk(const LeanTile &lt, const LeanU 
 
 // All chunks of one tile row.  The case (output type, PReLU, sign mode) is chosen once per tile by the caller; row
 // pointers and constants are formed once.  Requires 16-byte aligned rows and N % 16 == 0 (whole chunks).
-template <int OUT, bool SLOPE, int SGN>
-__device__ __forceinline__ void lean_tile(const LeanTile &lt, const LeanU &u, int64_t zp) {
-    constexpr int esz = OUT == FPCC_OUT_I8 ? 1 : 4;
+// POST2 (int32 first stage only): the int32 values go through the fused second stage ([PReLU] + requant, shift2 >= 32)
+// and leave as int8 rows: y*mul2 + c02 - [y < thr2], high word >> (shift2 - 32).
+template <int OUT, bool SLOPE, int SGN, bool POST2, bool SLOPE2>
+__device__ __forceinline__ void lean_tile(const LeanTile &lt, const LeanU &u, int64_t zp, const EpiParams &ep) {
+    constexpr int esz = (OUT == FPCC_OUT_I8 || POST2) ? 1 : 4;
     for (int c0 = lt.c_begin; c0 < lt.c_end; c0 += EC) {
         uint32_t acc[EC];
         __syncwarp();  // lanes without an output row skipped the previous chunk's stores
@@ -467,11 +511,11 @@ __device__ __forceinline__ void lean_tile(const LeanTile &lt, const LeanU &u, in
         const bool good = lean_chunk<OUT, SLOPE, SGN>(acc, lt.chan_addr + (uint32_t)c0 * 16, u, o);
         if (OUT == FPCC_OUT_I32 && (SGN == SGN_LO0 || SGN == SGN_THR_LO)) {
             if (__any_sync(0xffffffffu, !good)) {  // warp-uniform, rare
-                lean_redo_chunk<OUT, SLOPE>(lt, u, c0, zp);
+                lean_redo_chunk<OUT, SLOPE>(lt, u, c0, zp, ep);
                 continue;
             }
         }
-        if (!lt.row_ok && !(OUT == FPCC_OUT_I32 && lt.orow_pair)) continue;
+        if (!lt.row_ok) continue;
         if (OUT == FPCC_OUT_I32) {
             if (lt.res_row) {
                 const int4 *rp = reinterpret_cast<const int4 *>(lt.res_row + c0);
@@ -488,36 +532,25 @@ __device__ __forceinline__ void lean_tile(const LeanTile &lt, const LeanU &u, in
                     for (int q = 0; q < EC; ++q) o[q] = prelu_unit(o[q], u.post, u.k24);
                 }
             }
-            if (lt.orow_pair) {
-                // Row-per-lane STG.128 touches 32 HALF sectors per instruction (SM->L2 write bytes = 2x the output).  Lane
-                // pairs swap two of their four 16-byte pieces so that every STG.128 writes whole 32-byte sectors:
-                // even lanes send pieces 1 and 3, odd lanes pieces 0 and 2.
-                const bool odd = (threadIdx.x & 1) != 0;
-                uint4 rcv[2];
+            if (POST2) {
+                const int4 k2 = lds128(u.post2_addr);          // mul2, thr2, slope2, shift2 - 32
+                const int4 k3 = lds128(u.post2_addr + 16);     // c02 lo, c02 hi
+                const int64_t c02 = pack64((uint32_t)k3.x, (uint32_t)k3.y), c02m1 = c02 - 1;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int qs = 4 * (2 * h);  // first word of piece 2h
-                    rcv[h].x = __shfl_xor_sync(0xffffffffu, (uint32_t)(odd ? o[qs] : o[qs + 4]), 1);
-                    rcv[h].y = __shfl_xor_sync(0xffffffffu, (uint32_t)(odd ? o[qs + 1] : o[qs + 5]), 1);
-                    rcv[h].z = __shfl_xor_sync(0xffffffffu, (uint32_t)(odd ? o[qs + 2] : o[qs + 6]), 1);
-                    rcv[h].w = __shfl_xor_sync(0xffffffffu, (uint32_t)(odd ? o[qs + 3] : o[qs + 7]), 1);
+                for (int q = 0; q < EC; ++q) {
+                    int32_t y = o[q];
+                    if (SLOPE2) y = prelu_unit(y, k2.z, u.k24);
+                    const int64_t t2 = mad_wide(y, k2.x, y < k2.y ? c02m1 : c02);
+                    o[q] = (int32_t)((uint64_t)t2 >> 32) >> k2.w;
                 }
-                // stores 1 / 3: the EVEN lane's row (bytes 0-31 / 32-63 of the chunk), stores 2 / 4: the ODD lane's row
-                char *pa = (odd ? lt.orow_pair : lt.orow) + (size_t)c0 * esz + (odd ? 16 : 0);
-                char *pb = (odd ? lt.orow : lt.orow_pair) + (size_t)c0 * esz + (odd ? 16 : 0);
-                const uint4 own0 = odd ? make_uint4((uint32_t)o[4], (uint32_t)o[5], (uint32_t)o[6], (uint32_t)o[7])
-                                       : make_uint4((uint32_t)o[0], (uint32_t)o[1], (uint32_t)o[2], (uint32_t)o[3]);
-                const uint4 own1 = odd ? make_uint4((uint32_t)o[12], (uint32_t)o[13], (uint32_t)o[14], (uint32_t)o[15])
-                                       : make_uint4((uint32_t)o[8], (uint32_t)o[9], (uint32_t)o[10], (uint32_t)o[11]);
-                *reinterpret_cast<uint4 *>(pa) = odd ? rcv[0] : own0;
-                *reinterpret_cast<uint4 *>(pb) = odd ? own0 : rcv[0];
-                *reinterpret_cast<uint4 *>(pa + 32) = odd ? rcv[1] : own1;
-                *reinterpret_cast<uint4 *>(pb + 32) = odd ? own1 : rcv[1];
             } else {
                 uint4 *op = reinterpret_cast<uint4 *>(lt.orow + (size_t)c0 * esz);
 #pragma unroll
                 for (int t = 0; t < EC / 4; ++t) op[t] = make_uint4((uint32_t)o[4 * t], (uint32_t)o[4 * t + 1], (uint32_t)o[4 * t + 2], (uint32_t)o[4 * t + 3]);
             }
+        }
+        if (OUT == FPCC_OUT_I32 && !POST2) {
+            // stored above
         } else {
             uint32_t w[EC / 4];
 #pragma unroll
@@ -532,12 +565,17 @@ __device__ __forceinline__ void lean_tile(const LeanTile &lt, const LeanU &u, in
     }
 }
 
-template <int OUT, bool SLOPE>
-__device__ __forceinline__ void lean_tile_sgn(const LeanTile &lt, const LeanU &u, int64_t zp, int sgn) {
-    if (sgn == SGN_HI0) lean_tile<OUT, SLOPE, SGN_HI0>(lt, u, zp);
-    else if (sgn == SGN_LO0) lean_tile<OUT, SLOPE, SGN_LO0>(lt, u, zp);
-    else if (sgn == SGN_THR_HI) lean_tile<OUT, SLOPE, SGN_THR_HI>(lt, u, zp);
-    else lean_tile<OUT, SLOPE, SGN_THR_LO>(lt, u, zp);
+template <int OUT, bool SLOPE, bool POST2, bool SLOPE2>
+__device__ __forceinline__ void lean_tile_sgn(const LeanTile &lt, const LeanU &u, int64_t zp, int sgn, const EpiParams &ep) {
+    if (POST2) {  // int32 producers of a converted model sit at shift - 23 = 5..16: the *_LO modes
+        if (sgn == SGN_LO0) lean_tile<OUT, SLOPE, SGN_LO0, POST2, SLOPE2>(lt, u, zp, ep);
+        else lean_tile<OUT, SLOPE, SGN_THR_LO, POST2, SLOPE2>(lt, u, zp, ep);
+        return;
+    }
+    if (sgn == SGN_HI0) lean_tile<OUT, SLOPE, SGN_HI0, false, false>(lt, u, zp, ep);
+    else if (sgn == SGN_LO0) lean_tile<OUT, SLOPE, SGN_LO0, false, false>(lt, u, zp, ep);
+    else if (sgn == SGN_THR_HI) lean_tile<OUT, SLOPE, SGN_THR_HI, false, false>(lt, u, zp, ep);
+    else lean_tile<OUT, SLOPE, SGN_THR_LO, false, false>(lt, u, zp, ep);
 }
 
 // ---- floating-point epilogue (kind::f16 path): v = acc + bias; act; [+ residual; post act]; cast -------------
@@ -685,7 +723,20 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
     const int64_t zp_all = KIND == 0 ? ep.zp[0] : 0;
     int64_t vmax = 0;
     const int sgn_mode = KIND == 0 ? lean_mode(ep, zp_all, (int64_t)a.K * (MODE == 0 ? a.kvol : 1), ep.row_bias_bound, &vmax) : SGN_NONE;
-    if (tid == 0) { *lean_off = sgn_mode != SGN_NONE ? 0u : 1u; thr_s[0] = (1 << 24) - 1; thr_s[1] = 0; }
+    if (tid == 0) {
+        *lean_off = sgn_mode != SGN_NONE ? 0u : 1u;
+        thr_s[0] = (1 << 24) - 1; thr_s[1] = 0;
+        if (KIND == 0 && ep.post_mul) {  // second-stage constants of the lean path (LeanU::post2_addr)
+            const Post2 p2 = load_post2(ep);
+            int64_t t2 = 0;
+            if (p2.mul) { const int64_t nz = -p2.zp, m = (int64_t)p2.mul; t2 = nz >= 0 ? (nz + m - 1) / m : -((-nz) / m); }
+            const int64_t c02 = p2.zp + (p2.shift > 0 ? (int64_t)1 << (p2.shift - 1) : 0);
+            thr_s[4] = (int32_t)p2.mul;
+            thr_s[5] = (int32_t)(t2 > 2147483647ll ? 2147483647ll : (t2 < -2147483648ll ? -2147483648ll : t2));
+            thr_s[6] = p2.slope; thr_s[7] = p2.shift >= 32 ? p2.shift - 32 : 0;
+            thr_s[8] = (int32_t)(uint32_t)c02; thr_s[9] = (int32_t)(uint32_t)((uint64_t)c02 >> 32);
+        }
+    }
     __syncthreads();
     if (chan_static)
         for (int c = tid; c < a.n_tile; c += P_THREADS) {
@@ -896,6 +947,8 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
             lu.ovf_add = shift > 0 && shift <= 31 ? 1u << (shift - 1) : 0u;
             lu.ovf_lim = shift <= 31 ? (1u << shift) - 1u : 0xffffffffu;
         }
+        lu.post2_addr = smem_u32(thr_s + 4);
+        const bool post2_on = KIND == 0 && ep.post_mul != nullptr;
         int j = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
             const int slot = j & 1;
@@ -925,27 +978,25 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
             mbar_wait(&tmem_full[slot], (j >> 1) & 1);
             tc_fence_after();
             const uint32_t tacc = tmem_base + (uint32_t)(slot * a.tmem_cols) + ((uint32_t)(quarter * 32) << 16);
-            const bool lean = KIND == 0 && out_al && (a.N & 15) == 0 && *(volatile uint32_t *)lean_off == 0u;
+            const bool lean = KIND == 0 && out_al && (a.N & 15) == 0 && *(volatile uint32_t *)lean_off == 0u && !(post2_on && has_slope);
             if (KIND == 0 && lean) {
                 LeanTile lt;
                 lt.tacc = tacc; lt.chan_addr = smem_u32(chan4_s); lt.c_begin = c_begin; lt.c_end = c_end; lt.ncols = a.N - n0;
                 lt.have_acc = have_acc; lt.row_ok = row_ok; lt.has_post = has_post;
                 const int64_t row0 = row_ok ? m * a.N + n0 : 0;
-                lt.orow = (char *)out + row0 * (ep.out_type == FPCC_OUT_I8 ? 1 : 4);
-                lt.orow_pair = nullptr;
-                if (ep.out_type == FPCC_OUT_I32) {  // warp-uniform: pair stores need a row in every lane
-                    const unsigned long long mine = (unsigned long long)(uintptr_t)lt.orow;
-                    const unsigned long long other = __shfl_xor_sync(0xffffffffu, mine, 1);
-                    if (__all_sync(0xffffffffu, row_ok)) lt.orow_pair = (char *)(uintptr_t)other;
-                }
+                lt.orow = (char *)out + row0 * ((ep.out_type == FPCC_OUT_I8 || post2_on) ? 1 : 4);
                 lt.rb_row = ep.row_bias ? ep.row_bias + (row_ok ? (int64_t)__ldg(&ep.row_idx[m]) * a.N + n0 : 0) : nullptr;
                 lt.res_row = ep.residual ? ep.residual + row0 : nullptr;
                 if (ep.out_type == FPCC_OUT_I8) {
-                    if (has_slope) lean_tile_sgn<FPCC_OUT_I8, true>(lt, lu, zp, sgn_mode);
-                    else lean_tile_sgn<FPCC_OUT_I8, false>(lt, lu, zp, sgn_mode);
+                    if (has_slope) lean_tile_sgn<FPCC_OUT_I8, true, false, false>(lt, lu, zp, sgn_mode, ep);
+                    else lean_tile_sgn<FPCC_OUT_I8, false, false, false>(lt, lu, zp, sgn_mode, ep);
+                } else if (!post2_on) {
+                    if (has_slope) lean_tile_sgn<FPCC_OUT_I32, true, false, false>(lt, lu, zp, sgn_mode, ep);
+                    else lean_tile_sgn<FPCC_OUT_I32, false, false, false>(lt, lu, zp, sgn_mode, ep);
+                } else if (ep.post_slope2 != nullptr) {  // selection linears of the multi-step predictors: no PReLU of their own
+                    lean_tile_sgn<FPCC_OUT_I32, false, true, true>(lt, lu, zp, sgn_mode, ep);
                 } else {
-                    if (has_slope) lean_tile_sgn<FPCC_OUT_I32, true>(lt, lu, zp, sgn_mode);
-                    else lean_tile_sgn<FPCC_OUT_I32, false>(lt, lu, zp, sgn_mode);
+                    lean_tile_sgn<FPCC_OUT_I32, false, true, false>(lt, lu, zp, sgn_mode, ep);
                 }
             } else
             for (int c0 = c_begin; c0 < c_end; c0 += EC) {
@@ -975,12 +1026,15 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
                 cx.residual = ep.residual ? ep.residual + m * a.N + nb : nullptr;
                 cx.has_post = has_post;
                 cx.nvalid = min(EC, a.N - nb);
-                void *optr = (char *)out + (m * a.N + nb) * (ep.out_type == FPCC_OUT_I8 ? 1 : (ep.out_type == FPCC_OUT_I16 ? 2 : 4));
+                void *optr = (char *)out + (m * a.N + nb) * ((ep.out_type == FPCC_OUT_I8 || post2_on) ? 1 : (ep.out_type == FPCC_OUT_I16 ? 2 : 4));
                 const bool vec = out_al && (a.N & 15) == 0;
                 const bool rb = ep.row_bias != nullptr;
-                if (ep.out_type == FPCC_OUT_I8) epi_dispatch<FPCC_OUT_I8>(acc, cx, optr, vec, has_slope, rb);
-                else if (ep.out_type == FPCC_OUT_I32) epi_dispatch<FPCC_OUT_I32>(acc, cx, optr, vec, has_slope, rb);
-                else epi_dispatch<FPCC_OUT_I16>(acc, cx, optr, vec, has_slope, rb);
+                Post2 p2;
+                p2.on = false;
+                if (post2_on) p2 = load_post2(ep);
+                if (ep.out_type == FPCC_OUT_I8) epi_dispatch<FPCC_OUT_I8>(acc, cx, optr, vec, has_slope, rb, p2);
+                else if (ep.out_type == FPCC_OUT_I32) epi_dispatch<FPCC_OUT_I32>(acc, cx, optr, vec, has_slope, rb, p2);
+                else epi_dispatch<FPCC_OUT_I16>(acc, cx, optr, vec, has_slope, rb, p2);
             }
             tc_fence_before();
             __syncwarp();

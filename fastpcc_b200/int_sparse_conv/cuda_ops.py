@@ -189,7 +189,7 @@ class _AffineIn8(LoadSaveUint32RequantMul):
         self.register_buffer('scale_out', torch.zeros((1,), dtype=torch.float32) - 1, persistent=True)
         self.register_buffer('zero_point_out', torch.zeros((1,), dtype=torch.float32), persistent=True)
 
-    def epilogue(self, with_bias: bool, residual=None, post_slope=None, row_bias=None):
+    def epilogue(self, with_bias: bool, residual=None, post_slope=None, row_bias=None, post_requant=None):
         shift = _shift_of(self)
         if self.out_scaled_int:
             out_type = ops.OUT_I8
@@ -198,7 +198,7 @@ class _AffineIn8(LoadSaveUint32RequantMul):
         return ops.make_epilogue(self.requant_mul, self.int_zero_point_out, shift, out_type,
                                  bias=self.bias if with_bias else None,
                                  slope=self.slope if self.with_prelu else None,
-                                 residual=residual, post_slope=post_slope, row_bias=row_bias)
+                                 residual=residual, post_slope=post_slope, row_bias=row_bias, post_requant=post_requant)
 
     def _import_scales(self, scale_in, scale_out):
         assert scale_in.dtype == torch.float32 and scale_in.numel() == 1
@@ -441,6 +441,14 @@ class RequantFxpToScaledInt8(LoadSaveUint32RequantMul):
         ep = ops.make_epilogue(self.requant_mul, self.int_zero_point_out, SharedFxpShift + _shift_of(self), ops.OUT_I8, slope=slope)
         return ops.requant(input, ep)
 
+    def as_post_stage(self, prelu: Optional['PReLUIn32Out32'] = None):
+        """This requant (and a PReLUIn32Out32 in front of it) as the fused second stage of the producing int32 layer
+        (ops.make_epilogue(post_requant=...)), or None when it cannot be fused with identical integers (slope outside
+        [0, 1]: the stand-alone PReLU saturates to int32 first)."""
+        if prelu is not None and not prelu.slope_in_unit_range():
+            return None
+        return (self.requant_mul, self.int_zero_point_out, SharedFxpShift + _shift_of(self), prelu.slope if prelu is not None else None)
+
     def bit_levels(self):
         """int8 images of the Q8.23 values 0 and 1.0 (an occupancy bit << 23) under this requant, cached."""
         key = (self.requant_mul._version, self.requant_shift._version, self.int_zero_point_out._version)
@@ -486,9 +494,14 @@ class LinearIn8W8(_AffineIn8):
             assert zero_point_out is None
             _fill_requant(self, scale_in * scale_weight, None)
 
-    def forward(self, input: torch.Tensor, sel=None, n_out_rows=None) -> torch.Tensor:
+    def forward(self, input: torch.Tensor, sel=None, n_out_rows=None, post_requant=None) -> torch.Tensor:
         """GEMM + bias + [PReLU] + requant in one kernel.  `sel` (from ops.slot_pairs) evaluates only the
-        occupied (row, child) blocks of a C -> 8C linear: identical values, 4-8x less work."""
+        occupied (row, child) blocks of a C -> 8C linear: identical values, 4-8x less work.  `post_requant`
+        (RequantFxpToScaledInt8.as_post_stage of the ONLY consumer of this layer's int32 output) makes the kernel
+        emit that consumer's int8 directly: the Q8.23 tensor is never written."""
+        if post_requant is not None:
+            assert not self.out_scaled_int and not getattr(self, 'padded_output', False)
+            return ops.linear(input, self.weight, self.epilogue(True, post_requant=post_requant), sel=sel, n_out_rows=n_out_rows)
         if sel is None and getattr(self, 'padded_output', False) and self.out_ch % 16 != 0 and self.in_ch % 16 == 0 and self.in_ch >= 32:
             # opt-in (the consumer must accept a row pitch), e.g. the 255 logits feeding the CDF kernels: run the
             # kernel on 256 zero-padded channels so that its rows are 16-byte aligned

@@ -68,14 +68,18 @@ class _Trace:
 class SparseSequential(nn.Sequential):
     """model.py:524-534; `sel`/`n_out_rows` are forwarded to the LAST linear (occupied-children form)."""
 
-    def forward(self, input: SparseTensor, sel=None, n_out_rows=None) -> SparseTensor:
+    def forward(self, input: SparseTensor, sel=None, n_out_rows=None, post_requant=None, skip=0) -> SparseTensor:
+        """`post_requant`: fused second stage of the LAST linear (see LinearIn8W8.forward); `skip`: leading modules
+        whose work a producer's fused second stage has already done."""
         x = SparseTensor(input.F, input.C, input.stride, input.spatial_range)
         x._caches = input._caches
         last = len(self) - 1
         for i, module in enumerate(self):
+            if i < skip:
+                continue
             if isinstance(module, _DENSE):
-                if i == last and sel is not None:
-                    x.F = module(x.F, sel=sel, n_out_rows=n_out_rows)
+                if i == last and (sel is not None or post_requant is not None):
+                    x.F = module(x.F, sel=sel, n_out_rows=n_out_rows, post_requant=post_requant)
                 else:
                     x.F = module(x.F)
             else:
@@ -236,12 +240,28 @@ class OneScaleMultiStepPredictor(nn.Module):
             cur.F = torch.cat([cur.F, embed_f], 1)
             cur = self.dec(cur)
         x = cur
+
+        def consumer_stage(j):
+            """The Q8.23 output of step j's selection linear has ONE consumer, the [PReLU +] Requant that opens step j+1:
+            run it inside the linear's epilogue (identical integers, no int32 round trip through HBM) when the linear
+            runs on the tensor cores."""
+            if j + 1 >= S:
+                return None
+            nxt = self.pred[j + 1]
+            lin = self.pred[j][-1]
+            if ops.gemm_engine(lin.in_ch, lin.out_ch // 8) != 'tc' or lin.out_ch % 128 != 0:
+                return None
+            return nxt[1].as_post_stage(nxt[0]) if j + 1 != S - 1 else nxt[0].as_post_stage(None)
+
+        fused = None  # second stage already applied to x.F by the producing linear
         for j, block in enumerate(self.pred):
+            post = consumer_stage(j)
             if j == 0:
                 if S > 1:
-                    x = block(cur, sel=levels[1].sel(), n_out_rows=levels[1].n)
+                    x = block(cur, sel=levels[1].sel(), n_out_rows=levels[1].n, post_requant=post)
                 else:
                     x = block(cur)
+                fused = post
                 continue
             lv = levels[j]
             f = x.F  # [n_j, C]: features of the occupied children (selection already applied)
@@ -249,11 +269,16 @@ class OneScaleMultiStepPredictor(nn.Module):
             seed_kernel_map(cur._caches, cur._caches, tuple(s >> (j - 1) for s in cur.stride), levels[j - 1].occ, lv)
             if j != S - 1:
                 # PReLU -> Requant -> LinearPReLU(C+8 -> C) on cat(f, bits) -> Conv -> Linear(C -> 8C)[child mask]
-                f = linear_with_bits(block[1], block[2], f, lv.occ, prelu=block[0])
+                if fused is not None:
+                    q0, q1 = block[1].bit_levels()
+                    f = block[2].forward_with_bits(f, lv.occ, q0, q1)
+                else:
+                    f = linear_with_bits(block[1], block[2], f, lv.occ, prelu=block[0])
                 x = block[3](_with(f, cur, C=lv.C, stride=st))
-                x.F = block[4](x.F, sel=levels[j + 1].sel(), n_out_rows=levels[j + 1].n)
+                x.F = block[4](x.F, sel=levels[j + 1].sel(), n_out_rows=levels[j + 1].n, post_requant=post)
             else:
-                x = block(_with(f, cur, C=lv.C, stride=st))
+                x = block(_with(f, cur, C=lv.C, stride=st), skip=1 if fused is not None else 0)
+            fused = post
         return cur, x.F
 
 

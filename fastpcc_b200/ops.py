@@ -107,8 +107,16 @@ def workspace(nbytes, device):
     return buf
 
 
+def _ep_out_dtype(ep):
+    """dtype of the rows a fused kernel writes: int8 when the second stage is on"""
+    return torch.int8 if ep.post_requant_mul else _OUT_DTYPE[ep.out_type]
+
+
 def make_epilogue(requant_mul, zero_point, shift, out_type, bias=None, slope=None, residual=None, post_slope=None,
-                  row_bias=None):
+                  row_bias=None, post_requant=None):
+    """post_requant = (mul uint32[1], zero_point int64[1], shift, slope int32[1] | None): the fused second stage of the
+    tensor-core kernels -- an int32 (Q8.23) result is not stored, the consumer's [PReLUIn32Out32 +] RequantFxpToScaledInt8
+    runs in the same epilogue and int8 rows come out (fpcc_epilogue::post_requant_mul)."""
     _need(requant_mul, torch.uint32, 'requant_mul')
     _need(zero_point, torch.int64, 'zero_point')
     if shift < 0:
@@ -128,7 +136,15 @@ def make_epilogue(requant_mul, zero_point, shift, out_type, bias=None, slope=Non
         e.row_bias = _p(_need(table, torch.int32, 'row_bias table', 2))
         e.row_idx = _p(_need(idx, torch.uint8, 'row_bias index', 1))
         e.row_bias_bound = int(row_bias[2]) if len(row_bias) > 2 else 0  # max |table entry| when the caller knows it
-    e._keep = (bias, slope, requant_mul, zero_point, residual, post_slope, row_bias)
+    if post_requant is not None:
+        mul2, zp2, shift2, slope2 = post_requant
+        if out_type != OUT_I32:
+            raise RuntimeError('post_requant needs an int32 first stage')
+        e.post_requant_mul = _p(_need(mul2, torch.uint32, 'post requant_mul'))
+        e.post_zero_point = _p(_need(zp2, torch.int64, 'post zero_point'))
+        e.post_shift = int(shift2)
+        e.post_requant_slope = _p(_need(slope2, torch.int32, 'post slope')) if slope2 is not None else None
+    e._keep = (bias, slope, requant_mul, zero_point, residual, post_slope, row_bias, post_requant)
     return e
 
 
@@ -365,7 +381,7 @@ def spconv(in_feats, weight, table, ep, zp_comp=None, out=None, row_perm=None):
     if table.shape[0] != kv or in_feats.shape[1] != c_in:
         raise RuntimeError(f'spconv: shape mismatch weight {tuple(weight.shape)} table {tuple(table.shape)} feats {tuple(in_feats.shape)}')
     n_out = table.shape[1]
-    out = torch.empty((n_out, c_out), dtype=_OUT_DTYPE[ep.out_type], device=in_feats.device) if out is None else out
+    out = torch.empty((n_out, c_out), dtype=_ep_out_dtype(ep), device=in_feats.device) if out is None else out
     tag = work = None
     if _prof is not None:
         tag = 'spconv_' + gemm_engine(c_in, c_out, kv, zp_comp is not None)
@@ -392,7 +408,7 @@ def linear(a, weight, ep, sel=None, n_out_rows=None, out=None):
         raise RuntimeError(f'linear: K mismatch {tuple(a.shape)} x {tuple(weight.shape)}')
     if sel is None:
         n = weight.shape[0]
-        out = torch.empty((m, n), dtype=_OUT_DTYPE[ep.out_type], device=a.device) if out is None else out
+        out = torch.empty((m, n), dtype=_ep_out_dtype(ep), device=a.device) if out is None else out
         _call('fpcc_linear_i8', _p(a), m, k, _p(weight), n, None, None, None, 1, 0, C.byref(ep), _p(out), _s(),
               tag='linear_' + gemm_engine(k, n) if _prof is not None else None,
               work={'ops': 2.0 * m * k * n, 'desc': f'{m}x{k}->{n} out{ep.out_type} rb{int(bool(ep.row_bias))}'})
@@ -400,7 +416,7 @@ def linear(a, weight, ep, sel=None, n_out_rows=None, out=None):
         sel_row, sel_out, offsets = sel
         groups = offsets.numel() - 1
         n = weight.shape[0] // groups
-        out = torch.empty((n_out_rows, n), dtype=_OUT_DTYPE[ep.out_type], device=a.device) if out is None else out
+        out = torch.empty((n_out_rows, n), dtype=_ep_out_dtype(ep), device=a.device) if out is None else out
         _call('fpcc_linear_i8', _p(a), m, k, _p(weight), n, _p(sel_row), _p(sel_out), _p(offsets), groups, n_out_rows,
               C.byref(ep), _p(out), _s(), tag='linear_sel_' + gemm_engine(k, n) if _prof is not None else None,
               work={'ops': 2.0 * n_out_rows * k * n, 'desc': f'{m}x{k}->{groups}x{n} rows{n_out_rows} out{ep.out_type}'})

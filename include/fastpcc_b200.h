@@ -215,6 +215,15 @@ typedef struct {
     const uint8_t *row_idx;      /* [rows] table row of every output row            */
     int32_t row_bias_bound;      /* max |entry| of the row_bias table if the caller knows it, else 0: lets the fused
                                   * kernels prove that acc + row_bias + bias stays inside int32 (32-bit epilogue)  */
+    /* Fused second stage (tensor-core kernels, out_type FPCC_OUT_I32 only): when post_requant_mul is set the finished
+     * int32 (Q8.23) value y is not stored; instead the consumer's PReLUIn32Out32 (optional, prelu.cu:6-21) and
+     * RequantFxpToScaledInt8 (cuda_ops.py:473-509) run in the same epilogue and `out` receives int8 rows:
+     *     out = sat8(rha(prelu(y) * post_requant_mul + post_zero_point, post_shift))
+     * i.e. exactly what fpcc_prelu_i32 + fpcc_requant would produce from the int32 tensor. */
+    const uint32_t *post_requant_mul;   /* device [1] or NULL */
+    const int64_t *post_zero_point;     /* device [1]         */
+    int32_t post_shift;                 /* 0 .. 62            */
+    const int32_t *post_requant_slope;  /* device [1] Q6.25 or NULL */
 } fpcc_epilogue;
 
 /* replaces the 12 requant entry points of binding.cu:118-129 */

@@ -324,6 +324,57 @@ def test_epilogue_shift0_and_small_negatives(ops):
                 assert (got == want).all(), ('requant', shift, mulv, zpv)
 
 
+@pytest.mark.parametrize('k,n', [(64, 64), (256, 256), (32, 48)])
+def test_fused_second_stage_equals_prelu_then_requant(ops, k, n):
+    """fpcc_epilogue::post_requant_mul: an int32 (Q8.23) linear whose only consumer is [PReLUIn32Out32 +]
+    RequantFxpToScaledInt8 emits that consumer's int8 directly.  Must equal the three stand-alone steps of the
+    reference (bias_requant_to_int32 -> prelu -> requant_to_int8) for plain and selection linears, symmetric and
+    asymmetric second stages, values that saturate the int32 first stage (exact per-column redo) and first-stage
+    parameters outside the lean path (generic epilogue)."""
+    rng = np.random.default_rng(k * 1000 + n)
+    m = 700
+    a = rng.integers(-128, 128, (m, k)).astype(np.int8)
+    w = rng.integers(-127, 128, (n, k)).astype(np.int8)
+    acc = K.gemm_int8(a, w, None)
+    cases = 0
+    for shift1, mul_hi, bias_hi in ((9, 1 << 20, 1 << 16), (12, 1 << 22, 1 << 20), (3, 1 << 27, 1 << 28), (5, (1 << 32) - 1, 1000), (0, 7, 100)):
+        mul1 = rng.integers(mul_hi >> 2, mul_hi, n, endpoint=True).astype(np.uint32)
+        bias = rng.integers(-bias_hi, bias_hi, n, endpoint=True).astype(np.int32)
+        zp1 = np.zeros(1, np.int64)
+        y = K.requant(acc, mul1, zp1, shift1, np.int32, bias=bias)
+        for shift2, mul2v, zp2v, slope2v in ((48, (1 << 30) + 12345, 0, None), (48, (1 << 29) + 7, 0, int(0.25 * (1 << 25))),
+                                            (44, (1 << 30) - 3, (5 << 44) + 99, int(0.1 * (1 << 25))), (40, 12345, -(3 << 39), None),
+                                            (33, (1 << 31) - 1, 1, 1 << 25), (62, (1 << 30) + 1, -(1 << 59), 0)):
+            mul2, zp2 = np.array([mul2v], np.uint32), np.array([zp2v], np.int64)
+            sl2 = None if slope2v is None else np.array([slope2v], np.int32)
+            y2 = y if sl2 is None else K.prelu(y, sl2)
+            want = K.requant(y2, np.full(n, mul2v, np.uint32), zp2, shift2, np.int8)
+            post = (dev(mul2), dev(zp2), shift2, None if sl2 is None else dev(sl2))
+            ep = ops.make_epilogue(dev(mul1), dev(zp1), shift1, ops.OUT_I32, bias=dev(bias), post_requant=post)
+            got = ops.linear(dev(a), dev(w), ep)
+            assert got.dtype == torch.int8 and (got.cpu().numpy() == want).all(), (shift1, shift2, mul2v, zp2v, slope2v)
+            cases += 1
+    assert cases == 30
+    # selection form (Linear(C -> 8C)[child mask] of the multi-step predictors), per-group bias / multipliers
+    if n % 16 == 0:
+        occ = rng.integers(1, 256, m).astype(np.uint8)
+        w8 = rng.integers(-127, 128, (8 * n, k)).astype(np.int8)
+        bias8 = rng.integers(-100000, 100000, 8 * n).astype(np.int32)
+        mul8 = rng.integers(1 << 18, 1 << 21, 8 * n).astype(np.uint32)
+        dense = K.requant(K.gemm_int8(a, w8, bias8), mul8, np.zeros(1, np.int64), 10, np.int32)
+        bits = ((occ[:, None] >> np.arange(7, -1, -1)[None]) & 1).astype(bool)
+        y = dense.reshape(m, 8, n)[bits]
+        sl2, mul2, zp2 = np.array([int(0.3 * (1 << 25))], np.int32), np.array([(1 << 30) + 77], np.uint32), np.array([3 << 45], np.int64)
+        want = K.requant(K.prelu(y, sl2), np.full(n, mul2[0], np.uint32), zp2, 47, np.int8)
+        C4 = np.zeros((m, 4), np.int32); C4[:, 1] = np.arange(m)
+        _, par, slot, n_child = ops.upsample(dev(C4), dev(occ))
+        sel = ops.slot_pairs(par, slot)
+        ep = ops.make_epilogue(dev(mul8), dev(np.zeros(1, np.int64)), 10, ops.OUT_I32, bias=dev(bias8),
+                               post_requant=(dev(mul2), dev(zp2), 47, dev(sl2)))
+        got = ops.linear(dev(a), dev(w8), ep, sel=sel, n_out_rows=n_child)
+        assert got.dtype == torch.int8 and (got.cpu().numpy() == want).all()
+
+
 def test_selected_linear_equals_masked_dense(ops):
     """Linear(C->8C) + child mask (model.py:64-66) == occupied-children-only evaluation."""
     rng = np.random.default_rng(4)
