@@ -486,11 +486,30 @@ __device__ __forceinline__ void lean_redo_chunk(const LeanTile &lt, const LeanU 
 // pointers and constants are formed once.  Requires 16-byte aligned rows and N % 16 == 0 (whole chunks).
 // POST2 (int32 first stage only): the int32 values go through the fused second stage ([PReLU] + requant, shift2 >= 32)
 // and leave as int8 rows: y*mul2 + c02 - [y < thr2], high word >> (shift2 - 32).
-template <int OUT, bool SLOPE, int SGN, bool POST2, bool SLOPE2>
+template <int OUT, bool SLOPE, int SGN, bool POST2, bool SLOPE2, bool RESPF>
 __device__ __forceinline__ void lean_tile(const LeanTile &lt, const LeanU &u, int64_t zp, const EpiParams &ep) {
     constexpr int esz = (OUT == FPCC_OUT_I8 || POST2) ? 1 : 4;
+    // int32 residual rows (ResBlock conv2) come from HBM: the loads of chunk c+1 are issued before the arithmetic of
+    // chunk c (one register set ahead), so that their latency hides behind it instead of stalling every chunk
+    // (RESPF: the conv kernel only; the linear kernel sits at its 80-register cap and has no residual user)
+    const bool res_on = RESPF && OUT == FPCC_OUT_I32 && lt.res_row != nullptr && lt.row_ok;
+    const int c_last = min(lt.c_end, lt.ncols);
+    int4 rnext[EC / 4];
+#pragma unroll
+    for (int t = 0; t < EC / 4; ++t) rnext[t] = make_int4(0, 0, 0, 0);
+    if (res_on && lt.c_begin < c_last) {
+#pragma unroll
+        for (int t = 0; t < EC / 4; ++t) rnext[t] = __ldg(reinterpret_cast<const int4 *>(lt.res_row + lt.c_begin) + t);
+    }
     for (int c0 = lt.c_begin; c0 < lt.c_end; c0 += EC) {
         uint32_t acc[EC];
+        int4 rcur[EC / 4];
+#pragma unroll
+        for (int t = 0; t < EC / 4; ++t) rcur[t] = rnext[t];
+        if (res_on && c0 + EC < c_last) {
+#pragma unroll
+            for (int t = 0; t < EC / 4; ++t) rnext[t] = __ldg(reinterpret_cast<const int4 *>(lt.res_row + c0 + EC) + t);
+        }
         __syncwarp();  // lanes without an output row skipped the previous chunk's stores
         if (lt.have_acc) {
             tmem_ld16(lt.tacc + (uint32_t)c0, acc);  // .sync.aligned: every lane, also those without a row
@@ -518,10 +537,9 @@ __device__ __forceinline__ void lean_tile(const LeanTile &lt, const LeanU &u, in
         if (!lt.row_ok) continue;
         if (OUT == FPCC_OUT_I32) {
             if (lt.res_row) {
-                const int4 *rp = reinterpret_cast<const int4 *>(lt.res_row + c0);
 #pragma unroll
                 for (int t = 0; t < EC / 4; ++t) {
-                    const int4 rv = __ldg(rp + t);
+                    const int4 rv = RESPF ? rcur[t] : __ldg(reinterpret_cast<const int4 *>(lt.res_row + c0) + t);
                     o[4 * t] = (int32_t)((uint32_t)o[4 * t] + (uint32_t)rv.x);  // int32 add wraps
                     o[4 * t + 1] = (int32_t)((uint32_t)o[4 * t + 1] + (uint32_t)rv.y);
                     o[4 * t + 2] = (int32_t)((uint32_t)o[4 * t + 2] + (uint32_t)rv.z);
@@ -565,17 +583,17 @@ __device__ __forceinline__ void lean_tile(const LeanTile &lt, const LeanU &u, in
     }
 }
 
-template <int OUT, bool SLOPE, bool POST2, bool SLOPE2>
+template <int OUT, bool SLOPE, bool POST2, bool SLOPE2, bool RESPF>
 __device__ __forceinline__ void lean_tile_sgn(const LeanTile &lt, const LeanU &u, int64_t zp, int sgn, const EpiParams &ep) {
     if (POST2) {  // int32 producers of a converted model sit at shift - 23 = 5..16: the *_LO modes
-        if (sgn == SGN_LO0) lean_tile<OUT, SLOPE, SGN_LO0, POST2, SLOPE2>(lt, u, zp, ep);
-        else lean_tile<OUT, SLOPE, SGN_THR_LO, POST2, SLOPE2>(lt, u, zp, ep);
+        if (sgn == SGN_LO0) lean_tile<OUT, SLOPE, SGN_LO0, POST2, SLOPE2, RESPF>(lt, u, zp, ep);
+        else lean_tile<OUT, SLOPE, SGN_THR_LO, POST2, SLOPE2, RESPF>(lt, u, zp, ep);
         return;
     }
-    if (sgn == SGN_HI0) lean_tile<OUT, SLOPE, SGN_HI0, false, false>(lt, u, zp, ep);
-    else if (sgn == SGN_LO0) lean_tile<OUT, SLOPE, SGN_LO0, false, false>(lt, u, zp, ep);
-    else if (sgn == SGN_THR_HI) lean_tile<OUT, SLOPE, SGN_THR_HI, false, false>(lt, u, zp, ep);
-    else lean_tile<OUT, SLOPE, SGN_THR_LO, false, false>(lt, u, zp, ep);
+    if (sgn == SGN_HI0) lean_tile<OUT, SLOPE, SGN_HI0, false, false, RESPF>(lt, u, zp, ep);
+    else if (sgn == SGN_LO0) lean_tile<OUT, SLOPE, SGN_LO0, false, false, RESPF>(lt, u, zp, ep);
+    else if (sgn == SGN_THR_HI) lean_tile<OUT, SLOPE, SGN_THR_HI, false, false, RESPF>(lt, u, zp, ep);
+    else lean_tile<OUT, SLOPE, SGN_THR_LO, false, false, RESPF>(lt, u, zp, ep);
 }
 
 // ---- floating-point epilogue (kind::f16 path): v = acc + bias; act; [+ residual; post act]; cast -------------
@@ -975,6 +993,12 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
             const int64_t mt = (int64_t)tile_m * TC_M + r;  // MODE 0: column of the neighbour table
             const bool row_ok = MODE == 0 ? (mt < a.n_out) : (rows[TC_M + r] >= 0);
             const int64_t m = MODE == 0 ? ((a.row_perm && row_ok) ? (int64_t)__ldg(&a.row_perm[mt]) : mt) : (int64_t)rows[TC_M + r];
+            if (KIND == 0 && ep.residual && row_ok) {
+                // residual rows of this tile: start them towards L2 while the MMAs of the tile are still running
+                const char *rp = (const char *)(ep.residual + m * a.N + n0 + c_begin);
+                for (int off = 0; off < (c_end - c_begin) * 4; off += 128)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + off));
+            }
             mbar_wait(&tmem_full[slot], (j >> 1) & 1);
             tc_fence_after();
             const uint32_t tacc = tmem_base + (uint32_t)(slot * a.tmem_cols) + ((uint32_t)(quarter * 32) << 16);
@@ -988,15 +1012,15 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
                 lt.rb_row = ep.row_bias ? ep.row_bias + (row_ok ? (int64_t)__ldg(&ep.row_idx[m]) * a.N + n0 : 0) : nullptr;
                 lt.res_row = ep.residual ? ep.residual + row0 : nullptr;
                 if (ep.out_type == FPCC_OUT_I8) {
-                    if (has_slope) lean_tile_sgn<FPCC_OUT_I8, true, false, false>(lt, lu, zp, sgn_mode, ep);
-                    else lean_tile_sgn<FPCC_OUT_I8, false, false, false>(lt, lu, zp, sgn_mode, ep);
+                    if (has_slope) lean_tile_sgn<FPCC_OUT_I8, true, false, false, false>(lt, lu, zp, sgn_mode, ep);
+                    else lean_tile_sgn<FPCC_OUT_I8, false, false, false, false>(lt, lu, zp, sgn_mode, ep);
                 } else if (!post2_on) {
-                    if (has_slope) lean_tile_sgn<FPCC_OUT_I32, true, false, false>(lt, lu, zp, sgn_mode, ep);
-                    else lean_tile_sgn<FPCC_OUT_I32, false, false, false>(lt, lu, zp, sgn_mode, ep);
+                    if (has_slope) lean_tile_sgn<FPCC_OUT_I32, true, false, false, false>(lt, lu, zp, sgn_mode, ep);
+                    else lean_tile_sgn<FPCC_OUT_I32, false, false, false, MODE == 0>(lt, lu, zp, sgn_mode, ep);
                 } else if (ep.post_slope2 != nullptr) {  // selection linears of the multi-step predictors: no PReLU of their own
-                    lean_tile_sgn<FPCC_OUT_I32, false, true, true>(lt, lu, zp, sgn_mode, ep);
+                    lean_tile_sgn<FPCC_OUT_I32, false, true, true, false>(lt, lu, zp, sgn_mode, ep);
                 } else {
-                    lean_tile_sgn<FPCC_OUT_I32, false, true, false>(lt, lu, zp, sgn_mode, ep);
+                    lean_tile_sgn<FPCC_OUT_I32, false, true, false, false>(lt, lu, zp, sgn_mode, ep);
                 }
             } else
             for (int c0 = c_begin; c0 < c_end; c0 += EC) {

@@ -288,7 +288,7 @@ class SparseConvIn8Out8(_AffineIn8):
             return self.forward_with_sparse_tensor(*args, **kwargs)
         return self.forward_with_coords(*args, **kwargs)
 
-    def forward_with_sparse_tensor(self, input: SparseTensor, residual=None, post_slope=None) -> SparseTensor:
+    def forward_with_sparse_tensor(self, input: SparseTensor, residual=None, post_slope=None, post_requant=None) -> SparseTensor:
         caches = input._caches
         tag = (input.stride, self.kernel_size, self.stride)
         cur_kmap: Dict[str, Any] = caches.kmaps.get(tag)
@@ -308,7 +308,8 @@ class SparseConvIn8Out8(_AffineIn8):
             else:
                 raise NotImplementedError((input.stride, self.stride))
         out_feats, hashmap_kv, in_out_maps = self.forward_with_coords(
-            input.F, input.C, output_coords, in_out_maps, hashmap_kv, same, residual=residual, post_slope=post_slope)
+            input.F, input.C, output_coords, in_out_maps, hashmap_kv, same, residual=residual, post_slope=post_slope,
+            post_requant=post_requant)
         caches.kmaps.setdefault(tag, {}).setdefault('in_out_maps', in_out_maps)
         if hashmap_kv is not None:
             caches.hashmaps.setdefault(input.stride, hashmap_kv)
@@ -319,9 +320,9 @@ class SparseConvIn8Out8(_AffineIn8):
         return ret
 
     def forward_with_coords(self, in_feats, in_coords, out_coords, in_out_maps=None, hashmap_kv=None,
-                            if_in_coords_equals_out_coords: bool = False, residual=None, post_slope=None):
+                            if_in_coords_equals_out_coords: bool = False, residual=None, post_slope=None, post_requant=None):
         """-> (out N2 x C2 int8 | Q8.23 int32, hashmap_kv, in_out_maps); conv + epilogue in one kernel."""
-        ep = self.epilogue(True, residual, post_slope)
+        ep = self.epilogue(True, residual, post_slope, post_requant=post_requant)
         if self.in_ch < 32 and not self.use_zero_point_in:
             # thin input (first conv C_in = 1, occupancy embeds C_in = 8): im2col + one tensor-core linear
             kv = self.kernel_volume
@@ -605,13 +606,19 @@ class SparseResBlockIn32W8Out32(nn.Module):
         self.conv2.import_parameters(scale2, zero_point2, block.conv2)
         self.prelu.import_parameters(block.act2)
 
-    def forward(self, input: SparseTensor) -> SparseTensor:
-        """cuda_ops.py:82-92.  The residual add (int32 wrap) and the final PReLU ride in conv2's epilogue."""
+    def can_fuse_consumer(self) -> bool:
+        """conv2 runs on the tensor-core kernel (the only one with the fused second stage)"""
+        return not self.conv2.use_zero_point_in and ops.gemm_engine(self.ch, self.ch, 27) == 'tc'
+
+    def forward(self, input: SparseTensor, post_requant=None) -> SparseTensor:
+        """cuda_ops.py:82-92.  The residual add (int32 wrap) and the final PReLU ride in conv2's epilogue.
+        `post_requant` (RequantFxpToScaledInt8.as_post_stage of the block's ONLY consumer): the block then returns
+        that consumer's int8 rows and its Q8.23 output is never written (check can_fuse_consumer first)."""
         x = SparseTensor(self.input_requant(input.F), input.C, input.stride, input.spatial_range)
         x._caches = input._caches
         x = self.conv_prelu(x)
-        x = self.conv2.forward_with_sparse_tensor(x, residual=input.F, post_slope=self.prelu.slope)
-        assert input.F.dtype == x.F.dtype == torch.int32
+        x = self.conv2.forward_with_sparse_tensor(x, residual=input.F, post_slope=self.prelu.slope, post_requant=post_requant)
+        assert input.F.dtype == torch.int32 and x.F.dtype == (torch.int8 if post_requant is not None else torch.int32)
         out = SparseTensor(x.F, input.C, input.stride, input.spatial_range)
         out._caches = input._caches
         return out

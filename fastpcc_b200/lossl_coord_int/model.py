@@ -180,6 +180,9 @@ class OneScalePredictor(nn.Module):
         Requant -> Linear(C -> 8C)[child mask]; the concat and the masked 8C output are never materialised."""
         u = self.upsample
         x = _with(linear_with_bits(u[0], u[1], cur.F, occ), cur)
+        post = u[3].as_post_stage(None) if u[2].can_fuse_consumer() else None
+        if post is not None:  # the ResBlock's only consumer is u[3]: its requant rides in conv2's epilogue
+            return u[4](u[2](x, post_requant=post).F, sel=child.sel(), n_out_rows=child.n)
         x = u[2](x)
         return u[4](u[3](x.F), sel=child.sel(), n_out_rows=child.n)
 
@@ -237,8 +240,15 @@ class OneScaleMultiStepPredictor(nn.Module):
         else:
             stride = tuple(s >> (S - 2) for s in cur.stride)
             embed_f = self.embed(_with(emb_lv.bits_fxp(), cur, C=emb_lv.C, stride=stride)).F
-            cur.F = torch.cat([cur.F, embed_f], 1)
-            cur = self.dec(cur)
+            dec = self.dec
+            if isinstance(dec, SparseSequential) and isinstance(dec[0], RequantFxpToScaledInt8):
+                # Requant(cat(F, embed)) == cat(Requant(F), Requant(embed)): one scalar multiplier for all channels, so the
+                # concatenation moves int8 rows (4x fewer bytes) and the Q8.23 cat tensor is never built (model.py:199-201)
+                q = torch.cat([dec[0](cur.F), dec[0](embed_f)], 1)
+                cur = dec[2](_with(dec[1](q), cur))
+            else:
+                cur.F = torch.cat([cur.F, embed_f], 1)
+                cur = dec(cur)
         x = cur
 
         def consumer_stage(j):
@@ -427,12 +437,17 @@ class Model(nn.Module):
         for xyz in frames:
             assert xyz.dtype == torch.int32 and xyz.dim() == 2 and xyz.shape[1] == 4
         sizes = [int(f.shape[0]) for f in frames]
-        xyz = torch.cat([f.to(dev) for f in frames]) if B > 1 else frames[0].to(dev).clone()
+        frames = [f.to(dev) for f in frames]
+        # per-frame minimum before the concatenation: B small reductions (a scatter-min over all points funnels
+        # millions of atomics into 3B addresses: 6 ms per 32 frames)
+        off_all = torch.stack([f[:, 1:].amin(0) for f in frames]) if min(sizes) > 0 else None
+        xyz = torch.cat(frames) if B > 1 else frames[0].clone()
         frame_id = torch.repeat_interleave(torch.arange(B, dtype=torch.int32, device=dev),
                                            torch.tensor(sizes, device=dev), output_size=sum(sizes))
-        big = torch.iinfo(torch.int32).max
-        off_all = torch.full((B, 3), big, dtype=torch.int32, device=dev)
-        off_all.scatter_reduce_(0, frame_id.long()[:, None].expand(-1, 3), xyz[:, 1:], 'amin')
+        if off_all is None:  # an empty frame in the batch: the generic segmented minimum
+            big = torch.iinfo(torch.int32).max
+            off_all = torch.full((B, 3), big, dtype=torch.int32, device=dev)
+            off_all.scatter_reduce_(0, frame_id.long()[:, None].expand(-1, 3), xyz[:, 1:], 'amin')
         xyz[:, 1:] -= off_all[frame_id.long()]
         xyz[:, 0] = frame_id
         if B == 1:
