@@ -250,6 +250,12 @@ __device__ __forceinline__ int4 lds128(uint32_t addr) {
     asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
 }
+// staged channel constants are written before a barrier and read-only afterwards: a plain (non-volatile) load
+__device__ __forceinline__ int4 lds128_ro(uint32_t addr) {
+    int4 v;
+    asm("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ int64_t pack64(uint32_t lo, uint32_t hi) {
     int64_t d;
     asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
@@ -439,6 +445,7 @@ struct LeanTile {
     uint32_t tacc;              // TMEM address of this warp's lane quarter, column 0 of the tile
     uint32_t chan_addr;         // shared-space address of the staged channel constants of column 0
     int c_begin, c_end, ncols;  // this warp's columns; valid columns of the tile (N - n0)
+    int n0, ncols_total;        // first channel of the tile, N
     bool have_acc, row_ok;
     char *orow;                 // output row (column n0), NULL rows are not stored
     const int32_t *rb_row;      // occupancy bias row (column n0) or NULL
@@ -596,6 +603,142 @@ __device__ __forceinline__ void lean_tile_sgn(const LeanTile &lt, const LeanU &u
     else lean_tile<OUT, SLOPE, SGN_THR_LO, false, false, RESPF>(lt, u, zp, ep);
 }
 
+// ---- quad layout for int32 outputs ------------------------------------------------------------------------------------
+// Row-per-lane (tcgen05.ld.32x32b) makes every global access of an int32 row a 16-byte piece in its own sector: a
+// STG.128 / LDG.128 touches 32 lines (32 L1 wavefronts) and writes HALF sectors (SM->L2 write bytes = 2x the output;
+// measured on the ResBlock conv2 and the logits linears).  tcgen05.ld.16x256b hands the accumulator out so that the four
+// lanes of a quad hold 8 consecutive columns of ONE row: lane 4i+j gets columns 2j, 2j+1 (and +8 with .x2) of rows i and
+// i+8.  An 8-byte access per lane then covers whole 32-byte sectors per quad, 8 lines per instruction.
+__device__ __forceinline__ void tmem_ld_q16(uint32_t taddr, uint32_t (&r)[16]) {  // 32 rows x 16 columns: two 16x256b.x2 loads
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr + (16u << 16)));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct QuadRows {
+    int64_t off[4];        // element offset (row * N + n0) of rows q, q+8, q+16, q+24 of this warp's quarter, -1 = no row
+    int32_t rb[4];         // row of the occupancy bias table for each of them
+};
+
+// register r of tmem_ld_q16 -> (row slot 0..3, channel slot 0..3): rows {q, q+8 | q+16, q+24}, channels {2j, 2j+1, 8+2j, 9+2j}
+__device__ __forceinline__ constexpr int quad_row(int r) { return (r >> 3) * 2 + ((r >> 1) & 1); }
+__device__ __forceinline__ constexpr int quad_chn(int r) { return ((r >> 2) & 1) * 2 + (r & 1); }
+
+template <bool SLOPE, int SGN, bool RESPF>
+__device__ __forceinline__ void quad_tile(const LeanTile &lt, const QuadRows &qr, const LeanU &u, int64_t zp, const EpiParams &ep,
+                                          int32_t *out) {
+    const int j2 = (threadIdx.x & 3) * 2;
+    const int c_last = min(lt.c_end, lt.ncols);
+    const bool res_pf = RESPF && ep.residual != nullptr;
+    int2 rnext[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) rnext[t] = make_int2(0, 0);
+    auto load_res = [&](int c0, int2 (&dst)[8]) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+                dst[i * 2 + b] = qr.off[i] >= 0 ? __ldg(reinterpret_cast<const int2 *>(ep.residual + qr.off[i] + c0 + 8 * b + j2)) : make_int2(0, 0);
+    };
+    if (res_pf && lt.c_begin < c_last) load_res(lt.c_begin, rnext);
+    for (int c0 = lt.c_begin; c0 < lt.c_end; c0 += EC) {
+        uint32_t acc[16];
+        int2 rcur[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) rcur[t] = rnext[t];
+        if (res_pf && c0 + EC < c_last) load_res(c0 + EC, rnext);
+        __syncwarp();
+        tmem_ld_q16(lt.tacc + (uint32_t)c0, acc);
+        if (c0 >= lt.ncols) continue;  // warp-uniform
+        if (ep.row_bias) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    const int2 rv = qr.off[i] >= 0 ? __ldg(reinterpret_cast<const int2 *>(ep.row_bias + (int64_t)qr.rb[i] * (lt.ncols_total) + lt.n0 + c0 + 8 * b + j2))
+                                                   : make_int2(0, 0);
+                    const int r0 = (i >> 1) * 8 + b * 4 + (i & 1) * 2;
+                    acc[r0] += (uint32_t)rv.x; acc[r0 + 1] += (uint32_t)rv.y;
+                }
+        }
+        int4 ch[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ch[k] = lds128_ro(lt.chan_addr + (uint32_t)(c0 + (k >> 1) * 8 + j2 + (k & 1)) * 16);
+        int32_t o[16];
+        bool bad = false;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const int4 c = ch[quad_chn(r)];
+            int32_t v = (int32_t)acc[r] + c.x;
+            if (SLOPE) v = prelu_unit(v, u.slope, u.k24);
+            int64_t add;
+            if (SGN == SGN_LO0) {
+                add = (int64_t)(uint64_t)(u.c0_lo + (uint32_t)(v >> 31));
+            } else if (SGN == SGN_HI0) {
+                const uint32_t sx = (uint32_t)(v >> 31);
+                add = pack64(sx, u.c0_hi + sx);
+            } else {
+                add = pack64(v < c.z ? u.c0_lo - 1u : u.c0_lo, u.c0_hi);
+            }
+            const int64_t t = mad_wide(v, c.y, add);
+            const uint32_t lo = (uint32_t)t, hi = (uint32_t)((uint64_t)t >> 32);
+            if (SGN == SGN_LO0 || SGN == SGN_THR_LO) {
+                o[r] = (int32_t)__funnelshift_rc(lo, hi, u.shift);
+                bad |= hi + u.ovf_add > u.ovf_lim;
+            } else {
+                o[r] = (int32_t)hi >> (u.shift - 32);
+            }
+        }
+        if (SGN == SGN_LO0 || SGN == SGN_THR_LO) {
+            if (__any_sync(0xffffffffu, bad)) {  // warp-uniform, rare: exact per-column redo in the row-per-lane layout
+                lean_redo_chunk<FPCC_OUT_I32, SLOPE>(lt, u, c0, zp, ep);
+                continue;
+            }
+        }
+        if (ep.residual) {
+            int2 rr[8];
+            if (res_pf) {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) rr[t] = rcur[t];
+            } else {
+                load_res(c0, rr);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    const int r0 = (i >> 1) * 8 + b * 4 + (i & 1) * 2;
+                    o[r0] = (int32_t)((uint32_t)o[r0] + (uint32_t)rr[i * 2 + b].x);  // int32 add wraps
+                    o[r0 + 1] = (int32_t)((uint32_t)o[r0 + 1] + (uint32_t)rr[i * 2 + b].y);
+                }
+            if (lt.has_post) {
+#pragma unroll
+                for (int r = 0; r < 16; ++r) o[r] = prelu_unit(o[r], u.post, u.k24);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const int r0 = (i >> 1) * 8 + b * 4 + (i & 1) * 2;
+                if (qr.off[i] >= 0) *reinterpret_cast<int2 *>(out + qr.off[i] + c0 + 8 * b + j2) = make_int2(o[r0], o[r0 + 1]);
+            }
+    }
+    __syncwarp();
+}
+
+template <bool SLOPE, bool RESPF>
+__device__ __forceinline__ void quad_tile_sgn(const LeanTile &lt, const QuadRows &qr, const LeanU &u, int64_t zp, int sgn,
+                                              const EpiParams &ep, int32_t *out) {
+    if (sgn == SGN_LO0) quad_tile<SLOPE, SGN_LO0, RESPF>(lt, qr, u, zp, ep, out);
+    else if (sgn == SGN_HI0) quad_tile<SLOPE, SGN_HI0, RESPF>(lt, qr, u, zp, ep, out);
+    else if (sgn == SGN_THR_HI) quad_tile<SLOPE, SGN_THR_HI, RESPF>(lt, qr, u, zp, ep, out);
+    else quad_tile<SLOPE, SGN_THR_LO, RESPF>(lt, qr, u, zp, ep, out);
+}
+
 // ---- floating-point epilogue (kind::f16 path): v = acc + bias; act; [+ residual; post act]; cast -------------
 // act codes: 0 none, 1 relu, 2 leaky-relu / PReLU with one slope.  out_type: 0 fp16, 1 bf16, 2 fp32.
 struct FEpi {
@@ -691,7 +834,12 @@ __device__ __forceinline__ void pairs_tile_lookup(const TcArgs &a, int tile_m, P
 
 // KIND: 0 = int8 x int8 -> int32 (kind::i8, integer requant epilogue), 1 = fp16, 2 = bf16 (kind::f16, fp32
 // accumulation, floating-point epilogue).  a.K is the contraction length in BYTES in every case.
-template <int MODE, int STAGES, int KIND, int EW>
+// OUTK: which integer epilogue a kernel instance carries (chosen on the host from the epilogue descriptor).  One
+// instance per output kind keeps the register allocation and the spills of each epilogue separate: with every path in
+// one body the int8 linears lost 30 % to the pressure of the int32 quad code.
+enum { OK_I8 = 0, OK_I16 = 1, OK_I32 = 2, OK_POST2 = 3 };
+
+template <int MODE, int STAGES, int KIND, int EW, int OUTK>
 __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_tc_persistent(TcArgs a, const __grid_constant__ CUtensorMap tmap_w,
                                                                     EpiParams ep, FEpi fe, void *__restrict__ out, int tiles_m,
                                                                     int tiles_n) {
@@ -966,7 +1114,7 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
             lu.ovf_lim = shift <= 31 ? (1u << shift) - 1u : 0xffffffffu;
         }
         lu.post2_addr = smem_u32(thr_s + 4);
-        const bool post2_on = KIND == 0 && ep.post_mul != nullptr;
+        const bool post2_on = KIND == 0 && OUTK == OK_POST2;
         int j = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
             const int slot = j & 1;
@@ -1002,25 +1150,43 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
             mbar_wait(&tmem_full[slot], (j >> 1) & 1);
             tc_fence_after();
             const uint32_t tacc = tmem_base + (uint32_t)(slot * a.tmem_cols) + ((uint32_t)(quarter * 32) << 16);
-            const bool lean = KIND == 0 && out_al && (a.N & 15) == 0 && *(volatile uint32_t *)lean_off == 0u && !(post2_on && has_slope);
+            const bool lean = KIND == 0 && OUTK != OK_I16 && out_al && (a.N & 15) == 0 && *(volatile uint32_t *)lean_off == 0u && !(post2_on && has_slope);
             if (KIND == 0 && lean) {
                 LeanTile lt;
-                lt.tacc = tacc; lt.chan_addr = smem_u32(chan4_s); lt.c_begin = c_begin; lt.c_end = c_end; lt.ncols = a.N - n0;
+                lt.tacc = tacc; lt.chan_addr = smem_u32(chan4_s); lt.c_begin = c_begin; lt.c_end = c_end; lt.ncols = a.N - n0; lt.n0 = n0; lt.ncols_total = a.N;
                 lt.have_acc = have_acc; lt.row_ok = row_ok; lt.has_post = has_post;
                 const int64_t row0 = row_ok ? m * a.N + n0 : 0;
                 lt.orow = (char *)out + row0 * ((ep.out_type == FPCC_OUT_I8 || post2_on) ? 1 : 4);
                 lt.rb_row = ep.row_bias ? ep.row_bias + (row_ok ? (int64_t)__ldg(&ep.row_idx[m]) * a.N + n0 : 0) : nullptr;
                 lt.res_row = ep.residual ? ep.residual + row0 : nullptr;
-                if (ep.out_type == FPCC_OUT_I8) {
+                if (OUTK == OK_I8) {
                     if (has_slope) lean_tile_sgn<FPCC_OUT_I8, true, false, false, false>(lt, lu, zp, sgn_mode, ep);
                     else lean_tile_sgn<FPCC_OUT_I8, false, false, false, false>(lt, lu, zp, sgn_mode, ep);
-                } else if (!post2_on) {
-                    if (has_slope) lean_tile_sgn<FPCC_OUT_I32, true, false, false, false>(lt, lu, zp, sgn_mode, ep);
-                    else lean_tile_sgn<FPCC_OUT_I32, false, false, false, MODE == 0>(lt, lu, zp, sgn_mode, ep);
-                } else if (ep.post_slope2 != nullptr) {  // selection linears of the multi-step predictors: no PReLU of their own
-                    lean_tile_sgn<FPCC_OUT_I32, false, true, true, false>(lt, lu, zp, sgn_mode, ep);
-                } else {
-                    lean_tile_sgn<FPCC_OUT_I32, false, true, false, false>(lt, lu, zp, sgn_mode, ep);
+                } else if (OUTK == OK_I32) {
+                    // int32 rows: quad layout (whole sectors per access); rows q, q+8, q+16, q+24 of the warp's quarter
+                    QuadRows qr;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int rr = quarter * 32 + (lane >> 2) + 8 * i;
+                        int64_t mm;
+                        bool ok;
+                        if (MODE == 0) {
+                            const int64_t mti = (int64_t)tile_m * TC_M + rr;
+                            ok = mti < a.n_out;
+                            mm = (a.row_perm && ok) ? (int64_t)__ldg(&a.row_perm[mti]) : mti;
+                        } else {
+                            mm = (int64_t)rows[TC_M + rr];
+                            ok = mm >= 0;
+                        }
+                        qr.off[i] = ok ? mm * a.N + n0 : -1;
+                        qr.rb[i] = (ep.row_bias && ok) ? (int32_t)__ldg(&ep.row_idx[mm]) : 0;
+                    }
+                    if (has_slope) quad_tile_sgn<true, false>(lt, qr, lu, zp, sgn_mode, ep, (int32_t *)out);
+                    else quad_tile_sgn<false, MODE == 0>(lt, qr, lu, zp, sgn_mode, ep, (int32_t *)out);
+                } else if (OUTK == OK_POST2) {
+                    // selection linears of the multi-step predictors / conv2 of a ResBlock: no PReLU of their own
+                    if (ep.post_slope2 != nullptr) lean_tile_sgn<FPCC_OUT_I32, false, true, true, false>(lt, lu, zp, sgn_mode, ep);
+                    else lean_tile_sgn<FPCC_OUT_I32, false, true, false, false>(lt, lu, zp, sgn_mode, ep);
                 }
             } else
             for (int c0 = c_begin; c0 < c_end; c0 += EC) {
@@ -1056,8 +1222,8 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
                 Post2 p2;
                 p2.on = false;
                 if (post2_on) p2 = load_post2(ep);
-                if (ep.out_type == FPCC_OUT_I8) epi_dispatch<FPCC_OUT_I8>(acc, cx, optr, vec, has_slope, rb, p2);
-                else if (ep.out_type == FPCC_OUT_I32) epi_dispatch<FPCC_OUT_I32>(acc, cx, optr, vec, has_slope, rb, p2);
+                if (OUTK == OK_I8) epi_dispatch<FPCC_OUT_I8>(acc, cx, optr, vec, has_slope, rb, p2);
+                else if (OUTK == OK_I32 || OUTK == OK_POST2) epi_dispatch<FPCC_OUT_I32>(acc, cx, optr, vec, has_slope, rb, p2);
                 else epi_dispatch<FPCC_OUT_I16>(acc, cx, optr, vec, has_slope, rb, p2);
             }
             tc_fence_before();
@@ -1179,13 +1345,11 @@ static int pick_tile(int N, int *n_tile, int *tmem_cols) {
 }
 
 constexpr size_t TC_SMEM_MAX = 227 * 1024;
-template <int MODE, int STAGES, int KIND>
-static int launch_stages(const TcArgs &a, const CUtensorMap &tmap, const EpiParams &ep, const FEpi &fe, void *out, int tiles_m,
-                         int n_blocks_n, int grid, int rows_k, cudaStream_t s) {
-    size_t smem = PSmem<STAGES>::bytes(a.n_tile, rows_k);
-    FPCC_REQUIRE(smem <= TC_SMEM_MAX, "igemm_tc: %zu bytes of shared memory exceed the 227 KB limit", smem);
+template <int MODE, int STAGES, int KIND, int OUTK>
+static int launch_outk(const TcArgs &a, const CUtensorMap &tmap, const EpiParams &ep, const FEpi &fe, void *out, int tiles_m,
+                       int n_blocks_n, int grid, size_t smem, cudaStream_t s) {
     constexpr int EW = MODE == 0 ? EPI_WARPS_CONV : EPI_WARPS_PAIRS;
-    auto kern = igemm_tc_persistent<MODE, STAGES, KIND, EW>;
+    auto kern = igemm_tc_persistent<MODE, STAGES, KIND, EW, (KIND == 0 ? OUTK : OK_I8)>;
     static bool configured = false;
     if (!configured) {
         FPCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX));
@@ -1194,6 +1358,18 @@ static int launch_stages(const TcArgs &a, const CUtensorMap &tmap, const EpiPara
     kern<<<grid, (EW + prod_warps<MODE>() + 2) * 32, smem, s>>>(a, tmap, ep, fe, out, tiles_m, n_blocks_n);
     FPCC_LAUNCH_CHECK();
     return FPCC_OK;
+}
+
+template <int MODE, int STAGES, int KIND>
+static int launch_stages(const TcArgs &a, const CUtensorMap &tmap, const EpiParams &ep, const FEpi &fe, void *out, int tiles_m,
+                         int n_blocks_n, int grid, int rows_k, cudaStream_t s) {
+    size_t smem = PSmem<STAGES>::bytes(a.n_tile, rows_k);
+    FPCC_REQUIRE(smem <= TC_SMEM_MAX, "igemm_tc: %zu bytes of shared memory exceed the 227 KB limit", smem);
+    if (KIND != 0) return launch_outk<MODE, STAGES, KIND, OK_I8>(a, tmap, ep, fe, out, tiles_m, n_blocks_n, grid, smem, s);
+    if (ep.post_mul) return launch_outk<MODE, STAGES, KIND, OK_POST2>(a, tmap, ep, fe, out, tiles_m, n_blocks_n, grid, smem, s);
+    if (ep.out_type == FPCC_OUT_I8) return launch_outk<MODE, STAGES, KIND, OK_I8>(a, tmap, ep, fe, out, tiles_m, n_blocks_n, grid, smem, s);
+    if (ep.out_type == FPCC_OUT_I32) return launch_outk<MODE, STAGES, KIND, OK_I32>(a, tmap, ep, fe, out, tiles_m, n_blocks_n, grid, smem, s);
+    return launch_outk<MODE, STAGES, KIND, OK_I16>(a, tmap, ep, fe, out, tiles_m, n_blocks_n, grid, smem, s);
 }
 
 template <int MODE, int KIND>

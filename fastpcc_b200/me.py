@@ -39,6 +39,57 @@ class RegionType(Enum):
     HYPER_CUBE = 0
 
 
+class SparseTensorOperationMode(Enum):
+    SEPARATE_COORDINATE_MANAGER = 0
+    SHARE_COORDINATE_MANAGER = 1
+
+
+class MinkowskiAlgorithm(Enum):
+    DEFAULT = 0
+    MEMORY_EFFICIENT = 1
+    SPEED_OPTIMIZED = 2
+
+
+class CoordinateMapType(Enum):
+    CPU = 0
+    CUDA = 1
+
+
+# ME's process-wide state (lossy_coord_v2/model.py:35,127-135,200-206): with SHARE_COORDINATE_MANAGER a SparseTensor
+# built without an explicit manager joins the global one
+_OPERATION_MODE = SparseTensorOperationMode.SEPARATE_COORDINATE_MANAGER
+_GLOBAL_CM = None
+
+
+def set_sparse_tensor_operation_mode(mode: SparseTensorOperationMode):
+    global _OPERATION_MODE
+    _OPERATION_MODE = mode
+
+
+def sparse_tensor_operation_mode():
+    return _OPERATION_MODE
+
+
+def set_global_coordinate_manager(cm):
+    global _GLOBAL_CM
+    _GLOBAL_CM = cm
+
+
+def global_coordinate_manager():
+    return _GLOBAL_CM
+
+
+def clear_global_coordinate_manager():
+    global _GLOBAL_CM
+    _GLOBAL_CM = None
+
+
+def _publish(t: torch.Tensor):
+    """a cached derived tensor may be read from another CUDA stream next: finish the kernels that fill it first"""
+    if t.is_cuda:
+        torch.cuda.current_stream(t.device).synchronize()
+
+
 class SparseTensorQuantizationMode(Enum):
     RANDOM_SUBSAMPLE = 0
     UNWEIGHTED_AVERAGE = 1
@@ -196,6 +247,10 @@ class SparseTensor:
     def __init__(self, features: torch.Tensor, coordinates: Optional[torch.Tensor] = None, tensor_stride=1,
                  coordinate_map_key: Optional[CoordinateMapKey] = None, coordinate_manager: Optional[CoordinateManager] = None,
                  quantization_mode=None, device=None, **_):
+        if coordinate_manager is None and coordinate_map_key is None and _OPERATION_MODE == SparseTensorOperationMode.SHARE_COORDINATE_MANAGER:
+            if _GLOBAL_CM is None:
+                set_global_coordinate_manager(CoordinateManager())
+            coordinate_manager = _GLOBAL_CM
         if coordinate_manager is None:
             coordinate_manager = CoordinateManager()
         if coordinate_map_key is None:
@@ -331,7 +386,7 @@ class _ConvBase(nn.Module):
             if self.bias is not None:
                 b = torch.zeros(cout_p, dtype=torch.float32, device=k.device)
                 b[:k.shape[2]] = self.bias.detach().reshape(-1).float()
-            torch.cuda.current_stream().synchronize()  # the cache may be read from another stream next
+            _publish(w)
             self._cache = (key, w, b, cin_p, cout_p)
         return self._cache[1:]
 
@@ -444,7 +499,7 @@ class MinkowskiLinear(nn.Module):
             if lin.bias is not None:
                 b = torch.zeros(cout_p, dtype=torch.float32, device=w.device)
                 b[:lin.out_features] = lin.bias.detach().float()
-            torch.cuda.current_stream().synchronize()  # the cache may be read from another stream next
+            _publish(w)
             self._cache = (key, w, b, cin_p, cout_p)
         _, w, b, cin_p, cout_p = self._cache
         f = _pad_cols(_as_compute(x.F), cin_p).contiguous()

@@ -106,3 +106,65 @@ def build_reference_model(ref, cfg, sd_np, device='cpu'):
     m.load_state_dict(sd, strict=False)
     m.eval()
     return m.to(device)
+
+
+LOSSY_V2_BASELINE_R1 = dict(  # config/convolutional/lossy_coord_v2/baseline_r1.yaml:2-14
+    activation='prelu', compressed_channels=(1,), skip_encoding_fea=1, encoder_channels=(16, 64), decoder_channels=(16,),
+    adaptive_pruning=True, geo_lossl_if_sample=(0, 1, 0, 1, 0, 1, 0, 1, 0, 1, 0, 1),
+    geo_lossl_channels=(64, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 1),
+    bits_loss_factor=0.4, warmup_fea_loss_steps=5000, warmup_fea_loss_factor=0.01)
+
+
+def import_reference_lossy_v2(ref_root, me_module, rans=None, morton_ext=None):
+    """-> the reference's UNMODIFIED `models.convolutional.lossy_coord_v2.model` (PCC: Encoder, GeoLosslessEntropyModel,
+    Decoder with top-k pruning; lossy_coord_v2/model.py:230-275, layers.py, lossy_coord_lossy_color/geo_lossl_em.py) and
+    its own lib/minkowski_sparse_conv_layers.py, running on `me_module` bound as `MinkowskiEngine`
+    (fastpcc_b200.me on the GPU, oracle.me_cpu.load() on the CPU).  `rans`: the reference's compiled rans_ext_cpp."""
+    if ref_root not in sys.path:
+        sys.path.insert(1, ref_root)
+    sys.modules['MinkowskiEngine'] = me_module
+    sub = types.ModuleType('MinkowskiEngine.MinkowskiSparseTensor')
+    sub.SparseTensorQuantizationMode = me_module.SparseTensorQuantizationMode
+    sub.SparseTensor = me_module.SparseTensor
+    sys.modules['MinkowskiEngine.MinkowskiSparseTensor'] = sub
+    for name in ('plyfile', 'open3d', 'cv2'):
+        if name not in sys.modules:
+            try:
+                importlib.import_module(name)
+            except ImportError:
+                m = types.ModuleType(name)
+                m.PlyData = m.PlyElement = object
+                sys.modules[name] = m
+    import torch.utils.cpp_extension as cpp_ext
+
+    def fake_load(name, *a, **kw):
+        if name == 'rans_ext_cpp':
+            return rans
+        if name == 'space_filling_curves_ext' and morton_ext is not None:
+            return morton_ext
+        return types.ModuleType(name)
+    cpp_ext.load = fake_load
+    # drop modules imported earlier against another backend (the importer may be used twice in one process)
+    for k in [k for k in sys.modules if k.startswith(('models.convolutional.lossy_coord', 'lib.minkowski_sparse_conv_layers'))]:
+        del sys.modules[k]
+    for _ in range(20):
+        try:
+            return importlib.import_module('models.convolutional.lossy_coord_v2.model')
+        except ModuleNotFoundError as e:
+            if e.name.split('.')[0] in ('lib', 'models'):
+                raise
+            sys.modules[e.name] = types.ModuleType(e.name)
+    raise RuntimeError('could not import the reference lossy_coord_v2 model')
+
+
+def build_reference_lossy_v2(ref, cfg_overrides, seed=0, device='cpu'):
+    """PCC(ModelConfig(**overrides)) with seeded parameters (there is no checkpoint offline): default torch init under
+    `seed`, eval mode."""
+    torch.manual_seed(seed)
+    cfg = ref.ModelConfig()
+    for k, v in cfg_overrides.items():
+        setattr(cfg, k, v)
+    cfg.check_local_value()
+    model = ref.PCC(cfg)
+    model.eval()
+    return model.to(device)
