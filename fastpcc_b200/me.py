@@ -159,7 +159,7 @@ class CoordinateManager:
         """Registers a coordinate set as given (the codecs pass unique, Morton-sorted coordinates,
         lossy_coord_v2/model.py:138-154).  Returns (key, (unique_index, inverse_index))."""
         assert coordinates.dtype == torch.int32 and coordinates.shape[1] == 4
-        key = self._new_key(tensor_stride, coordinates)
+        key = self._new_key(tensor_stride, coordinates, string_id)
         idx = torch.arange(coordinates.shape[0], device=coordinates.device)
         return key, (idx, idx)
 

@@ -166,5 +166,19 @@ def build_reference_lossy_v2(ref, cfg_overrides, seed=0, device='cpu'):
         setattr(cfg, k, v)
     cfg.check_local_value()
     model = ref.PCC(cfg)
+    # Seeded Kaiming-uniform weights and small random biases: with the shim's default init (or zero biases) the
+    # activations shrink layer by layer and every rounded residual is 0, a histogram the reference's own coder rejects
+    # (cdf_ops.cpp:29).  Generated on the CPU so that both backends get identical parameters.
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if 'bottom_fea_entropy_model' in name:
+                continue
+            if p.dim() >= 2 and p.shape[-2] * (p.shape[0] if p.dim() == 3 else 1) > 1:
+                fan_in = p.shape[-2] * (p.shape[0] if p.dim() == 3 else 1) if name.endswith('kernel') else p.shape[-1]
+                bound = (6.0 / fan_in) ** 0.5
+                p.copy_((torch.rand(p.shape, generator=g) * 2 - 1) * bound)
+            elif name.endswith('bias'):
+                p.copy_((torch.rand(p.shape, generator=g) * 2 - 1) * 0.1)
     model.eval()
     return model.to(device)
