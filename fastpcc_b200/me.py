@@ -396,10 +396,14 @@ class _ConvBase(nn.Module):
         if residual is not None:
             residual = _pad_cols(_as_compute(residual), cout_p).contiguous()
         kv = w.shape[0]
+        # single-channel heads (occupancy logits, top-k scores, the clipped bottom feature) keep the fp32 accumulator:
+        # rounded to fp16 they collide into ties that the codecs' `kthvalue` / `>` selections (lossy_coord_v2/layers.py:
+        # 166-176) and 16-bit probabilities (geo_lossl_em.py:95-99) would see
+        od = torch.float32 if (self.out_channels == 1 and residual is None) else None
         if kv == 1:
-            out = ops.linear_f16(f, w[0], bias=b, act=act, slope=slope, residual=residual)
+            out = ops.linear_f16(f, w[0], bias=b, act=act, slope=slope, residual=residual, out_dtype=od)
         else:
-            out = ops.spconv_f16(f, w, table, bias=b, act=act, slope=slope, residual=residual, row_perm=row_perm)
+            out = ops.spconv_f16(f, w, table, bias=b, act=act, slope=slope, residual=residual, row_perm=row_perm, out_dtype=od)
         return out[:, :self.out_channels] if cout_p != self.out_channels else out
 
 
@@ -503,7 +507,8 @@ class MinkowskiLinear(nn.Module):
             self._cache = (key, w, b, cin_p, cout_p)
         _, w, b, cin_p, cout_p = self._cache
         f = _pad_cols(_as_compute(x.F), cin_p).contiguous()
-        out = ops.linear_f16(f, w, bias=b, act=code, slope=slope)
+        od = torch.float32 if lin.out_features == 1 else None  # single-channel heads keep fp32 (see _ConvBase._run)
+        out = ops.linear_f16(f, w, bias=b, act=code, slope=slope, out_dtype=od)
         return x._like(out[:, :lin.out_features] if cout_p != lin.out_features else out)
 
 

@@ -27,8 +27,9 @@ from tests import ref_import  # noqa: E402
 from tests.golden.lossy_cases import CASES, case_cloud  # noqa: E402
 
 
-def stride2_sha(xyz):
-    c = np.unique(xyz // 2, axis=0)
+def stride2_sha(xyz, origin):
+    """occupied stride-2 cells on the codec's grid (coordinates relative to the cloud's minimum, model.py:231-232)"""
+    c = np.unique((xyz - origin) // 2, axis=0)
     return hashlib.sha256(np.ascontiguousarray(c.astype('<i4')).tobytes()).hexdigest(), int(c.shape[0])
 
 
@@ -50,7 +51,7 @@ def main():
     for case in CASES:
         xyz, data, rec = run_case(ref, case)
         err = metrics.pc_error(xyz, rec, 2 ** case['bits'])
-        sha, n2 = stride2_sha(xyz)
+        sha, n2 = stride2_sha(xyz, xyz.min(0))
         out['cases'].append({'name': case['name'], 'n_points': int(xyz.shape[0]), 'n_bytes': len(data),
                              'bpp': len(data) * 8 / xyz.shape[0], 'n_rec': int(rec.shape[0]),
                              'd1_psnr': err['mseF,PSNR (p2point)'], 'd1_mse1': err['mse1      (p2point)'],

@@ -46,4 +46,4 @@ def test_reference_lossy_v2_on_the_cpu_oracle_matches_its_fixture(tmp_path_facto
     err = metrics.pc_error(xyz, rec, 2 ** case['bits'])
     assert abs(err['mseF,PSNR (p2point)'] - g['d1_psnr']) < 1e-9
     # the entropy model codes the stride-2 geometry losslessly, and the top-k pruning keeps the best child of every cell
-    assert stride2_sha(rec)[0] == g['stride2_sha256'] == stride2_sha(xyz)[0]
+    assert stride2_sha(rec, xyz.min(0))[0] == g['stride2_sha256'] == stride2_sha(xyz, xyz.min(0))[0]
