@@ -64,6 +64,41 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "WAIT_DONE:\n\t"
         "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
 }
+// ---- 2-CTA cluster helpers (weight tiles shared by TMA multicast, see CL2 below) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t rank) {  // same offset in CTA `rank` of the cluster
+    uint32_t a;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(local_smem_addr), "r"(rank));
+    return a;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {  // acquire at cluster scope: sees the peer's DSMEM store
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAITC_LOOP:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra.uni WAITC_DONE;\n\t"
+        "bra.uni WAITC_LOOP;\n\t"
+        "WAITC_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t cta_mask) {  // arrives on `bar` of every CTA in the mask
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
@@ -130,6 +165,22 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
+#ifdef FPCC_TC_TRACE
+// Experiment builds only (build.build_variant(name, ['-DFPCC_TC_TRACE'])): CTA 0 writes globaltimer stamps of its roles
+// per tile into g_trace[tile_local][slot]; tools/trace_tiles.py reads them back through fpcc_trace_read.
+__device__ unsigned long long g_trace[4096][8];
+__device__ __forceinline__ void trace_stamp(int j, int slot) {
+    if (blockIdx.x == 0 && j < 4096) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_trace[j][slot] = t;
+    }
+}
+#define TRACE(j, slot) trace_stamp((j), (slot))
+#else
+#define TRACE(j, slot)
+#endif
+
 struct TcArgs {
     // common
     const int8_t *A;   // activations [*, K]
@@ -839,7 +890,12 @@ __device__ __forceinline__ void pairs_tile_lookup(const TcArgs &a, int tile_m, P
 // one body the int8 linears lost 30 % to the pressure of the int32 quad code.
 enum { OK_I8 = 0, OK_I16 = 1, OK_I32 = 2, OK_POST2 = 3 };
 
-template <int MODE, int STAGES, int KIND, int EW, int OUTK>
+// CL2 (sparse conv only): the kernel runs as clusters of two CTAs.  CTA r of cluster c works on tile 2p + r of the tile
+// pairs p = c, c + n_clusters, ...; both follow the UNION of their two tiles' offset masks (row grouping makes adjacent
+// tiles nearly equal), each loads HALF of every weight tile and TMA-multicasts it into both CTAs' shared memory, so the
+// L2->SM weight bytes -- 69 % of the operand traffic of the L2-bound conv -- halve.  A stage is free when BOTH CTAs'
+// MMAs have consumed it: every tcgen05.commit arrives on the `empty` barrier of both CTAs.
+template <int MODE, int STAGES, int KIND, int EW, int OUTK, bool CL2>
 __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_tc_persistent(TcArgs a, const __grid_constant__ CUtensorMap tmap_w,
                                                                     EpiParams ep, FEpi fe, void *__restrict__ out, int tiles_m,
                                                                     int tiles_n) {
@@ -859,23 +915,32 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
     uint64_t *bars = (uint64_t *)(thr_s + a.n_tile);
     uint64_t *full = bars, *empty = bars + STAGES;
     uint64_t *meta_full = bars + 2 * STAGES, *tmem_full = meta_full + 2, *tmem_empty = tmem_full + 2;
-    PMeta *meta = (PMeta *)(tmem_empty + 2);
+    uint64_t *xchg = tmem_empty + 2;  // CL2: the peer's offset mask of a tile pair has arrived
+    PMeta *meta = (PMeta *)(xchg + 2);
     uint32_t *tmem_ptr = (uint32_t *)(meta + 2);
     uint32_t *lean_off = tmem_ptr + 1;  // set once a staged channel block fails the lean-epilogue preconditions
+    uint32_t *peer_kmask = lean_off + 1;  // [2] CL2: written by the peer CTA through DSMEM
+    const uint32_t cl_rank = CL2 ? cluster_ctarank() : 0u;
+    // tile sequence of this CTA: p = p0, p0 + p_step, ... < p_end; tile = CL2 ? 2 p + rank : p
+    const int p0 = CL2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int p_step = CL2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_chunks = (a.K + TC_KB - 1) / TC_KB;
     const int total_tiles = tiles_m * tiles_n;
+    const int p_end = CL2 ? (total_tiles + 1) / 2 : total_tiles;
+#define FPCC_TILE_OF(p) (CL2 ? 2 * (p) + (int)cl_rank : (p))
 
     if (warp == P_MMA_WARP && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full[s], PT + 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], CL2 ? 2 : 1);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&meta_full[b], PT);
             mbar_init(&tmem_full[b], 1);
             mbar_init(&tmem_empty[b], P_EPI_WARPS);
+            mbar_init(&xchg[b], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -917,6 +982,7 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (CL2) cluster_sync_all();  // the peer's barriers are initialised before any remote arrive / multicast write
     const uint32_t tmem_base = *tmem_ptr;
 
     if (warp >= P_PROD_WARP0 && warp < P_PROD_WARP0 + PW) {
@@ -935,12 +1001,15 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
 #pragma unroll
             for (int u = 0; u < PRE; ++u) nv[u] = (ok && u < a.kvol) ? __ldg(&a.nbr[(int64_t)u * a.ld + m]) : 0;
         };
-        if (pre) fetch(blockIdx.x);
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
+        if (pre) fetch(FPCC_TILE_OF(p0));
+        for (int p = p0; p < p_end; p += p_step, ++j) {
+            const int tile = FPCC_TILE_OF(p);
             const int slot = j & 1;
             const int tile_m = tile / tiles_n;
             int32_t *rows = rows_s + slot * rows_k * TC_M;
+            if (r == 0) TRACE(j, 0);
             mbar_wait(&tmem_empty[slot], ((j >> 1) & 1) ^ 1);  // slot's previous tile (j-2) fully consumed
+            if (r == 0) TRACE(j, 1);
             if (r == 0) meta[slot].kmask = 0;
             asm volatile("bar.sync 1, %0;" ::"n"(PT) : "memory");
             if (MODE == 0) {
@@ -953,7 +1022,7 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
                             rows[u * TC_M + r] = nv[u] - 1;
                             mine |= (uint32_t)(nv[u] != 0) << u;
                         }
-                    fetch(tile + gridDim.x);
+                    fetch(FPCC_TILE_OF(p + p_step));
                 } else {
                     for (int k = 0; k < a.kvol; ++k) {
                         int32_t v = m < a.n_out ? __ldg(&a.nbr[(int64_t)k * a.ld + m]) : 0;
@@ -982,12 +1051,25 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
 #endif
                 if (r == 0) meta[slot].kmask = meta[slot].begin >= 0 && meta[slot].begin < meta[slot].end ? 1u : 0u;
             }
+            if (CL2) {
+                // union of the pair's offset masks: own mask -> peer (DSMEM store + remote arrive), wait for the peer's
+                asm volatile("bar.sync 1, %0;" ::"n"(PT) : "memory");  // every warp's atomicOr has landed
+                if (r == 0) {
+                    const uint32_t own = *(volatile uint32_t *)&meta[slot].kmask;
+                    const uint32_t peer = cl_rank ^ 1u;
+                    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(mapa_u32(smem_u32(&peer_kmask[slot]), peer)), "r"(own) : "memory");
+                    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa_u32(smem_u32(&xchg[slot]), peer)) : "memory");
+                    mbar_wait_cluster(&xchg[slot], (j >> 1) & 1);
+                    meta[slot].kmask = own | *(volatile uint32_t *)&peer_kmask[slot];
+                }
+            }
             __threadfence_block();
             mbar_arrive(&meta_full[slot]);
             mbar_wait(&meta_full[slot], (j >> 1) & 1);
             uint32_t rem = meta[slot].kmask;
             const int total = __popc(rem) * n_chunks;
             int k = 0, kc = n_chunks - 1;
+            if (r == 0) TRACE(j, 2);
             for (int i = 0; i < total; ++i, ++it) {
                 if (++kc == n_chunks) { kc = 0; k = __ffs(rem) - 1; rem &= rem - 1; }
                 const int stage = it % STAGES;
@@ -1044,7 +1126,8 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
         // ================= weight producer (TMA) =================
         if (lane == 0) {
             int it = 0, j = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
+            for (int p = p0; p < p_end; p += p_step, ++j) {
+                const int tile = FPCC_TILE_OF(p);
                 const int slot = j & 1;
                 const int n0 = (tile % tiles_n) * a.n_tile;
                 mbar_wait(&meta_full[slot], (j >> 1) & 1);
@@ -1058,7 +1141,13 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
                     mbar_wait(&empty[stage], ((it / STAGES) & 1) ^ 1);
                     mbar_expect_tx(&full[stage], (uint32_t)b_bytes);
                     const int wrow = (MODE == 0 ? k : group) * a.N + n0;
-                    tma_load_2d(smem_u32(sB + (size_t)stage * b_bytes), &tmap_w, &full[stage], kc * TC_KB, wrow);
+                    if (CL2) {  // this CTA's half of the weight tile, into both CTAs (the peer sends the other half)
+                        const int half = a.n_tile >> 1;
+                        tma_load_2d_mc(smem_u32(sB + (size_t)stage * b_bytes + (size_t)cl_rank * half * TC_KB), &tmap_w, &full[stage],
+                                       kc * TC_KB, wrow + (int)cl_rank * half, (uint16_t)3);
+                    } else {
+                        tma_load_2d(smem_u32(sB + (size_t)stage * b_bytes), &tmap_w, &full[stage], kc * TC_KB, wrow);
+                    }
                 }
             }
         }
@@ -1067,7 +1156,7 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
         if (lane == 0) {
             const uint32_t idesc = KIND == 0 ? umma_idesc_i8(a.n_tile) : umma_idesc_f16(a.n_tile, KIND == 2);
             int it = 0, j = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
+            for (int p = p0; p < p_end; p += p_step, ++j) {
                 const int slot = j & 1;
                 mbar_wait(&meta_full[slot], (j >> 1) & 1);
                 const int total = __popc(meta[slot].kmask) * n_chunks;
@@ -1077,6 +1166,7 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
                 for (int i = 0; i < total; ++i, ++it) {
                     const int stage = it % STAGES;
                     mbar_wait(&full[stage], (it / STAGES) & 1);
+                    if (i == 0) TRACE(j, 3);
                     fence_proxy_async();  // the gathered rows were written through the generic proxy (cp.async)
                     tc_fence_after();
                     const uint64_t ad = umma_desc_sw128(smem_u32(sA + stage * a_bytes));
@@ -1088,8 +1178,10 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
                             else umma_f16(tacc, ad + 2 * q, bd + 2 * q, idesc, (uint32_t)(i > 0 || q > 0));
                         }
                     }
-                    umma_commit(&empty[stage]);
+                    if (CL2) umma_commit_mc(&empty[stage], (uint16_t)3);  // the stage is free once BOTH CTAs consumed it
+                    else umma_commit(&empty[stage]);
                 }
+                TRACE(j, 4);
                 if (total > 0) umma_commit(&tmem_full[slot]);
                 else mbar_arrive(&tmem_full[slot]);
             }
@@ -1116,7 +1208,8 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
         lu.post2_addr = smem_u32(thr_s + 4);
         const bool post2_on = KIND == 0 && OUTK == OK_POST2;
         int j = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
+        for (int p = p0; p < p_end; p += p_step, ++j) {
+            const int tile = FPCC_TILE_OF(p);
             const int slot = j & 1;
             const int tile_m = tile / tiles_n, n0 = (tile % tiles_n) * a.n_tile;
             mbar_wait(&meta_full[slot], (j >> 1) & 1);
@@ -1149,6 +1242,7 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
             }
             mbar_wait(&tmem_full[slot], (j >> 1) & 1);
             tc_fence_after();
+            if (tid == 0) TRACE(j, 5);
             const uint32_t tacc = tmem_base + (uint32_t)(slot * a.tmem_cols) + ((uint32_t)(quarter * 32) << 16);
             const bool lean = KIND == 0 && OUTK != OK_I16 && out_al && (a.N & 15) == 0 && *(volatile uint32_t *)lean_off == 0u && !(post2_on && has_slope);
             if (KIND == 0 && lean) {
@@ -1228,14 +1322,17 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
             }
             tc_fence_before();
             __syncwarp();
+            if (tid == 0) TRACE(j, 6);
             if (lane == 0) mbar_arrive(&tmem_empty[slot]);
         }
     }
     tc_fence_before();
     __syncthreads();
+    if (CL2) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it or arrive on its barriers
     if (warp == P_MMA_WARP) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * a.tmem_cols)) : "memory");
     }
+#undef FPCC_TILE_OF
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1347,45 +1444,81 @@ static int pick_tile(int N, int *n_tile, int *tmem_cols) {
 constexpr size_t TC_SMEM_MAX = 227 * 1024;
 template <int MODE, int STAGES, int KIND, int OUTK>
 static int launch_outk(const TcArgs &a, const CUtensorMap &tmap, const EpiParams &ep, const FEpi &fe, void *out, int tiles_m,
-                       int n_blocks_n, int grid, size_t smem, cudaStream_t s) {
+                       int n_blocks_n, int grid, size_t smem, bool cl2, cudaStream_t s) {
     constexpr int EW = MODE == 0 ? EPI_WARPS_CONV : EPI_WARPS_PAIRS;
-    auto kern = igemm_tc_persistent<MODE, STAGES, KIND, EW, (KIND == 0 ? OUTK : OK_I8)>;
+    constexpr int OK = KIND == 0 ? OUTK : OK_I8;
+    constexpr int THREADS = (EW + prod_warps<MODE>() + 2) * 32;
+    if (MODE == 0 && KIND == 0 && cl2) {  // 2-CTA clusters sharing every weight tile (see CL2 at the kernel)
+        auto kern = igemm_tc_persistent<MODE, STAGES, KIND, EW, OK, (MODE == 0 && KIND == 0)>;
+        static bool configured = false;
+        if (!configured) {
+            FPCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX));
+            configured = true;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        FPCC_CUDA(cudaLaunchKernelEx(&cfg, kern, a, tmap, ep, fe, out, tiles_m, n_blocks_n));
+        return FPCC_OK;
+    }
+    auto kern = igemm_tc_persistent<MODE, STAGES, KIND, EW, OK, false>;
     static bool configured = false;
     if (!configured) {
         FPCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX));
         configured = true;
     }
-    kern<<<grid, (EW + prod_warps<MODE>() + 2) * 32, smem, s>>>(a, tmap, ep, fe, out, tiles_m, n_blocks_n);
+    kern<<<grid, THREADS, smem, s>>>(a, tmap, ep, fe, out, tiles_m, n_blocks_n);
     FPCC_LAUNCH_CHECK();
     return FPCC_OK;
 }
 
 template <int MODE, int STAGES, int KIND>
 static int launch_stages(const TcArgs &a, const CUtensorMap &tmap, const EpiParams &ep, const FEpi &fe, void *out, int tiles_m,
-                         int n_blocks_n, int grid, int rows_k, cudaStream_t s) {
+                         int n_blocks_n, int grid, int rows_k, bool cl2, cudaStream_t s) {
     size_t smem = PSmem<STAGES>::bytes(a.n_tile, rows_k);
     FPCC_REQUIRE(smem <= TC_SMEM_MAX, "igemm_tc: %zu bytes of shared memory exceed the 227 KB limit", smem);
-    if (KIND != 0) return launch_outk<MODE, STAGES, KIND, OK_I8>(a, tmap, ep, fe, out, tiles_m, n_blocks_n, grid, smem, s);
-    if (ep.post_mul) return launch_outk<MODE, STAGES, KIND, OK_POST2>(a, tmap, ep, fe, out, tiles_m, n_blocks_n, grid, smem, s);
-    if (ep.out_type == FPCC_OUT_I8) return launch_outk<MODE, STAGES, KIND, OK_I8>(a, tmap, ep, fe, out, tiles_m, n_blocks_n, grid, smem, s);
-    if (ep.out_type == FPCC_OUT_I32) return launch_outk<MODE, STAGES, KIND, OK_I32>(a, tmap, ep, fe, out, tiles_m, n_blocks_n, grid, smem, s);
-    return launch_outk<MODE, STAGES, KIND, OK_I16>(a, tmap, ep, fe, out, tiles_m, n_blocks_n, grid, smem, s);
+    if (KIND != 0) return launch_outk<MODE, STAGES, KIND, OK_I8>(a, tmap, ep, fe, out, tiles_m, n_blocks_n, grid, smem, cl2, s);
+    if (ep.post_mul) return launch_outk<MODE, STAGES, KIND, OK_POST2>(a, tmap, ep, fe, out, tiles_m, n_blocks_n, grid, smem, cl2, s);
+    if (ep.out_type == FPCC_OUT_I8) return launch_outk<MODE, STAGES, KIND, OK_I8>(a, tmap, ep, fe, out, tiles_m, n_blocks_n, grid, smem, cl2, s);
+    if (ep.out_type == FPCC_OUT_I32) return launch_outk<MODE, STAGES, KIND, OK_I32>(a, tmap, ep, fe, out, tiles_m, n_blocks_n, grid, smem, cl2, s);
+    return launch_outk<MODE, STAGES, KIND, OK_I16>(a, tmap, ep, fe, out, tiles_m, n_blocks_n, grid, smem, cl2, s);
+}
+
+// Measured on B200 (391 k rows, C = 256, grouped 3x3x3): 0.222 ms with the clusters against 0.199 ms without -- the
+// lock-step of the pair costs more than the halved weight reads save (the conv is not L2->SM bandwidth bound after all).
+// Kept as an experiment: FPCC_CL2=1 selects it, the default is off.
+static int g_cl2_mode = -1;  // -1: read FPCC_CL2 from the environment on first use
+static bool cl2_enabled() {
+    if (g_cl2_mode < 0) {
+        const char *e = getenv("FPCC_CL2");
+        g_cl2_mode = (e && e[0] == '1') ? 1 : 0;
+    }
+    return g_cl2_mode == 1;
 }
 
 template <int MODE, int KIND>
 static int launch_tc(TcArgs &a, const void *W, int64_t w_rows, int tiles_m, const EpiParams &ep, const FEpi &fe, void *out,
                      cudaStream_t s) {
     int n_blocks_n = pick_tile(a.N, &a.n_tile, &a.tmem_cols);
-    CUtensorMap tmap;
-    int rc = weight_tensor_map((const int8_t *)W, w_rows, a.K, a.n_tile, &tmap);
-    if (rc) return rc;
     const int rows_k = MODE == 0 ? a.kvol : 2;
     int total = tiles_m * n_blocks_n;
     int sms = g_sm_budget > 0 && g_sm_budget < sm_count() ? g_sm_budget : sm_count();
+    // int8 sparse conv with one channel block and enough tiles: 2-CTA clusters, each CTA loads half of a weight tile
+    const bool cl2 = MODE == 0 && KIND == 0 && n_blocks_n == 1 && (a.n_tile % 16) == 0 && total >= 4 && sms >= 2 && cl2_enabled();
+    CUtensorMap tmap;
+    int rc = weight_tensor_map((const int8_t *)W, w_rows, a.K, cl2 ? a.n_tile / 2 : a.n_tile, &tmap);
+    if (rc) return rc;
     int grid = total < sms ? total : sms;
+    if (cl2) {
+        const int pairs = (total + 1) / 2, clusters = sms / 2;
+        grid = 2 * (pairs < clusters ? pairs : clusters);
+    }
     if (PSmem<4>::bytes(a.n_tile, rows_k) <= TC_SMEM_MAX)
-        return launch_stages<MODE, 4, KIND>(a, tmap, ep, fe, out, tiles_m, n_blocks_n, grid, rows_k, s);
-    return launch_stages<MODE, 3, KIND>(a, tmap, ep, fe, out, tiles_m, n_blocks_n, grid, rows_k, s);
+        return launch_stages<MODE, 4, KIND>(a, tmap, ep, fe, out, tiles_m, n_blocks_n, grid, rows_k, cl2, s);
+    return launch_stages<MODE, 3, KIND>(a, tmap, ep, fe, out, tiles_m, n_blocks_n, grid, rows_k, cl2, s);
 }
 
 int launch_conv_tc(const int8_t *feats, int n_in, int c_in, const int8_t *weight, int kvol, int c_out, const int32_t *nbr,
@@ -1488,6 +1621,14 @@ extern "C" int fpcc_mma_i8_peak(int iters, int n, double *tops_out, void *stream
     *tops_out = 2.0 * TC_M * n * 32.0 * 4.0 * iters * sms / (ms * 1e-3) / 1e12;
     return FPCC_OK;
 }
+
+#ifdef FPCC_TC_TRACE
+extern "C" int fpcc_trace_read(unsigned long long *host, int n) {
+    FPCC_CUDA(cudaDeviceSynchronize());
+    FPCC_CUDA(cudaMemcpyFromSymbol(host, fpcc::g_trace, sizeof(unsigned long long) * 8 * (size_t)n));
+    return FPCC_OK;
+}
+#endif
 
 extern "C" int fpcc_gemm_engine(int k, int n, int kvol, int has_zp_comp) {
     return fpcc::tc_enabled() && !has_zp_comp && k >= 32 && k % 16 == 0 && n >= 16 && kvol <= fpcc::TC_MAX_KVOL;
