@@ -196,7 +196,11 @@ def main():
 
     G = args.groups
 
+    pipe = os.environ.get('FPCC_BENCH_PIPE', '1') != '0'  # per-group encode -> decode pipelines (Model.roundtrip_batch)
+
     def step_device():
+        if pipe:
+            return model.roundtrip_batch(frames_dev, n_groups=G)[1]
         data = model.compress_batch(frames_dev, n_groups=G)  # one rANS stream per frame; G slices coded concurrently
         return model.decompress_batch(data, n_groups=G)
 
@@ -207,8 +211,11 @@ def main():
         nonlocal h2d, d2h
         h2d = d2h = 0
         xs = [p.to(dev, non_blocking=True) for p in pinned]
-        data = model.compress_batch(xs, n_groups=G)     # bytes on the host: D2H of the bitstreams inside
-        rec = model.decompress_batch(data, n_groups=G)  # H2D of the bitstreams inside
+        if pipe:
+            data, rec = model.roundtrip_batch(xs, n_groups=G)  # bytes on the host inside: D2H + H2D of every bitstream
+        else:
+            data = model.compress_batch(xs, n_groups=G)     # bytes on the host: D2H of the bitstreams inside
+            rec = model.decompress_batch(data, n_groups=G)  # H2D of the bitstreams inside
         # D2H of the decoded coordinates: one copy of the concatenated frames into a reused pinned buffer
         cat = torch.cat(rec)
         if host_out[0] is None or host_out[0].shape[0] < cat.shape[0]:
@@ -334,7 +341,7 @@ def main():
             'metric': 'encode+decode Mpts/s', 'value': pts_all / (ms_dev * 1e-3) / 1e6, 'unit': 'Mpts/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_dev,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int8', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'frames_per_step_per_gpu': args.frames, 'concurrent_groups': G, 'points_per_step': pts_all,
+            'config': {'workload': WORKLOAD, 'frames_per_step_per_gpu': args.frames, 'concurrent_groups': G, 'schedule': 'per-group encode->decode pipelines on prioritised streams' if pipe else 'all groups encode, then all groups decode', 'points_per_step': pts_all,
                        'l2': 'flushed between timed iterations (256 MB write)', 'weights': 'seeded random int8 (seed 7)',
                        'roundtrip_lossless': bool(lossless), 'parity_sample': parity,
                        'parity_note': 'bitstream of the CUDA codec == bitstream of the CPU oracle (pinned to the reference Python, '

@@ -32,6 +32,7 @@
 #include <tuple>
 
 #include "common.cuh"
+#include "epi_nt.cuh"
 
 namespace fpcc {
 
@@ -291,7 +292,20 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&acc)[EC], const EpiCt
     }
 }
 
-__device__ __forceinline__ int64_t mad_wide(int32_t a, int32_t b, int64_t c) {  // one IMAD.WIDE
+// a * b + c in 64 bits, two spellings (measured on B200, profiles/r02_epilogue_variants.txt):
+//   mad_wide_c   product pinned to mul.wide.s32, the sum written in C: ptxas picks the instruction from what is USED of the
+//                result -- IMAD.HI Rd, Ra, Rb, Rc.64 (high word of the full sum, ONE instruction) where only bits 32..63
+//                are consumed (every shift >= 32), IMAD.WIDE with the 64-bit addend as its C operand for the PReLU.
+//                int8 linears 0.087 -> 0.083 ms, with PReLU 0.110 -> 0.099 ms, int8 conv 0.198 -> 0.191 ms.
+//   mad_wide     inline mad.wide.s32: always IMAD.WIDE + IADD3 + IADD3.X.  Kept where BOTH words of the sum feed a funnel
+//                shift (shift < 32, the int32 outputs): there the one-instruction form measured slower (0.141 -> 0.153 ms).
+// (With a loop-invariant factor and a plain C product the front end hoists the sign extension and multiplies 64 x 64 bits.)
+__device__ __forceinline__ int64_t mad_wide_c(int32_t a, int32_t b, int64_t c) {
+    int64_t p;
+    asm("mul.wide.s32 %0, %1, %2;" : "=l"(p) : "r"(a), "r"(b));
+    return p + c;
+}
+__device__ __forceinline__ int64_t mad_wide(int32_t a, int32_t b, int64_t c) {
     int64_t d;
     asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
     return d;
@@ -315,8 +329,7 @@ __device__ __forceinline__ int64_t pack64(uint32_t lo, uint32_t hi) {
 // Q6.25 PReLU for 0 <= slope <= 2^25 (|result| <= |v|): rha(v*slope, 25) == (v*slope + 2^24 - 1) >> 25 for v < 0 (the product
 // is <= 0 there); for v >= 0 the same expression is <= v, so the PReLU is a plain max.
 __device__ __forceinline__ int32_t prelu_unit(int32_t v, int32_t slope, int64_t k24) {
-    const int64_t p = mad_wide(v, slope, k24);
-    return max(v, (int32_t)__funnelshift_r((uint32_t)p, (uint32_t)((uint64_t)p >> 32), 25));
+    return max(v, (int32_t)(mad_wide_c(v, slope, k24) >> 25));
 }
 
 template <int OUT>
@@ -413,7 +426,9 @@ struct LeanU {
     int shift;
     uint32_t ovf_add, ovf_lim;   // I32, shift < 32: the result fits iff (hi + ovf_add) <= ovf_lim (unsigned)
     uint32_t post2_addr;         // shared-space address of the staged second-stage constants (POST2 instantiations only):
-                                 // words {mul2, thr2, slope2, shift2 - 32, c02 lo, c02 hi},  c02 = zp2 + 2^(shift2 - 1)
+                                 // words {mul2, thr2, slope2, shift2 - 32, c02 lo, c02 hi, nt2},  c02 = zp2 + 2^(shift2 - 1),
+                                 // nt2 = 1 when the second stage cannot tie for any int32 input (no sign handling)
+    uint32_t nt_addr;            // shared-space address of the per-chunk tie-free flags (stage_nt_chunks)
     int64_t k24;                 // 2^24 - 1, read back from shared memory: ptxas splits an immediate or uniform 64-bit addend of
                                  // IMAD.WIDE into IADD3 + IMAD.X; a vector register pair stays the instruction's C operand
 };
@@ -461,6 +476,44 @@ __device__ __forceinline__ bool stage_channel(int32_t bias, uint32_t mul, int64_
     return ok;
 }
 
+// Measured on B200 (profiles/r02_epilogue_variants.txt): the per-chunk dispatch between the tie-free and the sign-exact body
+// costs more than the two instructions per element it saves (int8 linear 0.083 -> 0.096 ms: code size, spills at the
+// 80-register cap).  The first stage therefore keeps ONE sign-exact body; the flag remains a build-time experiment.  The
+// second stage of the fused [PReLU +] requant uses the tie analysis unconditionally (one CTA-uniform test, no extra body
+// per chunk).
+#ifndef FPCC_NT_SMEM
+#define FPCC_NT_SMEM 0
+#endif
+// Tie-free ("NT") chunks (epi_nt.cuh): when NO channel of a 16-channel chunk can produce a rounding tie inside the static
+// accumulator bound, rha(v*mul + zp, s) == (v*mul + zp + 2^(s-1)) >> s and the chunk needs no sign handling.  Called by a
+// whole warp for 32 consecutive channels (lane = channel; `valid` lanes hold a real channel, `ok` = the lean preconditions
+// of stage_channel hold); sets the per-chunk flags, the staged (bias, mul, thr) stay as they are.
+__device__ __forceinline__ void stage_nt_chunks(bool nt_on, bool valid, bool ok, int c, int32_t bias, uint32_t mul, int64_t zp, int shift,
+                                                int64_t abound, uint32_t *nt_flags) {
+    if (!nt_on) return;  // kernel-uniform
+    const int64_t ab = bias < 0 ? -(int64_t)bias : (int64_t)bias;
+    const bool nt = !valid || (ok && !tie_possible(mul, zp, shift, abound + ab));
+    const uint32_t b = __ballot_sync(0xffffffffu, nt);
+    const bool chunk_nt = ((b >> (threadIdx.x & 16)) & 0xffffu) == 0xffffu;
+    if (valid && (c & 15) == 0) nt_flags[c >> 4] = chunk_nt ? 1u : 0u;
+}
+
+// One tie-free chunk: (v * mul + c0) >> shift with the CTA-uniform c0 = zp + 2^(shift-1), no sign handling.  HI: shift >= 32
+// (arithmetic shift of the high word: one IMAD.HI + one SHF per element), else clamped funnel shift (shift <= 32).
+template <bool SLOPE, bool HI>
+__device__ __forceinline__ void lean_chunk_nt(const uint32_t (&acc)[EC], uint32_t chan_addr, const LeanU &u, int32_t (&o)[EC]) {
+    const int64_t c0 = pack64(u.c0_lo, u.c0_hi);
+#pragma unroll
+    for (int q = 0; q < EC; ++q) {
+        int32_t bias, mul;
+        asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(bias), "=r"(mul) : "r"(chan_addr + q * 16));
+        int32_t v = (int32_t)acc[q] + bias;
+        if (SLOPE) v = prelu_unit(v, u.slope, u.k24);
+        const int64_t t = HI ? mad_wide_c(v, mul, c0) : mad_wide(v, mul, c0);
+        o[q] = HI ? ((int32_t)(t >> 32) >> (u.shift - 32)) : (int32_t)__funnelshift_rc((uint32_t)t, (uint32_t)((uint64_t)t >> 32), u.shift);
+    }
+}
+
 template <int OUT, bool SLOPE, int SGN>
 __device__ __forceinline__ bool lean_chunk(const uint32_t (&acc)[EC], uint32_t chan_addr, const LeanU &u, int32_t (&o)[EC]) {
     bool bad = false;
@@ -478,7 +531,7 @@ __device__ __forceinline__ bool lean_chunk(const uint32_t (&acc)[EC], uint32_t c
         } else {
             add = pack64(v < ch.z ? u.c0_lo - 1u : u.c0_lo, u.c0_hi);
         }
-        const int64_t t = mad_wide(v, ch.y, add);
+        const int64_t t = (SGN == SGN_HI0 || SGN == SGN_THR_HI) ? mad_wide_c(v, ch.y, add) : mad_wide(v, ch.y, add);
         const uint32_t lo = (uint32_t)t, hi = (uint32_t)((uint64_t)t >> 32);
         int32_t r;
         if (SGN == SGN_LO0 || SGN == SGN_THR_LO) {
@@ -585,7 +638,16 @@ __device__ __forceinline__ void lean_tile(const LeanTile &lt, const LeanU &u, in
             }
         }
         int32_t o[EC];
-        const bool good = lean_chunk<OUT, SLOPE, SGN>(acc, lt.chan_addr + (uint32_t)c0 * 16, u, o);
+        bool good = true;
+        constexpr bool NT_ON = FPCC_NT_SMEM && OUT == FPCC_OUT_I8 && !POST2;  // tie-free chunks (stage_nt_chunks), warp-uniform per chunk
+        bool nt = false;
+        if (NT_ON) {
+            uint32_t f;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(f) : "r"(u.nt_addr + (uint32_t)(c0 >> 4) * 4));
+            nt = f != 0u;
+        }
+        if (NT_ON && nt) lean_chunk_nt<SLOPE, SGN == SGN_HI0 || SGN == SGN_THR_HI>(acc, lt.chan_addr + (uint32_t)c0 * 16, u, o);
+        else good = lean_chunk<OUT, SLOPE, SGN>(acc, lt.chan_addr + (uint32_t)c0 * 16, u, o);
         if (OUT == FPCC_OUT_I32 && (SGN == SGN_LO0 || SGN == SGN_THR_LO)) {
             if (__any_sync(0xffffffffu, !good)) {  // warp-uniform, rare
                 lean_redo_chunk<OUT, SLOPE>(lt, u, c0, zp, ep);
@@ -610,14 +672,31 @@ __device__ __forceinline__ void lean_tile(const LeanTile &lt, const LeanU &u, in
             }
             if (POST2) {
                 const int4 k2 = lds128(u.post2_addr);          // mul2, thr2, slope2, shift2 - 32
-                const int4 k3 = lds128(u.post2_addr + 16);     // c02 lo, c02 hi
+                const int4 k3 = lds128(u.post2_addr + 16);     // c02 lo, c02 hi, nt2
                 const int64_t c02 = pack64((uint32_t)k3.x, (uint32_t)k3.y), c02m1 = c02 - 1;
+#ifndef FPCC_NT2
+#define FPCC_NT2 1
+#endif
+                if (FPCC_NT2 && k3.z) {  // CTA-uniform: no int32 input can tie in the second stage, no sign handling
 #pragma unroll
-                for (int q = 0; q < EC; ++q) {
-                    int32_t y = o[q];
-                    if (SLOPE2) y = prelu_unit(y, k2.z, u.k24);
-                    const int64_t t2 = mad_wide(y, k2.x, y < k2.y ? c02m1 : c02);
-                    o[q] = (int32_t)((uint64_t)t2 >> 32) >> k2.w;
+                    for (int q = 0; q < EC; ++q) {
+                        int32_t y = o[q];
+                        if (SLOPE2) y = prelu_unit(y, k2.z, u.k24);
+                        const int64_t t2 = mad_wide_c(y, k2.x, c02);
+                        o[q] = (int32_t)((uint64_t)t2 >> 32) >> k2.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < EC; ++q) {
+                        int32_t y = o[q];
+                        if (SLOPE2) y = prelu_unit(y, k2.z, u.k24);
+#ifdef FPCC_POST2_ASM
+                        const int64_t t2 = mad_wide(y, k2.x, y < k2.y ? c02m1 : c02);
+#else
+                        const int64_t t2 = mad_wide_c(y, k2.x, y < k2.y ? c02m1 : c02);
+#endif
+                        o[q] = (int32_t)((uint64_t)t2 >> 32) >> k2.w;
+                    }
                 }
             } else {
                 uint4 *op = reinterpret_cast<uint4 *>(lt.orow + (size_t)c0 * esz);
@@ -734,7 +813,7 @@ __device__ __forceinline__ void quad_tile(const LeanTile &lt, const QuadRows &qr
             } else {
                 add = pack64(v < c.z ? u.c0_lo - 1u : u.c0_lo, u.c0_hi);
             }
-            const int64_t t = mad_wide(v, c.y, add);
+            const int64_t t = (SGN == SGN_HI0 || SGN == SGN_THR_HI) ? mad_wide_c(v, c.y, add) : mad_wide(v, c.y, add);
             const uint32_t lo = (uint32_t)t, hi = (uint32_t)((uint64_t)t >> 32);
             if (SGN == SGN_LO0 || SGN == SGN_THR_LO) {
                 o[r] = (int32_t)__funnelshift_rc(lo, hi, u.shift);
@@ -916,10 +995,12 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
     uint64_t *full = bars, *empty = bars + STAGES;
     uint64_t *meta_full = bars + 2 * STAGES, *tmem_full = meta_full + 2, *tmem_empty = tmem_full + 2;
     uint64_t *xchg = tmem_empty + 2;  // CL2: the peer's offset mask of a tile pair has arrived
-    PMeta *meta = (PMeta *)(xchg + 2);
+    uint64_t *meta_empty = xchg + 2;  // every reader of meta[slot] / rows[slot] of the slot's previous tile has taken its copy
+    PMeta *meta = (PMeta *)(meta_empty + 2);
     uint32_t *tmem_ptr = (uint32_t *)(meta + 2);
     uint32_t *lean_off = tmem_ptr + 1;  // set once a staged channel block fails the lean-epilogue preconditions
     uint32_t *peer_kmask = lean_off + 1;  // [2] CL2: written by the peer CTA through DSMEM
+    uint32_t *nt_flags = peer_kmask + 2;  // [16] tie-free flag of every 16-channel chunk of the staged block (stage_nt_chunks)
     const uint32_t cl_rank = CL2 ? cluster_ctarank() : 0u;
     // tile sequence of this CTA: p = p0, p0 + p_step, ... < p_end; tile = CL2 ? 2 p + rank : p
     const int p0 = CL2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -941,6 +1022,7 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
             mbar_init(&tmem_full[b], 1);
             mbar_init(&tmem_empty[b], P_EPI_WARPS);
             mbar_init(&xchg[b], 1);
+            mbar_init(&meta_empty[b], P_EPI_WARPS + 2);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -954,6 +1036,7 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
     const int64_t zp_all = KIND == 0 ? ep.zp[0] : 0;
     int64_t vmax = 0;
     const int sgn_mode = KIND == 0 ? lean_mode(ep, zp_all, (int64_t)a.K * (MODE == 0 ? a.kvol : 1), ep.row_bias_bound, &vmax) : SGN_NONE;
+    if (tid >= 32 && tid < 48) nt_flags[tid - 32] = 0u;
     if (tid == 0) {
         *lean_off = sgn_mode != SGN_NONE ? 0u : 1u;
         thr_s[0] = (1 << 24) - 1; thr_s[1] = 0;
@@ -966,16 +1049,27 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
             thr_s[5] = (int32_t)(t2 > 2147483647ll ? 2147483647ll : (t2 < -2147483648ll ? -2147483648ll : t2));
             thr_s[6] = p2.slope; thr_s[7] = p2.shift >= 32 ? p2.shift - 32 : 0;
             thr_s[8] = (int32_t)(uint32_t)c02; thr_s[9] = (int32_t)(uint32_t)((uint64_t)c02 >> 32);
+            thr_s[10] = (p2.shift >= 32 && !tie_possible(p2.mul, p2.zp, p2.shift, (int64_t)1 << 31)) ? 1 : 0;
         }
     }
     __syncthreads();
+    // tie-free chunks: int8-output instances on the lean path (the int32 first stages sit at shifts 5..16 where ties are common)
+    const bool nt_on = FPCC_NT_SMEM && KIND == 0 && OUTK == OK_I8 && sgn_mode != SGN_NONE;
+    const int64_t abound = (int64_t)a.K * (MODE == 0 ? a.kvol : 1) * 16384 + (ep.row_bias ? (int64_t)ep.row_bias_bound : 0);  // |acc (+ row bias)|
     if (chan_static)
-        for (int c = tid; c < a.n_tile; c += P_THREADS) {
+        for (int cb = warp * 32; cb < a.n_tile; cb += P_THREADS) {  // warp-uniform trip count (stage_nt_chunks ballots)
+            const int c = cb + lane;
+            const bool valid = c < a.n_tile;
             if (KIND == 0) {
                 const int32_t b = c < a.N && ep.bias ? ep.bias[c] : 0;
                 const uint32_t mu = c < a.N ? ep.mul[ep.mul_is_scalar ? 0 : c] : 0u;
-                if (!stage_channel(b, mu, zp_all, ep.shift, ep.out_type, vmax, &chan4_s[c]) && sgn_mode != SGN_NONE) atomicOr(lean_off, 1u);
-            } else {
+                bool ok = true;
+                if (valid) {
+                    ok = stage_channel(b, mu, zp_all, ep.shift, ep.out_type, vmax, &chan4_s[c]);
+                    if (!ok && sgn_mode != SGN_NONE) atomicOr(lean_off, 1u);
+                }
+                stage_nt_chunks(nt_on, valid, ok, c, b, mu, zp_all, ep.shift, abound, nt_flags);
+            } else if (valid) {
                 chan_s[c] = make_int2(c < a.N && fe.bias ? __float_as_int(fe.bias[c]) : 0, 0);
             }
         }
@@ -1008,7 +1102,11 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
             const int tile_m = tile / tiles_n;
             int32_t *rows = rows_s + slot * rows_k * TC_M;
             if (r == 0) TRACE(j, 0);
-            mbar_wait(&tmem_empty[slot], ((j >> 1) & 1) ^ 1);  // slot's previous tile (j-2) fully consumed
+            // The metadata slot is free once every reader of tile j-2 has taken its copy (the epilogue warps do that when
+            // they START tile j-2): the gathers of tile j run while the epilogue of tile j-2 still drains its accumulator;
+            // only the MMA issuer waits for tmem_empty.  (Waiting for tmem_empty here put meta + gather latency of every
+            // tile on the critical path: period = (fill + MMA + epilogue) / 2, measured with FPCC_TC_TRACE.)
+            mbar_wait(&meta_empty[slot], ((j >> 1) & 1) ^ 1);
             if (r == 0) TRACE(j, 1);
             if (r == 0) meta[slot].kmask = 0;
             asm volatile("bar.sync 1, %0;" ::"n"(PT) : "memory");
@@ -1134,6 +1232,7 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
                 uint32_t rem = meta[slot].kmask;
                 const int total = __popc(rem) * n_chunks;
                 const int group = MODE == 1 ? meta[slot].group : 0;
+                mbar_arrive(&meta_empty[slot]);
                 int k = 0, kc = n_chunks - 1;
                 for (int i = 0; i < total; ++i, ++it) {
                     if (++kc == n_chunks) { kc = 0; k = __ffs(rem) - 1; rem &= rem - 1; }
@@ -1160,6 +1259,7 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
                 const int slot = j & 1;
                 mbar_wait(&meta_full[slot], (j >> 1) & 1);
                 const int total = __popc(meta[slot].kmask) * n_chunks;
+                mbar_arrive(&meta_empty[slot]);
                 mbar_wait(&tmem_empty[slot], ((j >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)(slot * a.tmem_cols);
@@ -1206,25 +1306,69 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
             lu.ovf_lim = shift <= 31 ? (1u << shift) - 1u : 0xffffffffu;
         }
         lu.post2_addr = smem_u32(thr_s + 4);
+        lu.nt_addr = smem_u32(nt_flags);
         const bool post2_on = KIND == 0 && OUTK == OK_POST2;
+        // Output rows of grouped convs (row_perm): fetched ONE TILE AHEAD -- the dependent global load sat on the tile
+        // boundary of every epilogue warp (~1 us per tile in the FPCC_TC_TRACE timeline).
+        const bool use_perm = MODE == 0 && a.row_perm != nullptr;
+        constexpr bool QUAD = KIND == 0 && OUTK == OK_I32;
+        int32_t pm_next = 0, qpm_next[4] = {0, 0, 0, 0};
+        auto perm_fetch = [&](int pp) {
+            if (pp >= p_end) return;
+            const int64_t base = (int64_t)(FPCC_TILE_OF(pp) / tiles_n) * TC_M;
+            if (base + r < a.n_out) pm_next = __ldg(&a.row_perm[base + r]);
+            if (QUAD) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int64_t mti = base + quarter * 32 + (lane >> 2) + 8 * i;
+                    if (mti < a.n_out) qpm_next[i] = __ldg(&a.row_perm[mti]);
+                }
+            }
+        };
+        if (use_perm) perm_fetch(p0);
+        int64_t staged_key = -1;  // (bias block, channel block) whose constants are staged
         int j = 0;
         for (int p = p0; p < p_end; p += p_step, ++j) {
             const int tile = FPCC_TILE_OF(p);
             const int slot = j & 1;
             const int tile_m = tile / tiles_n, n0 = (tile % tiles_n) * a.n_tile;
+            const int32_t pm = pm_next;
+            int32_t qpm[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) qpm[i] = qpm_next[i];
+            if (use_perm) perm_fetch(p + p_step);
             mbar_wait(&meta_full[slot], (j >> 1) & 1);
             const bool have_acc = meta[slot].kmask != 0;
             const int pbase = (MODE == 1 && a.bias_per_group) ? meta[slot].group * a.N : 0;
-            if (!chan_static) {  // grouped weights / several channel blocks: restage (bias, mul) of this tile's block
+            // grouped weights / several channel blocks: restage (bias, mul) of this tile's block.  Restaging only when the
+            // block changes (the tiles of a weight group are consecutive: 8 restages per CTA for a C -> 8C selection linear)
+            // measured SLOWER on B200 -- selection linear with the fused second stage 0.203 -> 0.310 ms: without the two
+            // CTA-wide barriers per tile the 16 epilogue warps reach the accumulator wait early and their mbarrier polls take
+            // issue slots from the four gather-producer warps these kernels are bound by (profiles/r02_sel_linear_variants.txt).
+            // FPCC_RESTAGE_SKIP keeps the experiment.
+            const int64_t stage_key = ((int64_t)pbase << 20) | (int64_t)n0;
+#ifdef FPCC_RESTAGE_SKIP
+            const bool restage = !chan_static && stage_key != staged_key;
+#else
+            const bool restage = !chan_static;
+#endif
+            staged_key = stage_key;
+            if (restage) {
                 asm volatile("bar.sync 2, %0;" ::"n"(P_EPI_WARPS * 32) : "memory");  // every epilogue warp is done with the previous tile's values
                 const int t = warp * 32 + lane;
-                if (t < a.n_tile) {
+                if (warp * 32 < a.n_tile) {  // warp-uniform (stage_nt_chunks ballots); n_tile <= 256 <= 32 * epilogue warps
+                    const bool valid = t < a.n_tile;
                     const int pc = pbase + min(n0 + t, a.N - 1);
                     if (KIND == 0) {
                         const int32_t b = ep.bias ? __ldg(&ep.bias[pc]) : 0;
                         const uint32_t mu = __ldg(&ep.mul[ep.mul_is_scalar ? 0 : pc]);
-                        if (!stage_channel(b, mu, zp_all, ep.shift, ep.out_type, vmax, &chan4_s[t]) && sgn_mode != SGN_NONE) atomicOr(lean_off, 1u);
-                    } else {
+                        bool ok = true;
+                        if (valid) {
+                            ok = stage_channel(b, mu, zp_all, ep.shift, ep.out_type, vmax, &chan4_s[t]);
+                            if (!ok && sgn_mode != SGN_NONE) atomicOr(lean_off, 1u);
+                        }
+                        stage_nt_chunks(nt_on, valid, ok, t, b, mu, zp_all, ep.shift, abound, nt_flags);
+                    } else if (valid) {
                         chan_s[t] = make_int2(fe.bias ? __float_as_int(__ldg(&fe.bias[pc])) : 0, 0);
                     }
                 }
@@ -1233,13 +1377,36 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
             const int32_t *rows = rows_s + slot * rows_k * TC_M;
             const int64_t mt = (int64_t)tile_m * TC_M + r;  // MODE 0: column of the neighbour table
             const bool row_ok = MODE == 0 ? (mt < a.n_out) : (rows[TC_M + r] >= 0);
-            const int64_t m = MODE == 0 ? ((a.row_perm && row_ok) ? (int64_t)__ldg(&a.row_perm[mt]) : mt) : (int64_t)rows[TC_M + r];
+            const int64_t m = MODE == 0 ? ((use_perm && row_ok) ? (int64_t)pm : mt) : (int64_t)rows[TC_M + r];
             if (KIND == 0 && ep.residual && row_ok) {
                 // residual rows of this tile: start them towards L2 while the MMAs of the tile are still running
                 const char *rp = (const char *)(ep.residual + m * a.N + n0 + c_begin);
                 for (int off = 0; off < (c_end - c_begin) * 4; off += 128)
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + off));
             }
+            // int32 rows: quad layout (whole sectors per access); rows q, q+8, q+16, q+24 of the warp's quarter
+            QuadRows qr;
+            if (KIND == 0 && OUTK == OK_I32) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int rr = quarter * 32 + (lane >> 2) + 8 * i;
+                    int64_t mm;
+                    bool ok;
+                    if (MODE == 0) {
+                        const int64_t mti = (int64_t)tile_m * TC_M + rr;
+                        ok = mti < a.n_out;
+                        mm = (use_perm && ok) ? (int64_t)qpm[i] : mti;
+                    } else {
+                        mm = (int64_t)rows[TC_M + rr];
+                        ok = mm >= 0;
+                    }
+                    qr.off[i] = ok ? mm * a.N + n0 : -1;
+                    qr.rb[i] = (ep.row_bias && ok) ? (int32_t)__ldg(&ep.row_idx[mm]) : 0;
+                }
+            }
+            // this warp holds its copies of meta[slot] / rows[slot]: the producers may build tile j+2 in the slot
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&meta_empty[slot]);
             mbar_wait(&tmem_full[slot], (j >> 1) & 1);
             tc_fence_after();
             if (tid == 0) TRACE(j, 5);
@@ -1257,24 +1424,6 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
                     if (has_slope) lean_tile_sgn<FPCC_OUT_I8, true, false, false, false>(lt, lu, zp, sgn_mode, ep);
                     else lean_tile_sgn<FPCC_OUT_I8, false, false, false, false>(lt, lu, zp, sgn_mode, ep);
                 } else if (OUTK == OK_I32) {
-                    // int32 rows: quad layout (whole sectors per access); rows q, q+8, q+16, q+24 of the warp's quarter
-                    QuadRows qr;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int rr = quarter * 32 + (lane >> 2) + 8 * i;
-                        int64_t mm;
-                        bool ok;
-                        if (MODE == 0) {
-                            const int64_t mti = (int64_t)tile_m * TC_M + rr;
-                            ok = mti < a.n_out;
-                            mm = (a.row_perm && ok) ? (int64_t)__ldg(&a.row_perm[mti]) : mti;
-                        } else {
-                            mm = (int64_t)rows[TC_M + rr];
-                            ok = mm >= 0;
-                        }
-                        qr.off[i] = ok ? mm * a.N + n0 : -1;
-                        qr.rb[i] = (ep.row_bias && ok) ? (int32_t)__ldg(&ep.row_idx[mm]) : 0;
-                    }
                     if (has_slope) quad_tile_sgn<true, false>(lt, qr, lu, zp, sgn_mode, ep, (int32_t *)out);
                     else quad_tile_sgn<false, MODE == 0>(lt, qr, lu, zp, sgn_mode, ep, (int32_t *)out);
                 } else if (OUTK == OK_POST2) {

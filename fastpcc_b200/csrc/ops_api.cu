@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(256) requant_vec4_kernel(const int4 *__restric
 // input is needed, and |x*mul| < 2^62, |zp| < 2^60, half <= 2^61 keep the sum inside int64.
 template <bool SLOPE, bool HI>
 __device__ __forceinline__ void requant_scalar_fast_loop(const int4 *__restrict__ in, int64_t total16, uint4 *__restrict__ out,
-                                                         int32_t slope, int32_t B, int32_t thr, int32_t mul, int64_t c0, int shift) {
+                                                         int32_t slope, int32_t B, int32_t thr, int32_t mul, int64_t c0, int shift,
+                                                         int ch16, int64_t ld16) {
     const int64_t c_pos = c0, c_neg = c0 - 1;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total16; i += (int64_t)gridDim.x * blockDim.x) {
         int4 v[4];
@@ -95,7 +96,7 @@ __device__ __forceinline__ void requant_scalar_fast_loop(const int4 *__restrict_
             asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(up) : "r"(o[3]), "r"(o[2]), "r"(0));
             asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(w[q]) : "r"(o[1]), "r"(o[0]), "r"(up));
         }
-        out[i] = make_uint4(w[0], w[1], w[2], w[3]);
+        out[ld16 == ch16 ? i : (i / ch16) * ld16 + (i % ch16)] = make_uint4(w[0], w[1], w[2], w[3]);  // ld16: output row pitch / 16
     }
 }
 
@@ -104,7 +105,7 @@ __device__ __forceinline__ void requant_scalar_fast_loop(const int4 *__restrict_
 // v is first clamped to [-B, B] with B the smallest magnitude that already saturates int8, so v*mul + zp fits a
 // 64-bit accumulator whose shifted value fits 32 bits; "t < 0" is decided as v < thr = ceil(-zp / mul).
 __global__ void __launch_bounds__(256) requant_scalar_i8_kernel(const int4 *__restrict__ in, int64_t total16, EpiParams ep,
-                                                                uint4 *__restrict__ out) {
+                                                                uint4 *__restrict__ out, int ch16, int64_t ld16) {
     const int64_t zp = ep.zp[0];
     const uint32_t mul = ep.mul[0];
     const int shift = ep.shift;
@@ -137,11 +138,11 @@ __global__ void __launch_bounds__(256) requant_scalar_i8_kernel(const int4 *__re
     // chains of a thread interleave (a per-element fast/slow branch serialises them)
     if (fast) {
         if (hi) {
-            if (has_slope) requant_scalar_fast_loop<true, true>(in, total16, out, slope, B, thr, (int32_t)mul, c0, shift);
-            else requant_scalar_fast_loop<false, true>(in, total16, out, slope, B, thr, (int32_t)mul, c0, shift);
+            if (has_slope) requant_scalar_fast_loop<true, true>(in, total16, out, slope, B, thr, (int32_t)mul, c0, shift, ch16, ld16);
+            else requant_scalar_fast_loop<false, true>(in, total16, out, slope, B, thr, (int32_t)mul, c0, shift, ch16, ld16);
         } else {
-            if (has_slope) requant_scalar_fast_loop<true, false>(in, total16, out, slope, B, thr, (int32_t)mul, c0, shift);
-            else requant_scalar_fast_loop<false, false>(in, total16, out, slope, B, thr, (int32_t)mul, c0, shift);
+            if (has_slope) requant_scalar_fast_loop<true, false>(in, total16, out, slope, B, thr, (int32_t)mul, c0, shift, ch16, ld16);
+            else requant_scalar_fast_loop<false, false>(in, total16, out, slope, B, thr, (int32_t)mul, c0, shift, ch16, ld16);
         }
         return;
     }
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(256) requant_scalar_i8_kernel(const int4 *__re
             }
             w[q] = word;
         }
-        out[i] = make_uint4(w[0], w[1], w[2], w[3]);
+        out[ld16 == ch16 ? i : (i / ch16) * ld16 + (i % ch16)] = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
 
@@ -180,6 +181,20 @@ static int ew_grid(int64_t total) {
 
 using namespace fpcc;
 
+extern "C" int fpcc_requant_ld(const int32_t *in, int64_t rows, int ch, const fpcc_epilogue *e, void *out, int64_t out_ld, void *stream) {
+    FPCC_REQUIRE(in && out, "requant_ld: NULL pointer");
+    FPCC_REQUIRE(rows > 0 && ch > 0, "requant_ld: rows and channels must be positive");
+    int rc = check_epilogue(e, false);
+    if (rc) return rc;
+    FPCC_REQUIRE(e->out_type == FPCC_OUT_I8 && e->mul_is_scalar && !e->bias, "requant_ld: one multiplier, no bias, int8 output (RequantFxpToScaledInt8)");
+    FPCC_REQUIRE(ch % 16 == 0 && out_ld % 16 == 0 && out_ld >= ch && (((uintptr_t)in | (uintptr_t)out) & 15) == 0,
+                 "requant_ld: channels, output pitch and pointers must be multiples of 16");
+    const int64_t total16 = rows * (ch / 16);
+    requant_scalar_i8_kernel<<<ew_grid(total16), 256, 0, (cudaStream_t)stream>>>((const int4 *)in, total16, to_params(e), (uint4 *)out, ch / 16, out_ld / 16);
+    FPCC_LAUNCH_CHECK();
+    return FPCC_OK;
+}
+
 extern "C" int fpcc_requant(const int32_t *in, int64_t rows, int ch, const fpcc_epilogue *e, void *out, void *stream) {
     FPCC_REQUIRE(in && out, "requant: NULL pointer");
     FPCC_REQUIRE(rows > 0 && ch > 0, "requant: rows and channels must be positive");
@@ -190,7 +205,7 @@ extern "C" int fpcc_requant(const int32_t *in, int64_t rows, int ch, const fpcc_
     EpiParams ep = to_params(e);
     if (e->out_type == FPCC_OUT_I8 && e->mul_is_scalar && !e->bias && total % 16 == 0 &&
         (((uintptr_t)in | (uintptr_t)out) & 15) == 0) {
-        requant_scalar_i8_kernel<<<ew_grid(total / 16), 256, 0, s>>>((const int4 *)in, total / 16, ep, (uint4 *)out);
+        requant_scalar_i8_kernel<<<ew_grid(total / 16), 256, 0, s>>>((const int4 *)in, total / 16, ep, (uint4 *)out, 1, 1);
     } else if (ch % 4 == 0 && (((uintptr_t)in | (uintptr_t)out) & 15) == 0) {
         int64_t t4 = total / 4;
         if (e->out_type == FPCC_OUT_I8) requant_vec4_kernel<FPCC_OUT_I8><<<ew_grid(t4), 256, 0, s>>>((const int4 *)in, t4, ch / 4, ep, out);

@@ -429,8 +429,9 @@ class RequantFxpToScaledInt8(LoadSaveUint32RequantMul):
         self.int_zero_point_out[:] = (zero_point_out * (2 ** (SharedFxpShift + self.requant_shift.to(torch.float)))) \
             .round().to(torch.int64)
 
-    def forward(self, input: torch.Tensor, prelu: Optional['PReLUIn32Out32'] = None) -> torch.Tensor:
+    def forward(self, input: torch.Tensor, prelu: Optional['PReLUIn32Out32'] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """(Q8.23 x Qx.xx) >> (23 + xx) -> scaled int8; the single multiplier is broadcast by the kernel.
+        `out`: an int8 [rows, ch] column slice of a wider buffer to write into (concatenation without a copy).
         `prelu`: a PReLUIn32Out32 that precedes this requant; its pass is folded into this kernel when its slope
         lies in [0, 1] (then the int32 saturation of the stand-alone PReLU cannot trigger, so the integers agree)."""
         slope = None
@@ -440,7 +441,7 @@ class RequantFxpToScaledInt8(LoadSaveUint32RequantMul):
             else:
                 input = prelu(input)
         ep = ops.make_epilogue(self.requant_mul, self.int_zero_point_out, SharedFxpShift + _shift_of(self), ops.OUT_I8, slope=slope)
-        return ops.requant(input, ep)
+        return ops.requant(input, ep, out=out)
 
     def as_post_stage(self, prelu: Optional['PReLUIn32Out32'] = None):
         """This requant (and a PReLUIn32Out32 in front of it) as the fused second stage of the producing int32 layer

@@ -244,7 +244,13 @@ class OneScaleMultiStepPredictor(nn.Module):
             if isinstance(dec, SparseSequential) and isinstance(dec[0], RequantFxpToScaledInt8):
                 # Requant(cat(F, embed)) == cat(Requant(F), Requant(embed)): one scalar multiplier for all channels, so the
                 # concatenation moves int8 rows (4x fewer bytes) and the Q8.23 cat tensor is never built (model.py:199-201)
-                q = torch.cat([dec[0](cur.F), dec[0](embed_f)], 1)
+                c1, c2 = cur.F.shape[1], embed_f.shape[1]
+                if c1 % 16 == 0 and c2 % 16 == 0:  # the two requants write the column halves of one buffer: no copy at all
+                    q = torch.empty((cur.F.shape[0], c1 + c2), dtype=torch.int8, device=cur.F.device)
+                    dec[0](cur.F, out=q[:, :c1])
+                    dec[0](embed_f, out=q[:, c1:])
+                else:
+                    q = torch.cat([dec[0](cur.F), dec[0](embed_f)], 1)
                 cur = dec[2](_with(dec[1](q), cur))
             else:
                 cur.F = torch.cat([cur.F, embed_f], 1)
@@ -392,7 +398,12 @@ class Model(nn.Module):
                 err.append(e)
 
         if not hasattr(self, '_side_streams') or len(self._side_streams) < n_groups:
-            self._side_streams = [torch.cuda.Stream(self.device) for _ in range(n_groups)]
+            # descending stream priorities: the groups start together, but the hardware scheduler serves the pending
+            # thread blocks of group 0 first, so the groups drift apart and the latency-bound range-coder phase of one
+            # group meets the tensor-core phase of another instead of all groups idling in the same phase
+            import os
+            lo, hi = (0, 0) if os.environ.get('FPCC_STREAM_PRIO', '1') == '0' else (0, -5)
+            self._side_streams = [torch.cuda.Stream(self.device, priority=max(hi, lo - g)) for g in range(n_groups)]
         import sys
         from .. import _lib
         old_interval = sys.getswitchinterval()
@@ -422,6 +433,17 @@ class Model(nn.Module):
 
     def decompress_batch(self, streams: List[bytes], n_groups: int = 1) -> List[torch.Tensor]:
         return self._run_groups(self._decompress_group, list(streams), n_groups)
+
+    def roundtrip_batch(self, frames: List[torch.Tensor], n_groups: int = 1):
+        """compress + decompress of every frame, pipelined per group: each of the `n_groups` slices is encoded to its byte
+        strings and decoded from them on its own stream, so the encoder of one slice (tensor-core bound, no serial
+        chain) overlaps the level-by-level decoder of another.  Returns (bitstreams, decoded frames), both in order."""
+        res = self._run_groups(lambda part: [(d, r) for d, r in zip(*self._roundtrip_group(part))], list(frames), n_groups)
+        return [d for d, _ in res], [r for _, r in res]
+
+    def _roundtrip_group(self, frames):
+        data = self._compress_group(frames)
+        return data, self._decompress_group(data)
 
     @torch.no_grad()
     def _compress_group(self, frames: List[torch.Tensor]) -> List[bytes]:

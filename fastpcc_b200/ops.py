@@ -301,10 +301,16 @@ def requant(inp, ep, out=None):
     _need(inp, torch.int32, 'input', 2)
     if inp.shape[0] <= 0 or inp.shape[1] <= 0:
         raise RuntimeError('requant: N > 0 && Ch > 0')
+    work = ({'bytes': float(inp.numel() * 4 + inp.numel() * _OUT_DTYPE[ep.out_type].itemsize), 'desc': f'{inp.shape[0]}x{inp.shape[1]} out{ep.out_type}'}
+            if _prof is not None else None)
+    if out is not None and not out.is_contiguous():
+        # a column slice of a wider int8 buffer (the two halves of a concatenation): rows at the buffer's pitch
+        if out.dtype != torch.int8 or out.dim() != 2 or tuple(out.shape) != tuple(inp.shape) or out.stride(1) != 1:
+            raise RuntimeError('requant: a strided output must be an int8 [rows, ch] column slice')
+        _call('fpcc_requant_ld', _p(inp), inp.shape[0], inp.shape[1], C.byref(ep), out.data_ptr(), out.stride(0), _s(), tag='fpcc_requant', work=work)
+        return out
     out = torch.empty(inp.shape, dtype=_OUT_DTYPE[ep.out_type], device=inp.device) if out is None else out
-    _call('fpcc_requant', _p(inp), inp.shape[0], inp.shape[1], C.byref(ep), _p(out), _s(),
-          work={'bytes': float(inp.numel() * 4 + out.numel() * out.element_size()), 'desc': f'{inp.shape[0]}x{inp.shape[1]} out{ep.out_type}'}
-          if _prof is not None else None)
+    _call('fpcc_requant', _p(inp), inp.shape[0], inp.shape[1], C.byref(ep), _p(out), _s(), work=work)
     return out
 
 

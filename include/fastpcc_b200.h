@@ -228,6 +228,11 @@ typedef struct {
 
 /* replaces the 12 requant entry points of binding.cu:118-129 */
 int fpcc_requant(const int32_t *in, int64_t rows, int ch, const fpcc_epilogue *ep, void *out, void *stream);
+/* The same for RequantFxpToScaledInt8 (one multiplier, no bias, int8 output) with an output row pitch: row r goes to
+ * out + r * out_ld (bytes; ch, out_ld % 16 == 0).  Lets the two requants in front of `Linear(cat(F, embed))`
+ * (models/convolutional/lossl_coord_int/model.py:199-201) write the two column halves of ONE [rows, 2C] int8 buffer: the
+ * concatenation costs no copy. */
+int fpcc_requant_ld(const int32_t *in, int64_t rows, int ch, const fpcc_epilogue *ep, void *out, int64_t out_ld, void *stream);
 /* replaces prelu (prelu.cu) */
 int fpcc_prelu_i32(const int32_t *in, int64_t numel, const int32_t *slope, int32_t *out, void *stream);
 

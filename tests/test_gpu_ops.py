@@ -324,6 +324,103 @@ def test_epilogue_shift0_and_small_negatives(ops):
                 assert (got == want).all(), ('requant', shift, mulv, zpv)
 
 
+def test_requant_into_column_slices_of_one_buffer(ops):
+    """fpcc_requant_ld: the two RequantFxpToScaledInt8 in front of Linear(cat(F, embed)) (lossl_coord_int/model.py:199-201)
+    write the column halves of one [rows, 2C] int8 buffer; equal to requant + torch.cat, neighbours untouched."""
+    rng = np.random.default_rng(3)
+    rows, c1, c2 = 1237, 64, 32
+    x1 = rng.integers(-(1 << 31), (1 << 31) - 1, (rows, c1), endpoint=True).astype(np.int32)
+    x2 = rng.integers(-(1 << 26), 1 << 26, (rows, c2)).astype(np.int32)
+    for shift, mulv, zpv, slope_v in ((48, (1 << 30) + 12345, 0, None), (40, 12345, -(3 << 39), int(0.3 * (1 << 25))), (7, 77, 5, None)):
+        mul1, zp = np.array([mulv], np.uint32), np.array([zpv], np.int64)
+        sl = None if slope_v is None else np.array([slope_v], np.int32)
+        ep = ops.make_epilogue(dev(mul1), dev(zp), shift, ops.OUT_I8, slope=None if sl is None else dev(sl))
+        buf = torch.full((rows, c1 + c2 + 16), 99, dtype=torch.int8, device='cuda')
+        ops.requant(dev(x1), ep, out=buf[:, :c1])
+        ops.requant(dev(x2), ep, out=buf[:, c1:c1 + c2])
+        want = np.concatenate([K.requant(x1, np.full(c1, mulv, np.uint32), zp, shift, np.int8, slope=sl),
+                               K.requant(x2, np.full(c2, mulv, np.uint32), zp, shift, np.int8, slope=sl)], 1)
+        got = buf.cpu().numpy()
+        assert (got[:, :c1 + c2] == want).all() and (got[:, c1 + c2:] == 99).all(), (shift, mulv, zpv)
+    with pytest.raises(RuntimeError):
+        ops.requant(dev(x1[:, :24]), ep, out=buf[:, :24])  # 24 channels: not a multiple of 16
+
+
+def _tie_values(mul, zp, shift, lo, hi):
+    """all v in [lo, hi] for which v*mul + zp is an exact rounding tie of `shift` (brute force, python ints)"""
+    M, half = 1 << shift, 1 << (shift - 1)
+    return [v for v in range(lo, hi + 1) if (v * int(mul) + int(zp)) % M == half]
+
+
+@pytest.mark.parametrize('shift,tz,n', [(38, 28, 96), (30, 20, 96), (38, 28, 512), (33, 24, 96)])
+def test_epilogue_tie_free_and_tie_chunks(ops, shift, tz, n):
+    """int8 outputs take a tie-free form per 16-channel chunk when no channel of the chunk can hit an exact rounding
+    tie inside the accumulator bound (csrc/epi_nt.cuh); chunks with a tie-able channel keep the sign-exact arithmetic.
+    Multipliers with `tz` trailing zeros make ties reachable every 2^(shift - tz) values; the occupancy row-bias table
+    injects the exact tie values (negative and positive, also behind the PReLU) into a zero accumulator.  Chunk 0 is
+    all tie-free, chunk 1 mixes one tie-able channel in, chunk 2 is all tie-able; n = 512 restages the constants per
+    channel block.  Reference arithmetic: requant.cu:16-20, bias_prelu_requant.cu:6-37."""
+    rng = np.random.default_rng(shift * 100 + n)
+    m, k = 300, 64
+    a = np.zeros((m, k), np.int8)
+    w = np.zeros((n, k), np.int8)
+    bound = 1 << 13
+    for zpv in (0, 5 << tz, -(7 << tz) + 3):
+        mul = (rng.integers(1 << 20, 1 << 30, n) | 1).astype(np.uint32)  # odd: tie-free inside the bound for these shifts
+        tie_ch = [17] + list(range(32, 48)) + ([300, 511] if n > 300 else [])
+        for c in tie_ch:
+            mul[c] = np.uint32((2 * int(rng.integers(1, 4)) + 1) << tz)
+        bias = rng.integers(-500, 500, n).astype(np.int32)
+        zp = np.array([zpv], np.int64)
+        for slope_v in (None, 1 << 23):  # PReLU slope 0.25: prelu(4 v) == v exactly for v < 0
+            table = rng.integers(-bound + 600, bound - 600, (256, n)).astype(np.int32)
+            hits = 0
+            for c in tie_ch:
+                ties = _tie_values(mul[c], zpv, shift, -1500, 1500)
+                if zpv % (1 << tz) == 0:
+                    assert ties, (c, int(mul[c]))
+                for i, v in enumerate(ties[:40]):
+                    tv = 4 * v if (slope_v is not None and v < 0) else v
+                    table[3 + 5 * i, c] = tv - int(bias[c])
+                    hits += 1
+            idx = rng.integers(0, 256, m).astype(np.uint8)
+            idx[:256] = np.arange(256)
+            slope = None if slope_v is None else np.array([slope_v], np.int32)
+            accb = table[idx].astype(np.int32)
+            want = K.requant(accb, mul, zp, shift, np.int8, bias=bias, slope=slope)
+            # the ties must matter: dropping the "- [r < 0]" term changes at least one output
+            if hits and zpv % (1 << tz) == 0:
+                v = accb.astype(np.int64) + bias.astype(np.int64)
+                if slope is not None:
+                    v = K.prelu(v.astype(np.int32), slope).astype(np.int64)
+                naive = np.clip((v * mul.astype(np.int64) + zpv + (1 << (shift - 1))) >> shift, -128, 127)
+                assert (naive != want).any()
+            ep = ops.make_epilogue(dev(mul), dev(zp), shift, ops.OUT_I8, bias=dev(bias), slope=None if slope is None else dev(slope),
+                                   row_bias=(dev(table), dev(idx), bound))
+            got = ops.linear(dev(a), dev(w), ep).cpu().numpy()
+            assert (got == want).all(), (zpv, slope_v, np.argwhere(got != want)[:5])
+    # the same through the conv kernel (MODE 0: static constants, 12 epilogue warps): zero features, the bias carries
+    # one value per channel -- the tie itself for the tie-able channels
+    if n <= 256:
+        C = _cloud(11, n=1500, bits=6)
+        keys, vals = ops.hash_build(dev(C))
+        tab = ops.kmap_lookup(keys, vals, dev(C), (3, 3, 3), (1, 1, 1))
+        f = np.zeros((C.shape[0], 32), np.int8)
+        w3 = np.zeros((27, n, 32), np.int8)
+        for zpv in (0, 5 << tz):
+            mul = (rng.integers(1 << 20, 1 << 30, n) | 1).astype(np.uint32)
+            bias = rng.integers(-3000, 3000, n).astype(np.int32)
+            for c in [17] + list(range(32, 48)):
+                mul[c] = np.uint32(3 << tz)
+                ties = [v for v in _tie_values(mul[c], zpv, shift, -3000, 3000) if v < 0]
+                if ties:
+                    bias[c] = ties[c % len(ties)]
+            zp = np.array([zpv], np.int64)
+            want = K.requant(np.zeros((C.shape[0], n), np.int32), mul, zp, shift, np.int8, bias=bias)
+            got = ops.spconv(dev(f), dev(w3), tab, ops.make_epilogue(dev(mul), dev(zp), shift, ops.OUT_I8, bias=dev(bias))).cpu().numpy()
+            assert (got == want).all(), ('conv', zpv)
+
+
 @pytest.mark.parametrize('k,n', [(64, 64), (256, 256), (32, 48)])
 def test_fused_second_stage_equals_prelu_then_requant(ops, k, n):
     """fpcc_epilogue::post_requant_mul: an int32 (Q8.23) linear whose only consumer is [PReLUIn32Out32 +]
