@@ -65,6 +65,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "WAIT_DONE:\n\t"
         "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
 }
+// Wait of the 12-16 epilogue warps for the accumulator: test + nanosleep back-off instead of the blocking try_wait loop, so
+// that their polls do not take issue slots from the gather-producer warps (FPCC_EPI_SLEEP ns, 0 = plain mbar_wait).
+#ifndef FPCC_EPI_SLEEP
+#define FPCC_EPI_SLEEP 0
+#endif
+__device__ __forceinline__ void mbar_wait_epi(uint64_t *bar, uint32_t parity) {
+#if FPCC_EPI_SLEEP > 0
+    uint32_t done;
+    for (;;) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(FPCC_EPI_SLEEP);
+    }
+#else
+    mbar_wait(bar, parity);
+#endif
+}
 // ---- 2-CTA cluster helpers (weight tiles shared by TMA multicast, see CL2 below) ----
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -321,6 +339,18 @@ __device__ __forceinline__ int4 lds128_ro(uint32_t addr) {
     asm("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
 }
+// 32-byte accesses (sm_100: LDG/STG.E.ENL2.256): one WHOLE sector per lane.  With a row per lane (tcgen05.ld.32x32b) every
+// 16-byte store of a row is half a sector; two chunks' worth of an int8 row or 8 columns of an int32 row fill one.
+__device__ __forceinline__ void stg256(void *p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4, uint32_t a5, uint32_t a6, uint32_t a7) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(a5), "r"(a6), "r"(a7) : "memory");
+}
+__device__ __forceinline__ void ldg256(const void *p, int4 &lo, int4 &hi) {
+    asm volatile("ld.global.nc.v8.s32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "l"(p));
+}
+#ifndef FPCC_ST256
+#define FPCC_ST256 1
+#endif
 __device__ __forceinline__ int64_t pack64(uint32_t lo, uint32_t hi) {
     int64_t d;
     asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
@@ -555,6 +585,8 @@ struct LeanTile {
     const int32_t *rb_row;      // occupancy bias row (column n0) or NULL
     const int32_t *res_row;     // residual row (column n0) or NULL
     bool has_post;
+    bool al32;                  // 256-bit stores allowed: conv kernel (96 registers) and a 32-byte aligned output base.  The
+                                // linear kernels sit at their 80-register cap: holding 16 bytes across a chunk costs them 5-20 %
 };
 
 __device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t &r) {
@@ -612,6 +644,11 @@ __device__ __forceinline__ void lean_tile(const LeanTile &lt, const LeanU &u, in
 #pragma unroll
         for (int t = 0; t < EC / 4; ++t) rnext[t] = __ldg(reinterpret_cast<const int4 *>(lt.res_row + lt.c_begin) + t);
     }
+    // 32-byte stores need 32-byte aligned pieces: the warp's first column and the row pitch are multiples of 32 bytes
+    const bool wide8 = esz == 1 && (lt.c_begin & 31) == 0 && (lt.ncols_total & 31) == 0 && (lt.n0 & 31) == 0 && lt.al32;
+    const bool wide32 = esz == 4 && (lt.ncols_total & 7) == 0 && lt.al32;
+    uint32_t held[4] = {0u, 0u, 0u, 0u};
+    bool held_valid = false;  // per lane: the even chunk of a pair waits for its odd neighbour
     for (int c0 = lt.c_begin; c0 < lt.c_end; c0 += EC) {
         uint32_t acc[EC];
         int4 rcur[EC / 4];
@@ -650,6 +687,10 @@ __device__ __forceinline__ void lean_tile(const LeanTile &lt, const LeanU &u, in
         else good = lean_chunk<OUT, SLOPE, SGN>(acc, lt.chan_addr + (uint32_t)c0 * 16, u, o);
         if (OUT == FPCC_OUT_I32 && (SGN == SGN_LO0 || SGN == SGN_THR_LO)) {
             if (__any_sync(0xffffffffu, !good)) {  // warp-uniform, rare
+                if (held_valid) {  // the redo stores this chunk itself: flush the waiting even chunk of the pair first
+                    *reinterpret_cast<uint4 *>(lt.orow + (size_t)(c0 - EC) * esz) = make_uint4(held[0], held[1], held[2], held[3]);
+                    held_valid = false;
+                }
                 lean_redo_chunk<OUT, SLOPE>(lt, u, c0, zp, ep);
                 continue;
             }
@@ -699,9 +740,15 @@ __device__ __forceinline__ void lean_tile(const LeanTile &lt, const LeanU &u, in
                     }
                 }
             } else {
-                uint4 *op = reinterpret_cast<uint4 *>(lt.orow + (size_t)c0 * esz);
+                if (FPCC_ST256 && wide32) {  // 64 bytes of the int32 row: two whole sectors
+                    char *op = lt.orow + (size_t)c0 * esz;
+                    stg256(op, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
+                    stg256(op + 32, o[8], o[9], o[10], o[11], o[12], o[13], o[14], o[15]);
+                } else {
+                    uint4 *op = reinterpret_cast<uint4 *>(lt.orow + (size_t)c0 * esz);
 #pragma unroll
-                for (int t = 0; t < EC / 4; ++t) op[t] = make_uint4((uint32_t)o[4 * t], (uint32_t)o[4 * t + 1], (uint32_t)o[4 * t + 2], (uint32_t)o[4 * t + 3]);
+                    for (int t = 0; t < EC / 4; ++t) op[t] = make_uint4((uint32_t)o[4 * t], (uint32_t)o[4 * t + 1], (uint32_t)o[4 * t + 2], (uint32_t)o[4 * t + 3]);
+                }
             }
         }
         if (OUT == FPCC_OUT_I32 && !POST2) {
@@ -715,7 +762,20 @@ __device__ __forceinline__ void lean_tile(const LeanTile &lt, const LeanU &u, in
                 asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(up) : "r"(o[q + 3]), "r"(o[q + 2]), "r"(0));
                 asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(w[t]) : "r"(o[q + 1]), "r"(o[q]), "r"(up));
             }
-            *reinterpret_cast<uint4 *>(lt.orow + (size_t)c0 * esz) = make_uint4(w[0], w[1], w[2], w[3]);
+            if (FPCC_ST256 && wide8) {
+                // even chunk of a pair: hold its 16 bytes; odd chunk: one 32-byte store of both (a whole sector per lane)
+                if ((((c0 - lt.c_begin) >> 4) & 1) == 0 && c0 + EC < c_last) {
+                    held[0] = w[0]; held[1] = w[1]; held[2] = w[2]; held[3] = w[3];
+                    held_valid = true;
+                } else if (held_valid) {
+                    stg256(lt.orow + (size_t)(c0 - EC) * esz, held[0], held[1], held[2], held[3], w[0], w[1], w[2], w[3]);
+                    held_valid = false;
+                } else {
+                    *reinterpret_cast<uint4 *>(lt.orow + (size_t)c0 * esz) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            } else {
+                *reinterpret_cast<uint4 *>(lt.orow + (size_t)c0 * esz) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
         }
     }
 }
@@ -1337,7 +1397,7 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
 #pragma unroll
             for (int i = 0; i < 4; ++i) qpm[i] = qpm_next[i];
             if (use_perm) perm_fetch(p + p_step);
-            mbar_wait(&meta_full[slot], (j >> 1) & 1);
+            mbar_wait_epi(&meta_full[slot], (j >> 1) & 1);
             const bool have_acc = meta[slot].kmask != 0;
             const int pbase = (MODE == 1 && a.bias_per_group) ? meta[slot].group * a.N : 0;
             // grouped weights / several channel blocks: restage (bias, mul) of this tile's block.  Restaging only when the
@@ -1407,7 +1467,7 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
             // this warp holds its copies of meta[slot] / rows[slot]: the producers may build tile j+2 in the slot
             __syncwarp();
             if (lane == 0) mbar_arrive(&meta_empty[slot]);
-            mbar_wait(&tmem_full[slot], (j >> 1) & 1);
+            mbar_wait_epi(&tmem_full[slot], (j >> 1) & 1);
             tc_fence_after();
             if (tid == 0) TRACE(j, 5);
             const uint32_t tacc = tmem_base + (uint32_t)(slot * a.tmem_cols) + ((uint32_t)(quarter * 32) << 16);
@@ -1415,7 +1475,7 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
             if (KIND == 0 && lean) {
                 LeanTile lt;
                 lt.tacc = tacc; lt.chan_addr = smem_u32(chan4_s); lt.c_begin = c_begin; lt.c_end = c_end; lt.ncols = a.N - n0; lt.n0 = n0; lt.ncols_total = a.N;
-                lt.have_acc = have_acc; lt.row_ok = row_ok; lt.has_post = has_post;
+                lt.have_acc = have_acc; lt.row_ok = row_ok; lt.has_post = has_post; lt.al32 = MODE == 0 && ((uintptr_t)out & 31) == 0;
                 const int64_t row0 = row_ok ? m * a.N + n0 : 0;
                 lt.orow = (char *)out + row0 * ((ep.out_type == FPCC_OUT_I8 || post2_on) ? 1 : 4);
                 lt.rb_row = ep.row_bias ? ep.row_bias + (row_ok ? (int64_t)__ldg(&ep.row_idx[m]) * a.N + n0 : 0) : nullptr;
@@ -1665,7 +1725,10 @@ static int launch_tc(TcArgs &a, const void *W, int64_t w_rows, int tiles_m, cons
         const int pairs = (total + 1) / 2, clusters = sms / 2;
         grid = 2 * (pairs < clusters ? pairs : clusters);
     }
-    if (PSmem<4>::bytes(a.n_tile, rows_k) <= TC_SMEM_MAX)
+    // FPCC_STAGES=3 (environment, experiments): three operand stages leave ~48 KB of shared memory per SM, enough for the
+    // serial range-coder blocks of other streams to share an SM with a persistent GEMM CTA
+    static const bool force3 = [] { const char *e = getenv("FPCC_STAGES"); return e && e[0] == '3'; }();
+    if (!force3 && PSmem<4>::bytes(a.n_tile, rows_k) <= TC_SMEM_MAX)
         return launch_stages<MODE, 4, KIND>(a, tmap, ep, fe, out, tiles_m, n_blocks_n, grid, rows_k, cl2, s);
     return launch_stages<MODE, 3, KIND>(a, tmap, ep, fe, out, tiles_m, n_blocks_n, grid, rows_k, cl2, s);
 }
