@@ -40,6 +40,7 @@ SIGNATURES = {
     'fpcc_gather_patches': (_i, [_vp, _i, _vp, _i64, _i, _i, _vp, _i, _vp]),
     'fpcc_slot_table': (_i, [_vp, _vp, _i, _vp, _i64, _vp]),
     'fpcc_morton_encode': (_i, [_vp, _i64, _i, _i, _vp, _vp]),
+    'fpcc_gather_rows16': (_i, [_vp, _vp, _i64, _vp, _vp]),
     'fpcc_voxelize_workspace': (_sz, [_i64]),
     'fpcc_voxelize_f32': (_i, [_vp, _i64, _i, C.c_float, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     'fpcc_kd_split_workspace': (_sz, [_i64, _i]),

@@ -514,6 +514,27 @@ extern "C" int fpcc_morton_encode(const int32_t *xyz, int64_t ld, int n, int msb
 }
 
 namespace fpcc {
+// dst[i] = src[idx[i]] for 16-byte rows (coordinates): the permutation into Morton order after the sort
+// (model.py:396-398 `xyz = xyz[order]`).  torch's index kernel moves these rows at ~60 GB/s; one int4 per thread
+// runs at the sector rate of the random reads.
+__global__ void __launch_bounds__(256) gather_rows16_kernel(const int4 *__restrict__ src, const int64_t *__restrict__ idx, int64_t n,
+                                                            int4 *__restrict__ dst) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = __ldg(&src[__ldg(&idx[i])]);
+}
+}  // namespace fpcc
+
+extern "C" int fpcc_gather_rows16(const void *src, const int64_t *idx, int64_t n, void *dst, void *stream) {
+    FPCC_REQUIRE(src && idx && dst && n >= 0, "gather_rows16: bad arguments");
+    FPCC_REQUIRE((((uintptr_t)src | (uintptr_t)dst) & 15) == 0, "gather_rows16: rows must be 16-byte aligned");
+    if (n == 0) return FPCC_OK;
+    const int64_t blocks = (n + 255) / 256, cap = (int64_t)fpcc::sm_count() * 16;
+    fpcc::gather_rows16_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>((const int4 *)src, idx, n, (int4 *)dst);
+    FPCC_LAUNCH_CHECK();
+    return FPCC_OK;
+}
+
+namespace fpcc {
 __global__ void __launch_bounds__(256) slot_table_kernel(const int32_t *__restrict__ parent, const uint8_t *__restrict__ slot,
                                                          int n, int32_t *__restrict__ table, int64_t ld) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;

@@ -1654,7 +1654,28 @@ constexpr size_t TC_SMEM_MAX = 227 * 1024;
 template <int MODE, int STAGES, int KIND, int OUTK>
 static int launch_outk(const TcArgs &a, const CUtensorMap &tmap, const EpiParams &ep, const FEpi &fe, void *out, int tiles_m,
                        int n_blocks_n, int grid, size_t smem, bool cl2, cudaStream_t s) {
-    constexpr int EW = MODE == 0 ? EPI_WARPS_CONV : EPI_WARPS_PAIRS;
+    // Epilogue warps per kernel instance.  The register file splits over four sub-partitions: 12 + 6 warps get 96 registers
+    // per thread, 16 + 6 warps 80, 8 + 6 warps 128.  The int32-output instances (quad layout, residual prefetch) spill at 96 / 80
+    // and run faster on FEWER warps with more registers (ResBlock conv2: 0.354 -> 0.307 ms with 8, 0.371 ms with 16;
+    // profiles/r02_epilogue_warps.txt).
+#ifndef FPCC_CONV2_EW
+#define FPCC_CONV2_EW 8
+#endif
+#ifndef FPCC_LIN32_EW
+#define FPCC_LIN32_EW 8
+#endif
+#ifndef FPCC_LINP2_EW
+#define FPCC_LINP2_EW 8
+#endif
+#ifndef FPCC_CONV1_EW
+#define FPCC_CONV1_EW EPI_WARPS_CONV
+#endif
+#ifndef FPCC_LIN8_EW
+#define FPCC_LIN8_EW EPI_WARPS_PAIRS
+#endif
+    constexpr int EW = KIND != 0 ? (MODE == 0 ? EPI_WARPS_CONV : EPI_WARPS_PAIRS)
+                       : MODE == 0 ? (OUTK == OK_I32 ? FPCC_CONV2_EW : FPCC_CONV1_EW)
+                                   : (OUTK == OK_I32 ? FPCC_LIN32_EW : (OUTK == OK_POST2 ? FPCC_LINP2_EW : FPCC_LIN8_EW));
     constexpr int OK = KIND == 0 ? OUTK : OK_I8;
     constexpr int THREADS = (EW + prod_warps<MODE>() + 2) * 32;
     if (MODE == 0 && KIND == 0 && cl2) {  // 2-CTA clusters sharing every weight tile (see CL2 at the kernel)

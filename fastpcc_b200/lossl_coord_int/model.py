@@ -478,7 +478,7 @@ class Model(nn.Module):
             o1 = torch.argsort(ops.morton_encode(xyz, col0=1, msb_axis=0))
             o2 = torch.sort(frame_id[o1].to(torch.int16) if B < 32768 else frame_id[o1], stable=True).indices
             order = o1[o2]
-        xyz = xyz[order].contiguous()
+        xyz = ops.gather_rows(xyz.contiguous(), order)
         tr.mark('sort')
         levels = self.build_pyramid(xyz)
         tr.mark('pyramid')

@@ -293,6 +293,17 @@ def morton_encode(xyz_rows, col0=1, msb_axis=0):
     return codes
 
 
+def gather_rows(rows, idx):
+    """rows[idx] for an int32 [n, 4] coordinate tensor and an int64 permutation (the result of torch.argsort)."""
+    _need(rows, torch.int32, 'rows', 2)
+    _need(idx, torch.int64, 'index', 1)
+    if rows.shape[1] != 4:
+        raise RuntimeError('gather_rows: rows of 4 int32 expected')
+    out = torch.empty((idx.shape[0], 4), dtype=torch.int32, device=rows.device)
+    _call('fpcc_gather_rows16', _p(rows), _p(idx), idx.shape[0], _p(out), _s(), work={'bytes': 40.0 * idx.shape[0]})
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 # GEMMs and epilogues
 # ---------------------------------------------------------------------------------------------

@@ -124,6 +124,9 @@ int fpcc_occ_to_bits(const uint8_t *occ, int n, int32_t *bits_i32 /* [n,8] */, v
  * (ld=4 and xyz pointing at column 1 encodes (b,x,y,z) rows).  msb_axis: 0 -> x most significant
  * (the reference's inverse=True / 'zyx'), 2 -> z most significant ('xyz').  63-bit codes. */
 int fpcc_morton_encode(const int32_t *xyz, int64_t ld, int n, int msb_axis, int64_t *codes, void *stream);
+/* dst[i] = src[idx[i]] for n rows of 16 bytes (int32 (batch,x,y,z) coordinates): applies the sort permutation
+ * `xyz = xyz[order]` of models/convolutional/lossl_coord_int/model.py:396-398 (idx: int64 as torch.argsort returns). */
+int fpcc_gather_rows16(const void *src, const int64_t *idx, int64_t n, void *dst, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Front end: the step immediately before the codec.
