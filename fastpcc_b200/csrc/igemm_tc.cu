@@ -1674,7 +1674,7 @@ static int launch_outk(const TcArgs &a, const CUtensorMap &tmap, const EpiParams
 #define FPCC_LIN8_EW EPI_WARPS_PAIRS
 #endif
     constexpr int EW = KIND != 0 ? (MODE == 0 ? EPI_WARPS_CONV : EPI_WARPS_PAIRS)
-                       : MODE == 0 ? (OUTK == OK_I32 ? FPCC_CONV2_EW : FPCC_CONV1_EW)
+                       : MODE == 0 ? ((OUTK == OK_I32 || OUTK == OK_POST2) ? FPCC_CONV2_EW : FPCC_CONV1_EW)
                                    : (OUTK == OK_I32 ? FPCC_LIN32_EW : (OUTK == OK_POST2 ? FPCC_LINP2_EW : FPCC_LIN8_EW));
     constexpr int OK = KIND == 0 ? OUTK : OK_I8;
     constexpr int THREADS = (EW + prod_warps<MODE>() + 2) * 32;
