@@ -234,6 +234,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_cpu_ms = {}
+
     def timed(fn, steps, warmup, sample_clocks=False):
         for _ in range(warmup):
             fn()
@@ -242,6 +244,7 @@ def main():
             sampler.start()
         barrier()
         total_ms = 0.0
+        cpu0 = time.process_time()  # CPU seconds of ALL threads of this rank: how busy the launching side is
         for _ in range(steps):
             flush.fill_(1)  # evict L2 between timed iterations
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -250,9 +253,10 @@ def main():
             e1.record()
             e1.synchronize()
             total_ms += e0.elapsed_time(e1)
+        host_cpu_ms[fn.__name__] = 1e3 * (time.process_time() - cpu0) / steps
         barrier()
         clocks = sampler.summary() if sampler else None
-        sys.stderr.write(f'[bench] {fn.__name__}: {steps} steps, {total_ms / steps:.1f} ms/step, peak mem '
+        sys.stderr.write(f'[bench] {fn.__name__}: {steps} steps, {total_ms / steps:.1f} ms/step, host CPU {host_cpu_ms[fn.__name__]:.0f} ms/step, peak mem '
                          f'{torch.cuda.max_memory_allocated() / 2**30:.1f} GiB reserved {torch.cuda.memory_reserved() / 2**30:.1f} GiB\n')
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         if world > 1:
@@ -349,7 +353,7 @@ def main():
             'clocks': clocks,
             'e2e': {'value': pts_all / (ms_e2e * 1e-3) / 1e6, 'unit': 'Mpts/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': ms_e2e},
-            'gpu_launches': launches * args.steps,
+            'gpu_launches': launches * args.steps, 'host_cpu_ms_per_step': round(host_cpu_ms.get('step_device', 0.0), 1),
             'roofline': roof, 'cpu_baseline': cpu,
             'hbm_kernels': {'peak_gbs': hbm_peak, 'peak_source': f'MEASURED_PEAKS.json hbm_gbs ({peak_kind})', 'kernels': hbm},
             'kernels': {k: {'ms': round(v['ms'], 3), 'launches': v['launches']} for k, v in stats.items()},

@@ -5,15 +5,18 @@
   dgrad     dA[j]   = sum_k  dOut[nbr_k^T(j)] @ W[k]^T               the SAME kernel on the transposed kernel map: the
                                                                     parameter layout [K, C_in, C_out] is exactly the
                                                                     [K, C_out', C_in'] operand the kernel wants
-  wgrad     dW[k]   = A[in_k]^T @ dOut[out_k]                        per-offset gather + library GEMM (cuBLAS through
-                                                                    torch) on the compacted pair lists; a hand-written
-                                                                    reduction kernel is the next step
+  wgrad     dW[k]   = A[in_k]^T @ dOut[out_k]                        `fpcc_spconv_wgrad_f16`: tcgen05 with BOTH operands
+                                                                    MN-major (the contraction runs over the gathered
+                                                                    rows), split-K tiles meeting in fp32 atomics; a
+                                                                    per-offset library GEMM only above 256 channels
   dbias     = sum_m dOut[m]
 
 MinkowskiEngine computes the same three products per kernel offset (ME backward = transposed gather-GEMM-scatter)."""
 import torch
 
 from . import ops
+
+WGRAD_TC = True  # False: per-offset library GEMMs (A/B switch for the tests)
 
 
 def transpose_table(table: torch.Tensor, n_in: int) -> torch.Tensor:
@@ -60,12 +63,16 @@ class SparseConvFunction(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             in_map, out_map, offsets = ops.kmap_compact(table)
             off = offsets.tolist()
-            a32, g32 = feats.float(), g.float()
-            d_weight = torch.zeros_like(weight, dtype=torch.float32)
-            for k in range(kv):
-                s, e = off[k], off[k + 1]
-                if e > s:
-                    d_weight[k] = a32[in_map[s:e].long()].t() @ g32[out_map[s:e].long()]
+            if WGRAD_TC and ops.wgrad_supported(c_in, c_out):
+                # tensor cores: contraction over the gathered rows, both operands MN-major (fpcc_spconv_wgrad_f16)
+                d_weight = ops.spconv_wgrad_f16(feats.to(dt), g.to(dt), in_map, out_map, off, c_in, c_out)
+            else:  # library GEMM per offset (wide layers)
+                a32, g32 = feats.float(), g.float()
+                d_weight = torch.zeros_like(weight, dtype=torch.float32)
+                for k in range(kv):
+                    s, e = off[k], off[k + 1]
+                    if e > s:
+                        d_weight[k] = a32[in_map[s:e].long()].t() @ g32[out_map[s:e].long()]
             d_weight = d_weight.to(weight.dtype)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             d_bias = g.float().sum(0)

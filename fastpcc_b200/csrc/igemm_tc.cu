@@ -1832,6 +1832,198 @@ extern "C" int fpcc_linear_f16(const void *A, int dtype, int m, int k, const voi
     return launch_tc<1, 2>(a, W, (int64_t)n_groups * n, tiles, ep, fe, out, (cudaStream_t)stream);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Weight gradient of the float sparse convolution on the tensor cores (training: SURVEY 8a row 19, the wgrad product of
+// MinkowskiEngine's / torchsparse's backward, per kernel offset):
+//     dW[k][ci][co] += sum over the pairs p of offset k of  X[in[p]][ci] * dY[out[p]][co]
+// i.e. a GEMM whose CONTRACTION runs over the gathered rows.  Both operands are therefore MN-major for tcgen05 (idesc bits
+// 15 / 16): a gathered row (one pair) is one K index and its channels are contiguous, so the rows the producers copy with
+// cp.async land in shared memory exactly as the SWIZZLE_128B MN-major canonical layout wants them -- atoms of 8 rows x 128 B,
+// the 64-channel atoms of an operand LBO = 8 KB apart, 8-row groups SBO = 1 KB apart -- no transpose anywhere.
+// One tile = up to WG_CHUNK pairs of ONE offset (split-K); the fp32 accumulator [C_in (<= 2 x 128 lanes), C_out columns]
+// lives in TMEM over the whole tile and is added into dW with red.global.add.f32 (partial sums of the tiles of an offset
+// meet there, as in ME / torchsparse's atomics-based backward).
+//   warps 0-3 gather producers, 4-7 epilogue (TMEM lane quarter = warp % 4), 8 TMEM owner + MMA issuer
+// ---------------------------------------------------------------------------------------------
+namespace fpcc {
+constexpr int WG_PAIRS = 64;     // pairs per pipeline stage: four K = 16 instructions
+constexpr int WG_CHUNK = 2048;   // pairs per tile
+constexpr int WG_THREADS = 9 * 32;
+
+struct WgArgs {
+    const uint8_t *X, *dY;              // [*, c_in_p] / [*, c_out_p] fp16 or bf16 rows
+    const int32_t *in_idx, *out_idx;    // compacted pair lists (fpcc_kmap_compact)
+    const int4 *tiles;                  // per tile: (offset k, first pair, end pair, -)
+    int n_tiles;
+    int c_in_p, c_out_p;                // padded channels: c_in_p in {128, 256}, c_out_p a multiple of 64, <= 256
+    int c_in, c_out;                    // real channels of dW [kvol, c_in, c_out]
+    float *dW;
+    int bf16, stages, tmem_cols;
+};
+
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);  // start address
+    d |= (uint64_t)(8192u >> 4) << 16;             // leading byte offset: next 64-element atom along M / N
+    d |= (uint64_t)(1024u >> 4) << 32;             // stride byte offset: next group of 8 K rows
+    d |= (uint64_t)1 << 46;                        // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+    return d;
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int atoms_a = a.c_in_p / 64, atoms_b = a.c_out_p / 64;
+    const int a_bytes = atoms_a * 8192, b_bytes = atoms_b * 8192, st_bytes = a_bytes + b_bytes;
+    uint64_t *bars = (uint64_t *)(smem + (size_t)a.stages * st_bytes);
+    uint64_t *full = bars, *empty = bars + 8, *tmem_full = bars + 16, *tmem_empty = bars + 17;
+    uint32_t *tmem_ptr = (uint32_t *)(bars + 18);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ma = a.c_in_p / 128;
+
+    if (warp == 8 && lane == 0) {
+        for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"((uint32_t)a.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp < 4) {
+        // ---- gather producers: 8 consecutive lanes copy the 8 pieces of one 128-byte line (one pair, one 64-channel atom)
+        const int grp = tid >> 3, piece = tid & 7;  // 16 line groups
+        const int lines = WG_PAIRS * (atoms_a + atoms_b);
+        int it = 0;
+        for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+            const int4 tl = __ldg(&a.tiles[t]);
+            const int n_st = (tl.z - tl.y + WG_PAIRS - 1) / WG_PAIRS;
+            for (int s = 0; s < n_st; ++s, ++it) {
+                const int stage = it % a.stages;
+                mbar_wait(&empty[stage], ((it / a.stages) & 1) ^ 1);
+                const uint32_t sA = smem_u32(smem + (size_t)stage * st_bytes), sB = sA + a_bytes;
+                const int base = tl.y + s * WG_PAIRS;
+                for (int L = grp; L < lines; L += 16) {
+                    const int atom = L / WG_PAIRS, kk = L % WG_PAIRS;  // kk: K row of the stage = pair
+                    const int p = base + kk;
+                    const bool ok = p < tl.z;
+                    const bool is_a = atom < atoms_a;
+                    const int at = is_a ? atom : atom - atoms_a;
+                    const int32_t row = ok ? __ldg(is_a ? &a.in_idx[p] : &a.out_idx[p]) : 0;
+                    const uint8_t *src = (is_a ? a.X + (int64_t)row * a.c_in_p * 2 : a.dY + (int64_t)row * a.c_out_p * 2) + at * 128 + piece * 16;
+                    const uint32_t dst = (is_a ? sA : sB) + at * 8192 + kk * 128 + ((piece ^ (kk & 7)) << 4);
+                    cp_async16(dst, src, ok ? 16u : 0u);
+                }
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full[stage])) : "memory");
+            }
+        }
+    } else if (warp == 8) {
+        // ---- MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | ((uint32_t)a.bf16 << 7) | ((uint32_t)a.bf16 << 10) | (1u << 15) | (1u << 16) |
+                                   ((uint32_t)(a.c_out_p >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            int it = 0, j = 0;
+            for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++j) {
+                const int4 tl = __ldg(&a.tiles[t]);
+                const int n_st = (tl.z - tl.y + WG_PAIRS - 1) / WG_PAIRS;
+                mbar_wait(tmem_empty, (j & 1) ^ 1);  // the epilogue has drained the previous tile's accumulator
+                tc_fence_after();
+                for (int s = 0; s < n_st; ++s, ++it) {
+                    const int stage = it % a.stages;
+                    mbar_wait(&full[stage], (it / a.stages) & 1);
+                    fence_proxy_async();
+                    tc_fence_after();
+                    const uint32_t sA = smem_u32(smem + (size_t)stage * st_bytes), sB = sA + a_bytes;
+#pragma unroll
+                    for (int q = 0; q < WG_PAIRS / 16; ++q) {  // 16 pairs (K) per instruction: 16 rows of 128 B
+                        const uint64_t bd = umma_desc_mn_sw128(sB + q * 2048);
+                        for (int mb = 0; mb < ma; ++mb)
+                            umma_f16(tmem_base + (uint32_t)(mb * a.c_out_p), umma_desc_mn_sw128(sA + mb * 16384 + q * 2048), bd, idesc,
+                                     (uint32_t)(s > 0 || q > 0));
+                    }
+                    umma_commit(&empty[stage]);
+                }
+                if (n_st > 0) umma_commit(tmem_full);
+                else mbar_arrive(tmem_full);
+            }
+        }
+    } else {
+        // ---- epilogue: accumulator rows = input channels (TMEM lanes), columns = output channels
+        const int quarter = warp & 3;
+        int j = 0;
+        for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++j) {
+            const int4 tl = __ldg(&a.tiles[t]);
+            mbar_wait(tmem_full, j & 1);
+            tc_fence_after();
+            if (tl.z > tl.y) {
+                for (int mb = 0; mb < ma; ++mb) {
+                    const int ci = mb * 128 + quarter * 32 + lane;
+                    float *drow = a.dW + ((int64_t)tl.x * a.c_in + ci) * a.c_out;
+                    for (int c0 = 0; c0 < a.c_out_p; c0 += 16) {
+                        uint32_t v[16];
+                        __syncwarp();
+                        tmem_ld16(tmem_base + (uint32_t)(mb * a.c_out_p + c0) + ((uint32_t)(quarter * 32) << 16), v);
+                        if (ci < a.c_in) {
+#pragma unroll
+                            for (int q = 0; q < 16; ++q)
+                                if (c0 + q < a.c_out) atomicAdd(drow + c0 + q, __uint_as_float(v[q]));
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols) : "memory");
+    }
+}
+}  // namespace fpcc
+
+extern "C" int fpcc_spconv_wgrad_f16(const void *x, const void *dy, int dtype, int c_in_p, int c_out_p, const int32_t *in_idx,
+                                     const int32_t *out_idx, const int32_t *tiles, int n_tiles, float *dw, int c_in, int c_out,
+                                     void *stream) {
+    using namespace fpcc;
+    FPCC_REQUIRE(x && dy && in_idx && out_idx && tiles && dw, "spconv_wgrad_f16: NULL pointer");
+    FPCC_REQUIRE(dtype == 0 || dtype == 1, "spconv_wgrad_f16: dtype 0 (fp16) or 1 (bf16)");
+    FPCC_REQUIRE((c_in_p == 128 || c_in_p == 256) && c_out_p % 64 == 0 && c_out_p >= 64 && c_out_p <= 256,
+                 "spconv_wgrad_f16: padded channels must be C_in in {128, 256}, C_out a multiple of 64 up to 256 (got %d, %d)", c_in_p, c_out_p);
+    FPCC_REQUIRE(c_in > 0 && c_in <= c_in_p && c_out > 0 && c_out <= c_out_p, "spconv_wgrad_f16: real channels exceed the padded ones");
+    FPCC_REQUIRE((((uintptr_t)x | (uintptr_t)dy) & 15) == 0, "spconv_wgrad_f16: rows must be 16-byte aligned");
+    if (n_tiles <= 0) return FPCC_OK;
+    WgArgs a;
+    a.X = (const uint8_t *)x; a.dY = (const uint8_t *)dy; a.in_idx = in_idx; a.out_idx = out_idx; a.tiles = (const int4 *)tiles;
+    a.n_tiles = n_tiles; a.c_in_p = c_in_p; a.c_out_p = c_out_p; a.c_in = c_in; a.c_out = c_out; a.dW = dw; a.bf16 = dtype;
+    const int st_bytes = (c_in_p / 64 + c_out_p / 64) * 8192;
+    a.stages = (int)((200 * 1024) / st_bytes);
+    if (a.stages > 6) a.stages = 6;
+    int cols = (c_in_p / 128) * c_out_p, pow2 = 32;
+    while (pow2 < cols) pow2 <<= 1;
+    a.tmem_cols = pow2;
+    const size_t smem = 1024 + (size_t)a.stages * st_bytes + 256;
+    static bool configured = false;
+    if (!configured) {
+        FPCC_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    int sms = g_sm_budget > 0 && g_sm_budget < sm_count() ? g_sm_budget : sm_count();
+    const int grid = n_tiles < sms ? n_tiles : sms;
+    wgrad_tc_kernel<<<grid, WG_THREADS, smem, (cudaStream_t)stream>>>(a);
+    FPCC_LAUNCH_CHECK();
+    return FPCC_OK;
+}
+
 extern "C" int fpcc_mma_i8_peak(int iters, int n, double *tops_out, void *stream) {
     using namespace fpcc;
     FPCC_REQUIRE(iters > 0 && tops_out && n >= 16 && n <= 256 && n % 16 == 0, "mma_i8_peak: bad arguments");

@@ -608,6 +608,41 @@ def spconv_f16(feats, weight_t, table, bias=None, act=ACT_NONE, slope=0.0, resid
     return out
 
 
+WGRAD_CHUNK = 2048  # pairs per tile of fpcc_spconv_wgrad_f16 (csrc/igemm_tc.cu: WG_CHUNK)
+
+
+def wgrad_supported(c_in, c_out):
+    """channel counts the tensor-core weight-gradient kernel takes (after padding to 128 / 256 x a multiple of 64)"""
+    return c_in <= 256 and c_out <= 256
+
+
+def spconv_wgrad_f16(x, dy, in_map, out_map, offsets_host, c_in, c_out):
+    """dW[k] = x[in_k]^T @ dy[out_k] for every kernel offset on the tensor cores (fp32 accumulation, fp32 result
+    [kvol, c_in, c_out]).  x [n_in, >= c_in], dy [n_out, >= c_out] fp16 / bf16; in_map / out_map / offsets_host: the
+    compacted pair lists of `kmap_compact` (offsets as a host list)."""
+    if x.dtype not in _F_DT or dy.dtype != x.dtype:
+        raise RuntimeError('spconv_wgrad_f16: fp16/bf16 inputs of one dtype expected')
+    if not wgrad_supported(c_in, c_out):
+        raise RuntimeError('spconv_wgrad_f16: at most 256 input and output channels')
+    kv = len(offsets_host) - 1
+    c_in_p = 128 if c_in <= 128 else 256
+    c_out_p = (c_out + 63) // 64 * 64
+    xp = torch.nn.functional.pad(x[:, :c_in], (0, c_in_p - c_in)).contiguous() if x.shape[1] != c_in_p else x.contiguous()
+    gp = torch.nn.functional.pad(dy[:, :c_out], (0, c_out_p - c_out)).contiguous() if dy.shape[1] != c_out_p else dy.contiguous()
+    tiles = []
+    for k in range(kv):
+        s, e = int(offsets_host[k]), int(offsets_host[k + 1])
+        for b in range(s, e, WGRAD_CHUNK):
+            tiles.append((k, b, min(e, b + WGRAD_CHUNK), 0))
+    dw = torch.zeros((kv, c_in, c_out), dtype=torch.float32, device=x.device)
+    if tiles:
+        tl = torch.tensor(tiles, dtype=torch.int32).to(x.device, non_blocking=True)
+        n_pairs = int(offsets_host[-1])
+        _call('fpcc_spconv_wgrad_f16', _p(xp), _p(gp), _F_DT[x.dtype], c_in_p, c_out_p, _p(in_map), _p(out_map), _p(tl), len(tiles),
+              _p(dw), c_in, c_out, _s(), tag='spconv_wgrad_tc', work={'ops': 2.0 * n_pairs * c_in * c_out})
+    return dw
+
+
 def linear_f16(a, weight, bias=None, act=ACT_NONE, slope=0.0, residual=None, post_act=ACT_NONE, post_slope=0.0,
                out_dtype=None, sel=None, n_out_rows=None, out=None):
     """Fused fp16/bf16 linear: a [m, k], weight [n_groups*n, k]; sel = (sel_row, sel_out, offsets) as in `linear`."""

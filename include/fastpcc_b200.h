@@ -290,6 +290,16 @@ int fpcc_set_sm_budget(int sms);
 int fpcc_spconv_f16(const void *feats, int dtype, int n_in, int c_in, const void *weight, int kvol, int c_out,
                     const int32_t *nbr_table, int64_t ld, int n_out, const int32_t *row_perm, const float *bias, int act, float slope,
                     const void *residual, int post_act, float post_slope, void *out, int out_type, void *stream);
+/* Weight gradient of fpcc_spconv_f16 on the tensor cores (training; the wgrad product of MinkowskiEngine's /
+ * torchsparse's backward: per kernel offset dW[k] = X[in_k]^T * dY[out_k], reference call sites train.py:359-404 via
+ * loss.backward()).  x [*, c_in_p], dy [*, c_out_p] fp16 (dtype 0) / bf16 (1) rows padded to c_in_p in {128, 256} and
+ * c_out_p a multiple of 64 (<= 256); in_idx / out_idx are the compacted pair lists of fpcc_kmap_compact; tiles holds
+ * n_tiles int32 quadruples (offset k, first pair, end pair, 0), each at most 2048 pairs of ONE offset; dw is the fp32
+ * [kvol, c_in, c_out] gradient, ACCUMULATED into (zero it first).  Contraction over the gathered rows: tcgen05.mma with
+ * both operands MN-major; partial sums of the tiles of an offset meet in dw through fp32 atomics. */
+int fpcc_spconv_wgrad_f16(const void *x, const void *dy, int dtype, int c_in_p, int c_out_p, const int32_t *in_idx,
+                          const int32_t *out_idx, const int32_t *tiles, int n_tiles, float *dw, int c_in, int c_out,
+                          void *stream);
 int fpcc_linear_f16(const void *A, int dtype, int m, int k, const void *W, int n, const int32_t *sel_row,
                     const int32_t *sel_out, const int32_t *sel_offsets, int n_groups, int n_sel, const float *bias,
                     int act, float slope, const void *residual, int post_act, float post_slope, void *out,

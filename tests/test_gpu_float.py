@@ -165,3 +165,32 @@ def test_sparse_conv_autograd_matches_dense_reference():
         losses.append(float(loss.detach()))
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in blk.parameters())
     assert losses[-1] < losses[0]
+
+
+@pytest.mark.parametrize('cin,cout,dt', [(128, 128, torch.float16), (256, 192, torch.bfloat16), (64, 256, torch.float16), (24, 40, torch.float16)])
+def test_tensor_core_wgrad_equals_per_offset_gemm(cin, cout, dt):
+    """fpcc_spconv_wgrad_f16 (tcgen05, both operands MN-major, split-K tiles meeting in fp32 atomics) against the
+    per-offset gather + fp32 matmul it replaces, on the 3x3x3 map of a surface cloud (tiles of one offset larger and
+    smaller than 2048 pairs, offsets without pairs on the strided map).  Tolerance: fp32 accumulation of exact
+    fp16 / bf16 products in a different order, 1e-3 of the largest entry."""
+    from fastpcc_b200 import synth, ops
+    C = synth.with_batch(synth.surface_cloud(6, bits=8, n_target=12000))
+    C = torch.from_numpy(C[np.lexsort((C[:, 3], C[:, 2], C[:, 1], C[:, 0]))]).cuda()
+    keys, vals = ops.hash_build(C)
+    for ks, st, out_c in (((3, 3, 3), (1, 1, 1), C),
+                          ((2, 2, 2), (2, 2, 2), torch.unique(torch.cat([C[:, :1], C[:, 1:] >> 1], 1), dim=0))):
+        table = ops.kmap_lookup(keys, vals, out_c.contiguous(), ks, st)
+        kv = table.shape[0]
+        x = torch.randn(C.shape[0], cin, device='cuda').to(dt)
+        g = torch.randn(table.shape[1], cout, device='cuda').to(dt)
+        in_map, out_map, offsets = ops.kmap_compact(table)
+        off = offsets.tolist()
+        got = ops.spconv_wgrad_f16(x, g, in_map, out_map, off, cin, cout)
+        want = torch.zeros((kv, cin, cout), dtype=torch.float32, device='cuda')
+        for k in range(kv):
+            s_, e_ = off[k], off[k + 1]
+            if e_ > s_:
+                want[k] = x.float()[in_map[s_:e_].long()].t() @ g.float()[out_map[s_:e_].long()]
+        err = float((got - want).abs().max() / want.abs().max())
+        assert got.shape == want.shape and err < 1e-3, (ks, cin, cout, err)
+
