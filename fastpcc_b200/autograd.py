@@ -29,6 +29,39 @@ def transpose_table(table: torch.Tensor, n_in: int) -> torch.Tensor:
     return tt
 
 
+# Tensors derived from a kernel map (transposed map for dgrad, compacted pair lists + tile offsets for wgrad) are the same
+# for every layer and every step that uses the map: built once per table.  The entry keeps the table itself alive, so its
+# address cannot be reused by another tensor while the entry exists; a handful of maps are live at a time.
+_derived_cache = {}
+_DERIVED_MAX = 64
+
+
+def _derived(table: torch.Tensor, n_in: int) -> dict:
+    key = (table.data_ptr(), tuple(table.shape), n_in, table.device.index)
+    ent = _derived_cache.get(key)
+    if ent is None:
+        if len(_derived_cache) >= _DERIVED_MAX:
+            _derived_cache.pop(next(iter(_derived_cache)))
+        ent = {'table': table}
+        _derived_cache[key] = ent
+    return ent
+
+
+def _transposed(table, n_in):
+    ent = _derived(table, n_in)
+    if 'tt' not in ent:
+        ent['tt'] = transpose_table(table, n_in)
+    return ent['tt']
+
+
+def _compacted(table, n_in):
+    ent = _derived(table, n_in)
+    if 'pairs' not in ent:
+        in_map, out_map, offsets = ops.kmap_compact(table)
+        ent['pairs'] = (in_map, out_map, offsets.tolist())
+    return ent['pairs']
+
+
 class SparseConvFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feats, weight, bias, table, compute_dtype):
@@ -58,11 +91,10 @@ class SparseConvFunction(torch.autograd.Function):
             gp = torch.nn.functional.pad(g.to(dt), (0, cout_p - c_out)).contiguous()
             w = torch.zeros((kv, cin_p, cout_p), dtype=dt, device=weight.device)   # [K, "C_out" = c_in, "C_in" = c_out]
             w[:, :c_in, :c_out] = weight.detach().to(dt)
-            tt = transpose_table(table, feats.shape[0])
+            tt = _transposed(table, feats.shape[0])
             d_feats = ops.spconv_f16(gp, w, tt, out_dtype=torch.float32)[:, :c_in].to(feats.dtype)
         if ctx.needs_input_grad[1]:
-            in_map, out_map, offsets = ops.kmap_compact(table)
-            off = offsets.tolist()
+            in_map, out_map, off = _compacted(table, feats.shape[0])
             if WGRAD_TC and ops.wgrad_supported(c_in, c_out):
                 # tensor cores: contraction over the gathered rows, both operands MN-major (fpcc_spconv_wgrad_f16)
                 d_weight = ops.spconv_wgrad_f16(feats.to(dt), g.to(dt), in_map, out_map, off, c_in, c_out)

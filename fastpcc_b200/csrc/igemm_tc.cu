@@ -1898,28 +1898,47 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgArgs a) {
     const uint32_t tmem_base = *tmem_ptr;
 
     if (warp < 4) {
-        // ---- gather producers: 8 consecutive lanes copy the 8 pieces of one 128-byte line (one pair, one 64-channel atom)
-        const int grp = tid >> 3, piece = tid & 7;  // 16 line groups
-        const int lines = WG_PAIRS * (atoms_a + atoms_b);
+        // ---- gather producers: 8 consecutive lanes copy the 8 pieces of one 128-byte line (one pair, one 64-channel atom).
+        // Line group g (16 of them) serves the pairs g, g+16, g+32, g+48 of a stage for every atom of both operands; their
+        // 4 + 4 row indices are fetched one STAGE ahead into registers (a dependent index load per line serialised the
+        // whole stage behind the L2 latency: 43 TFLOP/s for this kernel).
+        const int grp = tid >> 3, piece = tid & 7;
         int it = 0;
+        int32_t nx_in[4], nx_out[4];
+        auto fetch_idx = [&](int t, int s) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { nx_in[i] = -1; nx_out[i] = -1; }
+            if (t >= a.n_tiles) return;
+            const int4 tl = __ldg(&a.tiles[t]);
+            const int base = tl.y + s * WG_PAIRS;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int p = base + grp + 16 * i;
+                if (p < tl.z) { nx_in[i] = __ldg(&a.in_idx[p]); nx_out[i] = __ldg(&a.out_idx[p]); }
+            }
+        };
+        fetch_idx(blockIdx.x, 0);
         for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
             const int4 tl = __ldg(&a.tiles[t]);
             const int n_st = (tl.z - tl.y + WG_PAIRS - 1) / WG_PAIRS;
             for (int s = 0; s < n_st; ++s, ++it) {
+                int32_t cin_[4], cout_[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { cin_[i] = nx_in[i]; cout_[i] = nx_out[i]; }
+                if (s + 1 < n_st) fetch_idx(t, s + 1);
+                else fetch_idx(t + gridDim.x, 0);
                 const int stage = it % a.stages;
                 mbar_wait(&empty[stage], ((it / a.stages) & 1) ^ 1);
                 const uint32_t sA = smem_u32(smem + (size_t)stage * st_bytes), sB = sA + a_bytes;
-                const int base = tl.y + s * WG_PAIRS;
-                for (int L = grp; L < lines; L += 16) {
-                    const int atom = L / WG_PAIRS, kk = L % WG_PAIRS;  // kk: K row of the stage = pair
-                    const int p = base + kk;
-                    const bool ok = p < tl.z;
-                    const bool is_a = atom < atoms_a;
-                    const int at = is_a ? atom : atom - atoms_a;
-                    const int32_t row = ok ? __ldg(is_a ? &a.in_idx[p] : &a.out_idx[p]) : 0;
-                    const uint8_t *src = (is_a ? a.X + (int64_t)row * a.c_in_p * 2 : a.dY + (int64_t)row * a.c_out_p * 2) + at * 128 + piece * 16;
-                    const uint32_t dst = (is_a ? sA : sB) + at * 8192 + kk * 128 + ((piece ^ (kk & 7)) << 4);
-                    cp_async16(dst, src, ok ? 16u : 0u);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int kk = grp + 16 * i;  // K row of the stage = pair
+                    const uint32_t sw = (uint32_t)((piece ^ (kk & 7)) << 4) + (uint32_t)kk * 128;
+                    const bool ok = cin_[i] >= 0;
+                    const uint8_t *xa = a.X + (int64_t)(ok ? cin_[i] : 0) * a.c_in_p * 2 + piece * 16;
+                    const uint8_t *ya = a.dY + (int64_t)(ok ? cout_[i] : 0) * a.c_out_p * 2 + piece * 16;
+                    for (int at = 0; at < atoms_a; ++at) cp_async16(sA + at * 8192 + sw, xa + at * 128, ok ? 16u : 0u);
+                    for (int at = 0; at < atoms_b; ++at) cp_async16(sB + at * 8192 + sw, ya + at * 128, ok ? 16u : 0u);
                 }
                 asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full[stage])) : "memory");
             }
@@ -1971,9 +1990,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgArgs a) {
                         __syncwarp();
                         tmem_ld16(tmem_base + (uint32_t)(mb * a.c_out_p + c0) + ((uint32_t)(quarter * 32) << 16), v);
                         if (ci < a.c_in) {
+                            if ((a.c_out & 3) == 0) {  // 16-byte aligned rows: four columns per reduction
 #pragma unroll
-                            for (int q = 0; q < 16; ++q)
-                                if (c0 + q < a.c_out) atomicAdd(drow + c0 + q, __uint_as_float(v[q]));
+                                for (int q = 0; q < 16; q += 4)
+                                    if (c0 + q < a.c_out)
+                                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(drow + c0 + q), "f"(__uint_as_float(v[q])),
+                                                     "f"(__uint_as_float(v[q + 1])), "f"(__uint_as_float(v[q + 2])), "f"(__uint_as_float(v[q + 3])) : "memory");
+                            } else {
+#pragma unroll
+                                for (int q = 0; q < 16; ++q)
+                                    if (c0 + q < a.c_out) atomicAdd(drow + c0 + q, __uint_as_float(v[q]));
+                            }
                         }
                     }
                 }

@@ -609,6 +609,7 @@ def spconv_f16(feats, weight_t, table, bias=None, act=ACT_NONE, slope=0.0, resid
 
 
 WGRAD_CHUNK = 2048  # pairs per tile of fpcc_spconv_wgrad_f16 (csrc/igemm_tc.cu: WG_CHUNK)
+_wgrad_tiles = {}
 
 
 def wgrad_supported(c_in, c_out):
@@ -629,16 +630,22 @@ def spconv_wgrad_f16(x, dy, in_map, out_map, offsets_host, c_in, c_out):
     c_out_p = (c_out + 63) // 64 * 64
     xp = torch.nn.functional.pad(x[:, :c_in], (0, c_in_p - c_in)).contiguous() if x.shape[1] != c_in_p else x.contiguous()
     gp = torch.nn.functional.pad(dy[:, :c_out], (0, c_out_p - c_out)).contiguous() if dy.shape[1] != c_out_p else dy.contiguous()
-    tiles = []
-    for k in range(kv):
-        s, e = int(offsets_host[k]), int(offsets_host[k + 1])
-        for b in range(s, e, WGRAD_CHUNK):
-            tiles.append((k, b, min(e, b + WGRAD_CHUNK), 0))
+    tkey = (tuple(int(o) for o in offsets_host), x.device.index)
+    tl = _wgrad_tiles.get(tkey)
+    if tl is None:  # the tile list of a kernel map is the same for every layer and step that uses the map
+        tiles = []
+        for k in range(kv):
+            s, e = int(offsets_host[k]), int(offsets_host[k + 1])
+            for b in range(s, e, WGRAD_CHUNK):
+                tiles.append((k, b, min(e, b + WGRAD_CHUNK), 0))
+        tl = torch.tensor(tiles, dtype=torch.int32).reshape(-1, 4).to(x.device)
+        if len(_wgrad_tiles) >= 64:
+            _wgrad_tiles.pop(next(iter(_wgrad_tiles)))
+        _wgrad_tiles[tkey] = tl
     dw = torch.zeros((kv, c_in, c_out), dtype=torch.float32, device=x.device)
-    if tiles:
-        tl = torch.tensor(tiles, dtype=torch.int32).to(x.device, non_blocking=True)
+    if tl.shape[0]:
         n_pairs = int(offsets_host[-1])
-        _call('fpcc_spconv_wgrad_f16', _p(xp), _p(gp), _F_DT[x.dtype], c_in_p, c_out_p, _p(in_map), _p(out_map), _p(tl), len(tiles),
+        _call('fpcc_spconv_wgrad_f16', _p(xp), _p(gp), _F_DT[x.dtype], c_in_p, c_out_p, _p(in_map), _p(out_map), _p(tl), tl.shape[0],
               _p(dw), c_in, c_out, _s(), tag='spconv_wgrad_tc', work={'ops': 2.0 * n_pairs * c_in * c_out})
     return dw
 
