@@ -180,6 +180,13 @@ def main():
     from fastpcc_b200 import _lib, ops, synth
     from fastpcc_b200.lossl_coord_int import Config, Model
     assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback exists)'
+    # Waiting host threads spin by default (lowest latency: 426 ms per step at N = 1) and then hold 2.6 cores per rank (three
+    # launching threads); sleeping instead costs 3 % of the step (440 ms) and 0.5 core.  Sleep when the ranks of this job
+    # would otherwise claim most of the box's cores (FPCC_SPIN_SYNC=1 / 0 forces either).
+    spin = os.environ.get('FPCC_SPIN_SYNC')
+    blocking = (spin == '0') if spin in ('0', '1') else (3 * world >= 0.6 * (os.cpu_count() or 1))
+    if blocking:
+        _lib.load(build_if_missing=False).fpcc_set_blocking_sync(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
@@ -345,7 +352,7 @@ def main():
             'metric': 'encode+decode Mpts/s', 'value': pts_all / (ms_dev * 1e-3) / 1e6, 'unit': 'Mpts/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_dev,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int8', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'frames_per_step_per_gpu': args.frames, 'concurrent_groups': G, 'schedule': 'per-group encode->decode pipelines on prioritised streams' if pipe else 'all groups encode, then all groups decode', 'points_per_step': pts_all,
+            'config': {'workload': WORKLOAD, 'frames_per_step_per_gpu': args.frames, 'concurrent_groups': G, 'schedule': 'per-group encode->decode pipelines on prioritised streams' if pipe else 'all groups encode, then all groups decode', 'host_sync': 'blocking' if blocking else 'spin', 'points_per_step': pts_all,
                        'l2': 'flushed between timed iterations (256 MB write)', 'weights': 'seeded random int8 (seed 7)',
                        'roundtrip_lossless': bool(lossless), 'parity_sample': parity,
                        'parity_note': 'bitstream of the CUDA codec == bitstream of the CPU oracle (pinned to the reference Python, '

@@ -64,6 +64,7 @@ SIGNATURES = {
     'fpcc_linear_f16': (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _i, C.c_float, _vp, _i, C.c_float, _vp, _i, _vp]),
     'fpcc_set_tc_mode': (_i, [_i]),
     'fpcc_set_sm_budget': (_i, [_i]),
+    'fpcc_set_blocking_sync': (_i, [_i]),
     'fpcc_mma_i8_peak': (_i, [_i, _i, _vp, _vp]),
     'fpcc_gemm_engine': (_i, [_i, _i, _i, _i]),
     'fpcc_softmax_i32': (_i, [_vp, _i64, _i, _vp, _vp]),

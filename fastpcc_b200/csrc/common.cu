@@ -55,6 +55,16 @@ int check_epilogue(const fpcc_epilogue *e, bool allow_residual) {
 extern "C" const char *fpcc_last_error(void) { return fpcc::g_err; }
 extern "C" int fpcc_version(void) { return 100; }
 
+// Host threads that wait for the device (stream / event synchronisation, blocking copies) sleep instead of spinning.
+// One process per GPU with several launching threads each (coding groups): under the default policy every waiting
+// thread burns a core (measured: 2.6 cores per rank at 3 groups), which starves the ranks of an 8-GPU job on a box with
+// fewer cores than that.  Must be called before the device's context is created to take effect everywhere.
+extern "C" int fpcc_set_blocking_sync(int device) {
+    FPCC_CUDA(cudaSetDevice(device));
+    FPCC_CUDA(cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync));
+    return FPCC_OK;
+}
+
 extern "C" int fpcc_device_check(int *cc_major, int *cc_minor, int *sm) {
     int dev = 0;
     FPCC_CUDA(cudaGetDevice(&dev));

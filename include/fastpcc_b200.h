@@ -280,6 +280,9 @@ int fpcc_set_tc_mode(int mode);
 /* Persistent GEMM kernels occupy one whole SM per CTA.  When serial range-coder kernels of another CUDA stream
  * should run beside them, cap the GEMM grids at `sms` SMs (0 = all SMs) so that the coder blocks find free SMs. */
 int fpcc_set_sm_budget(int sms);
+/* Waiting host threads sleep instead of spinning (cudaDeviceScheduleBlockingSync) on `device`; call before the first
+ * CUDA work of the process.  One process per GPU with several launching threads otherwise burns 2-3 cores per rank. */
+int fpcc_set_blocking_sync(int device);
 /* fp16 / bf16 twins of fpcc_spconv_i8 / fpcc_linear_i8 on tcgen05.mma.kind::f16 with fp32 accumulation in TMEM,
  * for the float layer API (MinkowskiEngine blocks of lib/minkowski_sparse_conv_layers.py:31-280, torchsparse
  * spnn.Conv3d of lossl_coord/model.py:34-46).  dtype: 0 fp16, 1 bf16 (features and weights); weight is
