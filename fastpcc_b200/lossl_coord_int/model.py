@@ -375,6 +375,13 @@ class Model(nn.Module):
     # ---- compress ---------------------------------------------------------------------------
     MAX_CDF = 130  # bottom-coordinate alphabet: the stream stores len(cdf)-2 <= 128 (model.py:371)
 
+    MAX_GROUP_FRAMES = 1022  # the coordinate key packs the frame index into 10 bits (include/fastpcc_b200.h: batch < 1023)
+
+    def _check_group_size(self, B: int):
+        if B > self.MAX_GROUP_FRAMES:
+            raise ValueError(f'{B} frames in one coding group: the coordinate hash keys hold at most {self.MAX_GROUP_FRAMES} frame '
+                             f'indices; code the batch in more groups (n_groups >= {-(-B // self.MAX_GROUP_FRAMES)})')
+
     def _run_groups(self, fn, items: list, n_groups: int) -> list:
         """Runs `fn` on `n_groups` contiguous slices of `items`, each in its own thread and CUDA stream, so that the
         serial range-coder kernels of one group overlap the tensor-core kernels of another.  Order is preserved."""
@@ -383,6 +390,17 @@ class Model(nn.Module):
             return fn(items)
         import threading
         bounds = [len(items) * g // n_groups for g in range(n_groups + 1)]
+        import os
+        split = os.environ.get('FPCC_GROUP_SPLIT')  # experiments: relative slice sizes, e.g. "5,4,3" (first = highest priority)
+        if split:
+            w = [float(v) for v in split.split(',')]
+            if len(w) == n_groups:
+                acc, tot = 0.0, sum(w)
+                bounds = [0]
+                for v in w:
+                    acc += v
+                    bounds.append(int(round(len(items) * acc / tot)))
+                bounds[-1] = len(items)
         out: list = [None] * n_groups
         err: list = []
         cur = torch.cuda.current_stream(self.device)
@@ -451,6 +469,7 @@ class Model(nn.Module):
         coordinate key), one rANS stream per frame, all streams coded concurrently.  Each returned bitstream is
         byte-identical to `compress(frame)` of the reference."""
         dev, B, L = self.device, len(frames), self._num_levels()
+        self._check_group_size(B)
         tr = _Trace()
         tr.mark('start')
         # model.py:396-398 for all frames at once: per-frame minimum, shift, Morton code (x most significant), then
@@ -588,6 +607,7 @@ class Model(nn.Module):
     @torch.no_grad()
     def _decompress_group(self, streams: List[bytes]) -> List[torch.Tensor]:
         dev, B, L, V = self.device, len(streams), self._num_levels(), self.MAX_CDF
+        self._check_group_size(B)
         heads = np.array([[int.from_bytes(s[2 * i: 2 * i + 2], 'little') for i in range(4)] for s in streams], dtype=np.int64)
         coord_offset = torch.from_numpy(heads[:, :3].astype(np.int32)).to(dev)
         nb = torch.from_numpy(heads[:, 3]).to(dev)                        # bottom points per frame

@@ -44,6 +44,7 @@ def enable_profile(on: bool):
     """When on, every C-ABI call is bracketed by CUDA events on the current stream."""
     global _prof
     _prof = [] if on else None
+    _pairs_cache.clear()  # its entries keep kernel maps alive: only for the duration of one instrumented pass
     return _prof
 
 
@@ -86,12 +87,16 @@ _pairs_cache = {}
 
 
 def _pairs_of(table):
-    key = (table.data_ptr(), tuple(table.shape))
-    if key not in _pairs_cache:
-        if len(_pairs_cache) > 256:
+    """matched pairs of a kernel map (instrumented pass only).  The entry holds the table itself, so its address cannot be
+    reused by another map while the count is cached (a bare data_ptr key could hand back a stale count)."""
+    key = (table.data_ptr(), tuple(table.shape), table._version)
+    ent = _pairs_cache.get(key)
+    if ent is None:
+        if len(_pairs_cache) > 64:
             _pairs_cache.clear()
-        _pairs_cache[key] = int(torch.count_nonzero(table).item())
-    return _pairs_cache[key]
+        ent = (table, int(torch.count_nonzero(table).item()))
+        _pairs_cache[key] = ent
+    return ent[1]
 
 
 _ws_cache = {}
