@@ -312,6 +312,10 @@ def main():
             'launches': conv['launches'], 'ms_per_step': conv['ms'],
             'executed_mma_tops': (conv.get('exec_ops', 0.0) / (conv['ms'] * 1e-3) / 1e12) if conv['ms'] else 0.0,
             'share_of_step': conv['ms'] / ms_dev if ms_dev else 0.0}
+    if traffic and roof['algorithmic_bytes_per_launch']:
+        # the ncu capture ran the bench's own schedule (launches of frames / groups scans), the instrumented pass one group
+        per = traffic.get('frames_per_launch', args.frames) / float(args.frames)
+        roof['traffic_over_algorithmic'] = round(traffic['dram_bytes_per_launch'] / (roof['algorithmic_bytes_per_launch'] * per), 2)
     roof['frac_vs_own_probe'] = roof['achieved'] / int8_probe if int8_probe else 0.0
     roof['frac'] = roof['achieved'] / roof['peak'] if roof['peak'] else 0.0
     launches = sum(v['launches'] for v in stats.values())

@@ -37,6 +37,9 @@ for dt in (torch.float16, torch.bfloat16):
     gb = (pairs * ch * 2 + n * ch * 2 + 27 * n * 4) / 1e9
     print(f'{dt}: surface n={n} C={ch} pairs/pt={pairs / n:.2f}: {ms:.3f} ms  algorithmic {alg / ms / 1e9:.1f} TFLOP/s  '
           f'executed {mma / ms / 1e9:.1f} TFLOP/s  gathered bytes {gb / ms * 1e3:.0f} GB/s')
+    tp, perm = ops.group_rows(table)  # rows grouped by neighbour pattern: what the layer API does above GROUP_ROWS_MIN rows
+    ms = t(lambda: ops.spconv_f16(f, w, tp, bias=b, act=ops.ACT_RELU, row_perm=perm))
+    print(f'{dt}: same conv on grouped rows: {ms:.3f} ms  algorithmic {alg / ms / 1e9:.1f} TFLOP/s')
     w1 = (torch.randn((ch, ch), generator=g, device='cuda') / ch ** 0.5).to(dt)
     ms = t(lambda: ops.linear_f16(f, w1, bias=b, act=ops.ACT_RELU))
     print(f'{dt}: linear n={n} {ch}->{ch}: {ms:.3f} ms  {2.0 * n * ch * ch / ms / 1e9:.1f} TFLOP/s  {(2 * n * ch * 2) / ms / 1e6:.0f} GB/s')
