@@ -46,6 +46,7 @@ int check_epilogue(const fpcc_epilogue *e, bool allow_residual) {
         FPCC_REQUIRE(e->post_shift >= 0 && e->post_shift < 63, "epilogue: post_shift %d out of range", e->post_shift);
     } else {
         FPCC_REQUIRE(e->post_requant_slope == nullptr, "epilogue: post_requant_slope without post_requant_mul");
+        FPCC_REQUIRE(e->aux_out == nullptr, "epilogue: aux_out without post_requant_mul");
     }
     return FPCC_OK;
 }

@@ -254,6 +254,7 @@ struct EpiCtx {
     const int32_t *residual;   // entries of this chunk, or NULL
     bool has_post;
     int nvalid;
+    int8_t *aux;               // dual output: int8 entries of this chunk, or NULL
 };
 
 __device__ __forceinline__ int32_t sat_s8(int64_t r) { int32_t o; asm("cvt.sat.s8.s64 %0, %1;" : "=r"(o) : "l"(r)); return o; }
@@ -279,6 +280,7 @@ __device__ __forceinline__ int32_t epi_exact(int32_t a32, int32_t bias, uint32_t
 // (requant.cu:7-26) applied to a finished int32 value.
 struct Post2 {
     bool on, has_slope;
+    bool dual;  // the int32 rows are stored as well (fpcc_epilogue::aux_out); the int8 rows go to the aux pointer
     int32_t slope;
     uint32_t mul;
     int64_t zp;
@@ -287,6 +289,7 @@ struct Post2 {
 __device__ __forceinline__ Post2 load_post2(const EpiParams &ep) {
     Post2 p2;
     p2.on = ep.post_mul != nullptr;
+    p2.dual = p2.on && ep.aux_out != nullptr;
     p2.has_slope = p2.on && ep.post_slope2 != nullptr;
     p2.slope = p2.has_slope ? ep.post_slope2[0] : 0;
     p2.mul = p2.on ? ep.post_mul[0] : 0u;
@@ -384,12 +387,16 @@ __device__ __forceinline__ void epi_store_chunk(int32_t (&o)[EC], const EpiCtx &
             for (int q = 0; q < EC; ++q) o[q] = sat_s32(prelu_q25((int64_t)o[q], cx.post));
         }
     }
-    if (OUT == FPCC_OUT_I32 && p2.on) {  // the int32 result feeds the fused second stage; int8 rows are stored
+    if (OUT == FPCC_OUT_I32 && p2.on && p2.dual) {  // dual output: int8 rows of the second stage to the aux buffer, int32 rows below
+#pragma unroll
+        for (int q = 0; q < EC; ++q)
+            if (q < cx.nvalid) cx.aux[q] = (int8_t)post2_exact(o[q], p2);
+    } else if (OUT == FPCC_OUT_I32 && p2.on) {  // the int32 result feeds the fused second stage; int8 rows are stored
 #pragma unroll
         for (int q = 0; q < EC; ++q) o[q] = post2_exact(o[q], p2);
     }
     if (vec) {  // nvalid == EC here (N is a multiple of 16)
-        if (OUT == FPCC_OUT_I8 || (OUT == FPCC_OUT_I32 && p2.on)) {
+        if (OUT == FPCC_OUT_I8 || (OUT == FPCC_OUT_I32 && p2.on && !p2.dual)) {
             uint32_t w[EC / 4];
 #pragma unroll
             for (int t = 0; t < EC / 4; ++t) {
@@ -414,7 +421,7 @@ __device__ __forceinline__ void epi_store_chunk(int32_t (&o)[EC], const EpiCtx &
 #pragma unroll
         for (int q = 0; q < EC; ++q) {
             if (q < cx.nvalid) {
-                if (OUT == FPCC_OUT_I8 || (OUT == FPCC_OUT_I32 && p2.on)) ((int8_t *)optr)[q] = (int8_t)max(min(o[q], 127), -128);
+                if (OUT == FPCC_OUT_I8 || (OUT == FPCC_OUT_I32 && p2.on && !p2.dual)) ((int8_t *)optr)[q] = (int8_t)max(min(o[q], 127), -128);
                 else if (OUT == FPCC_OUT_I16) ((int16_t *)optr)[q] = (int16_t)o[q];
                 else ((int32_t *)optr)[q] = o[q];
             }
@@ -585,6 +592,7 @@ struct LeanTile {
     const int32_t *rb_row;      // occupancy bias row (column n0) or NULL
     const int32_t *res_row;     // residual row (column n0) or NULL
     bool has_post;
+    int8_t *aux_row;            // dual output: int8 row (column n0) of fpcc_epilogue::aux_out, or NULL
     bool al32;                  // 256-bit stores allowed: conv kernel (96 registers) and a 32-byte aligned output base.  The
                                 // linear kernels sit at their 80-register cap: holding 16 bytes across a chunk costs them 5-20 %
 };
@@ -615,8 +623,14 @@ __device__ __forceinline__ void lean_redo_chunk(const LeanTile &lt, const LeanU 
                     r = (int32_t)((uint32_t)r + (uint32_t)__ldg(lt.res_row + c0 + q));
                     if (lt.has_post) r = sat_s32(prelu_q25((int64_t)r, u.post));
                 }
-                if (p2.on) ((int8_t *)lt.orow)[c0 + q] = (int8_t)post2_exact(r, p2);
-                else ((int32_t *)lt.orow)[c0 + q] = r;
+                if (p2.on && lt.aux_row) {  // dual output
+                    ((int32_t *)lt.orow)[c0 + q] = r;
+                    lt.aux_row[c0 + q] = (int8_t)post2_exact(r, p2);
+                } else if (p2.on) {
+                    ((int8_t *)lt.orow)[c0 + q] = (int8_t)post2_exact(r, p2);
+                } else {
+                    ((int32_t *)lt.orow)[c0 + q] = r;
+                }
             } else {
                 ((int8_t *)lt.orow)[c0 + q] = (int8_t)r;
             }
@@ -916,6 +930,30 @@ __device__ __forceinline__ void quad_tile(const LeanTile &lt, const QuadRows &qr
                 const int r0 = (i >> 1) * 8 + b * 4 + (i & 1) * 2;
                 if (qr.off[i] >= 0) *reinterpret_cast<int2 *>(out + qr.off[i] + c0 + 8 * b + j2) = make_int2(o[r0], o[r0 + 1]);
             }
+        if (ep.aux_out) {
+            // dual output (kernel-uniform): the consumer's [PReLU +] requant of the finished int32 values, stored as int8 rows
+            // beside them -- y*mul2 + c02 - [y < thr2] (no sign handling when the tie analysis allows), high word >> (shift2 - 32)
+            const int4 k2 = lds128(u.post2_addr);       // mul2, thr2, slope2, shift2 - 32
+            const int4 k3 = lds128(u.post2_addr + 16);  // c02 lo, c02 hi, nt2
+            const int64_t c02 = pack64((uint32_t)k3.x, (uint32_t)k3.y), c02m1 = c02 - 1;
+            const bool s2 = ep.post_slope2 != nullptr, nt2 = k3.z != 0;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                int32_t y = o[r];
+                if (s2) y = prelu_unit(y, k2.z, u.k24);
+                const int64_t t2 = mad_wide_c(y, k2.x, (nt2 || y >= k2.y) ? c02 : c02m1);
+                o[r] = (int32_t)((uint64_t)t2 >> 32) >> k2.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    const int r0 = (i >> 1) * 8 + b * 4 + (i & 1) * 2;
+                    uint32_t w;  // sat8(o[r0 + 1]) << 8 | sat8(o[r0])
+                    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(o[r0 + 1]), "r"(o[r0]), "r"(0));
+                    if (qr.off[i] >= 0) *reinterpret_cast<uint16_t *>(ep.aux_out + qr.off[i] + c0 + 8 * b + j2) = (uint16_t)w;
+                }
+        }
     }
     __syncwarp();
 }
@@ -1480,6 +1518,7 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
                 lt.orow = (char *)out + row0 * ((ep.out_type == FPCC_OUT_I8 || post2_on) ? 1 : 4);
                 lt.rb_row = ep.row_bias ? ep.row_bias + (row_ok ? (int64_t)__ldg(&ep.row_idx[m]) * a.N + n0 : 0) : nullptr;
                 lt.res_row = ep.residual ? ep.residual + row0 : nullptr;
+                lt.aux_row = (OUTK == OK_I32 && ep.aux_out) ? ep.aux_out + row0 : nullptr;
                 if (OUTK == OK_I8) {
                     if (has_slope) lean_tile_sgn<FPCC_OUT_I8, true, false, false, false>(lt, lu, zp, sgn_mode, ep);
                     else lean_tile_sgn<FPCC_OUT_I8, false, false, false, false>(lt, lu, zp, sgn_mode, ep);
@@ -1523,8 +1562,9 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
                 const bool vec = out_al && (a.N & 15) == 0;
                 const bool rb = ep.row_bias != nullptr;
                 Post2 p2;
-                p2.on = false;
-                if (post2_on) p2 = load_post2(ep);
+                p2.on = false; p2.dual = false;
+                if (post2_on || (OUTK == OK_I32 && ep.aux_out)) p2 = load_post2(ep);
+                cx.aux = p2.dual ? ep.aux_out + m * a.N + nb : nullptr;
                 if (OUTK == OK_I8) epi_dispatch<FPCC_OUT_I8>(acc, cx, optr, vec, has_slope, rb, p2);
                 else if (OUTK == OK_I32 || OUTK == OK_POST2) epi_dispatch<FPCC_OUT_I32>(acc, cx, optr, vec, has_slope, rb, p2);
                 else epi_dispatch<FPCC_OUT_I16>(acc, cx, optr, vec, has_slope, rb, p2);
@@ -1711,7 +1751,7 @@ static int launch_stages(const TcArgs &a, const CUtensorMap &tmap, const EpiPara
     size_t smem = PSmem<STAGES>::bytes(a.n_tile, rows_k);
     FPCC_REQUIRE(smem <= TC_SMEM_MAX, "igemm_tc: %zu bytes of shared memory exceed the 227 KB limit", smem);
     if (KIND != 0) return launch_outk<MODE, STAGES, KIND, OK_I8>(a, tmap, ep, fe, out, tiles_m, n_blocks_n, grid, smem, cl2, s);
-    if (ep.post_mul) return launch_outk<MODE, STAGES, KIND, OK_POST2>(a, tmap, ep, fe, out, tiles_m, n_blocks_n, grid, smem, cl2, s);
+    if (ep.post_mul && !ep.aux_out) return launch_outk<MODE, STAGES, KIND, OK_POST2>(a, tmap, ep, fe, out, tiles_m, n_blocks_n, grid, smem, cl2, s);
     if (ep.out_type == FPCC_OUT_I8) return launch_outk<MODE, STAGES, KIND, OK_I8>(a, tmap, ep, fe, out, tiles_m, n_blocks_n, grid, smem, cl2, s);
     if (ep.out_type == FPCC_OUT_I32) return launch_outk<MODE, STAGES, KIND, OK_I32>(a, tmap, ep, fe, out, tiles_m, n_blocks_n, grid, smem, cl2, s);
     return launch_outk<MODE, STAGES, KIND, OK_I16>(a, tmap, ep, fe, out, tiles_m, n_blocks_n, grid, smem, cl2, s);

@@ -189,7 +189,7 @@ class _AffineIn8(LoadSaveUint32RequantMul):
         self.register_buffer('scale_out', torch.zeros((1,), dtype=torch.float32) - 1, persistent=True)
         self.register_buffer('zero_point_out', torch.zeros((1,), dtype=torch.float32), persistent=True)
 
-    def epilogue(self, with_bias: bool, residual=None, post_slope=None, row_bias=None, post_requant=None):
+    def epilogue(self, with_bias: bool, residual=None, post_slope=None, row_bias=None, post_requant=None, aux_out=None):
         shift = _shift_of(self)
         if self.out_scaled_int:
             out_type = ops.OUT_I8
@@ -198,7 +198,7 @@ class _AffineIn8(LoadSaveUint32RequantMul):
         return ops.make_epilogue(self.requant_mul, self.int_zero_point_out, shift, out_type,
                                  bias=self.bias if with_bias else None,
                                  slope=self.slope if self.with_prelu else None,
-                                 residual=residual, post_slope=post_slope, row_bias=row_bias, post_requant=post_requant)
+                                 residual=residual, post_slope=post_slope, row_bias=row_bias, post_requant=post_requant, aux_out=aux_out)
 
     def _import_scales(self, scale_in, scale_out):
         assert scale_in.dtype == torch.float32 and scale_in.numel() == 1
@@ -288,7 +288,9 @@ class SparseConvIn8Out8(_AffineIn8):
             return self.forward_with_sparse_tensor(*args, **kwargs)
         return self.forward_with_coords(*args, **kwargs)
 
-    def forward_with_sparse_tensor(self, input: SparseTensor, residual=None, post_slope=None, post_requant=None) -> SparseTensor:
+    def forward_with_sparse_tensor(self, input: SparseTensor, residual=None, post_slope=None, post_requant=None, aux_out=None) -> SparseTensor:
+        """`aux_out` (int8 [n_out, out_ch], with `post_requant`): dual output -- the int32 rows are returned as usual and the
+        second stage's int8 rows are written to aux_out as well (ops.make_epilogue)."""
         caches = input._caches
         tag = (input.stride, self.kernel_size, self.stride)
         cur_kmap: Dict[str, Any] = caches.kmaps.get(tag)
@@ -309,7 +311,7 @@ class SparseConvIn8Out8(_AffineIn8):
                 raise NotImplementedError((input.stride, self.stride))
         out_feats, hashmap_kv, in_out_maps = self.forward_with_coords(
             input.F, input.C, output_coords, in_out_maps, hashmap_kv, same, residual=residual, post_slope=post_slope,
-            post_requant=post_requant)
+            post_requant=post_requant, aux_out=aux_out)
         caches.kmaps.setdefault(tag, {}).setdefault('in_out_maps', in_out_maps)
         if hashmap_kv is not None:
             caches.hashmaps.setdefault(input.stride, hashmap_kv)
@@ -320,9 +322,10 @@ class SparseConvIn8Out8(_AffineIn8):
         return ret
 
     def forward_with_coords(self, in_feats, in_coords, out_coords, in_out_maps=None, hashmap_kv=None,
-                            if_in_coords_equals_out_coords: bool = False, residual=None, post_slope=None, post_requant=None):
+                            if_in_coords_equals_out_coords: bool = False, residual=None, post_slope=None, post_requant=None,
+                            aux_out=None):
         """-> (out N2 x C2 int8 | Q8.23 int32, hashmap_kv, in_out_maps); conv + epilogue in one kernel."""
-        ep = self.epilogue(True, residual, post_slope, post_requant=post_requant)
+        ep = self.epilogue(True, residual, post_slope, post_requant=post_requant, aux_out=aux_out)
         if self.in_ch < 32 and not self.use_zero_point_in:
             # thin input (first conv C_in = 1, occupancy embeds C_in = 8): im2col + one tensor-core linear
             kv = self.kernel_volume
@@ -496,11 +499,21 @@ class LinearIn8W8(_AffineIn8):
             assert zero_point_out is None
             _fill_requant(self, scale_in * scale_weight, None)
 
-    def forward(self, input: torch.Tensor, sel=None, n_out_rows=None, post_requant=None) -> torch.Tensor:
+    def can_emit_aux(self) -> bool:
+        """int32 output on the tensor-core kernel: its epilogue can also emit a consumer's int8 rows (dual output)"""
+        return (not self.out_scaled_int and not getattr(self, 'padded_output', False) and self.out_ch % 16 == 0
+                and ops.gemm_engine(self.in_ch if self.in_ch % 16 == 0 else self.in_ch - 8, self.out_ch) == 'tc')
+
+    def forward(self, input: torch.Tensor, sel=None, n_out_rows=None, post_requant=None, aux_requant=None) -> torch.Tensor:
         """GEMM + bias + [PReLU] + requant in one kernel.  `sel` (from ops.slot_pairs) evaluates only the
         occupied (row, child) blocks of a C -> 8C linear: identical values, 4-8x less work.  `post_requant`
         (RequantFxpToScaledInt8.as_post_stage of the ONLY consumer of this layer's int32 output) makes the kernel
         emit that consumer's int8 directly: the Q8.23 tensor is never written."""
+        if aux_requant is not None:
+            # dual output: the Q8.23 rows AND `aux_requant` (a RequantFxpToScaledInt8.as_post_stage of one consumer) of them
+            assert self.can_emit_aux() and post_requant is None and sel is None
+            aux = torch.empty((input.shape[0], self.out_ch), dtype=torch.int8, device=input.device)
+            return ops.linear(input, self.weight, self.epilogue(True, post_requant=aux_requant, aux_out=aux)), aux
         if post_requant is not None:
             assert not self.out_scaled_int and not getattr(self, 'padded_output', False)
             return ops.linear(input, self.weight, self.epilogue(True, post_requant=post_requant), sel=sel, n_out_rows=n_out_rows)
@@ -534,7 +547,7 @@ class LinearIn8W8(_AffineIn8):
         cache = _cached(self, '_pad_cache', key, make)
         return cache[1], cache[2]
 
-    def forward_with_bits(self, input: torch.Tensor, occ: torch.Tensor, q0: int, q1: int) -> torch.Tensor:
+    def forward_with_bits(self, input: torch.Tensor, occ: torch.Tensor, q0: int, q1: int, aux_requant=None) -> torch.Tensor:
         """Linear over cat(input, bits) where `bits` are the 8 occupancy channels of `occ` (channel k = bit 7-k)
         already requantised to the two int8 values q0 (bit clear) / q1 (bit set).  Their contribution
         sum_k q[bit_k] * W[:, C+k] depends only on the occupancy byte, so it is a 256-row bias table and the
@@ -549,6 +562,9 @@ class LinearIn8W8(_AffineIn8):
             return w[:, :C].contiguous(), table, int(table.abs().max().item())
 
         _, w_main, table, bound = _cached(self, '_bits_cache', key, make)
+        if aux_requant is not None:  # dual output, see forward()
+            aux = torch.empty((input.shape[0], self.out_ch), dtype=torch.int8, device=input.device)
+            return ops.linear(input, w_main, self.epilogue(True, row_bias=(table, occ, bound), post_requant=aux_requant, aux_out=aux)), aux
         return ops.linear(input, w_main, self.epilogue(True, row_bias=(table, occ, bound)))
 
 
@@ -611,18 +627,27 @@ class SparseResBlockIn32W8Out32(nn.Module):
         """conv2 runs on the tensor-core kernel (the only one with the fused second stage)"""
         return not self.conv2.use_zero_point_in and ops.gemm_engine(self.ch, self.ch, 27) == 'tc'
 
-    def forward(self, input: SparseTensor, post_requant=None) -> SparseTensor:
+    def forward(self, input: SparseTensor, post_requant=None, input_q: Optional[torch.Tensor] = None, aux_requant=None):
         """cuda_ops.py:82-92.  The residual add (int32 wrap) and the final PReLU ride in conv2's epilogue.
         `post_requant` (RequantFxpToScaledInt8.as_post_stage of the block's ONLY consumer): the block then returns
         that consumer's int8 rows and its Q8.23 output is never written (check can_fuse_consumer first)."""
-        x = SparseTensor(self.input_requant(input.F), input.C, input.stride, input.spatial_range)
+        # `input_q`: input_requant(input.F) already emitted by the producer of input.F (its dual output);
+        # `aux_requant`: ONE further consumer's requant of the block output, emitted by conv2 beside the Q8.23 rows
+        # (returns (block output, int8 rows) then)
+        x = SparseTensor(self.input_requant(input.F) if input_q is None else input_q, input.C, input.stride, input.spatial_range)
         x._caches = input._caches
         x = self.conv_prelu(x)
-        x = self.conv2.forward_with_sparse_tensor(x, residual=input.F, post_slope=self.prelu.slope, post_requant=post_requant)
+        aux = None
+        if aux_requant is not None:
+            assert post_requant is None and self.can_fuse_consumer()
+            aux = torch.empty((input.F.shape[0], self.ch), dtype=torch.int8, device=input.F.device)
+            x = self.conv2.forward_with_sparse_tensor(x, residual=input.F, post_slope=self.prelu.slope, post_requant=aux_requant, aux_out=aux)
+        else:
+            x = self.conv2.forward_with_sparse_tensor(x, residual=input.F, post_slope=self.prelu.slope, post_requant=post_requant)
         assert input.F.dtype == torch.int32 and x.F.dtype == (torch.int8 if post_requant is not None else torch.int32)
         out = SparseTensor(x.F, input.C, input.stride, input.spatial_range)
         out._caches = input._caches
-        return out
+        return out if aux_requant is None else (out, aux)
 
 
 def softmax_int32(input: torch.Tensor) -> torch.Tensor:

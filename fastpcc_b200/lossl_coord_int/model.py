@@ -116,12 +116,12 @@ class Level:
 
 
 def linear_with_bits(requant: RequantFxpToScaledInt8, linear: LinearIn8W8, f: torch.Tensor, occ: torch.Tensor,
-                     prelu: Optional[PReLUIn32Out32] = None) -> torch.Tensor:
+                     prelu: Optional[PReLUIn32Out32] = None, aux_requant=None) -> torch.Tensor:
     """`linear(requant([prelu](cat(f, bits << 23))))` (model.py:63-64, 147, 172) without the concat: the bit
     channels requantise to two constants, so their share of the contraction is a bias row chosen by the
     occupancy byte (LinearIn8W8.forward_with_bits) and the GEMM keeps K = C."""
     q0, q1 = requant.bit_levels()
-    return linear.forward_with_bits(requant(f, prelu=prelu), occ, q0, q1)
+    return linear.forward_with_bits(requant(f, prelu=prelu), occ, q0, q1, aux_requant=aux_requant)
 
 
 def _with(f, ref: SparseTensor, C=None, stride=None):
@@ -131,6 +131,11 @@ def _with(f, ref: SparseTensor, C=None, stride=None):
 
 
 _K3 = ((3, 3, 3), (1, 1, 1))
+import os as _os
+# Dual-output fusion (fpcc_epilogue::aux_out): identical bytes either way.  Measured on B200 (96 frames): stand-alone requants
+# 35.0 -> 22.8 ms per step, but the producing conv / linear epilogues +7.1 / +4.7 ms: the step does not move (433 vs 435 ms,
+# profiles/r02_dual_outputs.txt) and peak memory grows, so it is OFF by default; FPCC_DUAL_OUTPUTS=1 turns it on.
+DUAL_OUTPUTS = _os.environ.get('FPCC_DUAL_OUTPUTS', '0') == '1'
 
 
 def seed_kernel_map(src_caches, dst_caches, coarse_stride, coarse_occ: torch.Tensor, fine: Level):
@@ -234,9 +239,28 @@ class OneScaleMultiStepPredictor(nn.Module):
         occupancy is what this block predicts.  Shared by compress and decompress."""
         S = self.pred_steps
         emb_lv = levels[S - 2]  # the level whose occupancy bits are embedded (cur_bins[1] / cur_bins[-1])
+        # Dual outputs (fpcc_epilogue::aux_out): an int32 tensor with a Requant among its consumers leaves its producer in
+        # both forms -- dec[1]'s Q8.23 rows + the int8 rows of the ResBlock's input_requant; the ResBlock's output + the
+        # int8 rows of the Requant that opens pred[0] -- and those stand-alone requant passes disappear.
+        res = self.dec[2] if isinstance(self.dec, SparseSequential) and len(self.dec) == 3 and isinstance(self.dec[2], SparseResBlockIn32W8Out32) else None
+        dual_in = res is not None and DUAL_OUTPUTS and isinstance(self.dec[1], LinearIn8W8) and self.dec[1].can_emit_aux()
+        dual_out = (res is not None and DUAL_OUTPUTS and res.can_fuse_consumer() and isinstance(self.pred[0][0], RequantFxpToScaledInt8)
+                    and res.ch % 16 == 0)
+        aux_in = res.input_requant.as_post_stage(None) if dual_in else None
+        aux_out = self.pred[0][0].as_post_stage(None) if dual_out else None
+        cur_q = None  # pred[0][0](cur.F), emitted by the ResBlock
+
+        def res_block(f, f8):
+            nonlocal cur_q
+            y = res(_with(f, cur), input_q=f8, aux_requant=aux_out)
+            if aux_out is not None:
+                y, cur_q = y
+            return y
+
         if len(self.embed) == 0:  # pred_steps == 2: the embedding is the occupancy itself
-            f = linear_with_bits(self.dec[0], self.dec[1], cur.F, emb_lv.occ)
-            cur = self.dec[2](_with(f, cur))
+            f = linear_with_bits(self.dec[0], self.dec[1], cur.F, emb_lv.occ, aux_requant=aux_in)
+            f, f8 = f if aux_in is not None else (f, None)
+            cur = res_block(f, f8)
         else:
             stride = tuple(s >> (S - 2) for s in cur.stride)
             embed_f = self.embed(_with(emb_lv.bits_fxp(), cur, C=emb_lv.C, stride=stride)).F
@@ -251,7 +275,9 @@ class OneScaleMultiStepPredictor(nn.Module):
                     dec[0](embed_f, out=q[:, c1:])
                 else:
                     q = torch.cat([dec[0](cur.F), dec[0](embed_f)], 1)
-                cur = dec[2](_with(dec[1](q), cur))
+                f = dec[1](q, aux_requant=aux_in)
+                f, f8 = f if aux_in is not None else (f, None)
+                cur = res_block(f, f8)
             else:
                 cur.F = torch.cat([cur.F, embed_f], 1)
                 cur = dec(cur)
@@ -273,10 +299,11 @@ class OneScaleMultiStepPredictor(nn.Module):
         for j, block in enumerate(self.pred):
             post = consumer_stage(j)
             if j == 0:
+                src, skip = (cur, 0) if cur_q is None else (_with(cur_q, cur), 1)
                 if S > 1:
-                    x = block(cur, sel=levels[1].sel(), n_out_rows=levels[1].n, post_requant=post)
+                    x = block(src, sel=levels[1].sel(), n_out_rows=levels[1].n, post_requant=post, skip=skip)
                 else:
-                    x = block(cur)
+                    x = block(src, skip=skip)
                 fused = post
                 continue
             lv = levels[j]

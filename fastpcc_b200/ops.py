@@ -113,15 +113,16 @@ def workspace(nbytes, device):
 
 
 def _ep_out_dtype(ep):
-    """dtype of the rows a fused kernel writes: int8 when the second stage is on"""
-    return torch.int8 if ep.post_requant_mul else _OUT_DTYPE[ep.out_type]
+    """dtype of the rows a fused kernel writes to `out`: int8 when the second stage replaces the int32 rows (no aux_out)"""
+    return torch.int8 if (ep.post_requant_mul and not ep.aux_out) else _OUT_DTYPE[ep.out_type]
 
 
 def make_epilogue(requant_mul, zero_point, shift, out_type, bias=None, slope=None, residual=None, post_slope=None,
-                  row_bias=None, post_requant=None):
+                  row_bias=None, post_requant=None, aux_out=None):
     """post_requant = (mul uint32[1], zero_point int64[1], shift, slope int32[1] | None): the fused second stage of the
     tensor-core kernels -- an int32 (Q8.23) result is not stored, the consumer's [PReLUIn32Out32 +] RequantFxpToScaledInt8
-    runs in the same epilogue and int8 rows come out (fpcc_epilogue::post_requant_mul)."""
+    runs in the same epilogue and int8 rows come out (fpcc_epilogue::post_requant_mul).  With `aux_out` (int8 [rows, ch])
+    the int32 rows are ALSO stored (dual output for int32 tensors with a second consumer)."""
     _need(requant_mul, torch.uint32, 'requant_mul')
     _need(zero_point, torch.int64, 'zero_point')
     if shift < 0:
@@ -149,7 +150,12 @@ def make_epilogue(requant_mul, zero_point, shift, out_type, bias=None, slope=Non
         e.post_zero_point = _p(_need(zp2, torch.int64, 'post zero_point'))
         e.post_shift = int(shift2)
         e.post_requant_slope = _p(_need(slope2, torch.int32, 'post slope')) if slope2 is not None else None
-    e._keep = (bias, slope, requant_mul, zero_point, residual, post_slope, row_bias, post_requant)
+    if aux_out is not None:
+        # dual output: the int32 rows go to `out` as usual, the second stage's int8 rows to aux_out [rows, ch]
+        if post_requant is None:
+            raise RuntimeError('aux_out needs post_requant (the second stage whose int8 rows it receives)')
+        e.aux_out = _p(_need(aux_out, torch.int8, 'aux_out', 2))
+    e._keep = (bias, slope, requant_mul, zero_point, residual, post_slope, row_bias, post_requant, aux_out)
     return e
 
 

@@ -227,6 +227,12 @@ typedef struct {
     const int64_t *post_zero_point;     /* device [1]         */
     int32_t post_shift;                 /* 0 .. 62            */
     const int32_t *post_requant_slope;  /* device [1] Q6.25 or NULL */
+    /* Dual output: with post_requant_mul AND aux_out set the int32 (Q8.23) rows are stored to `out` as usual and the second
+     * stage's int8 rows go to aux_out ([rows, ch] int8) as well -- an int32 tensor with two consumers (the residual input of
+     * SparseResBlockIn32W8Out32 and its input_requant, cuda_ops.py:82-92; a block output and the Requant that opens the next
+     * predictor step, lossl_coord_int/model.py:147-172) leaves its producer once in each form and the stand-alone requant
+     * pass over it disappears. */
+    int8_t *aux_out;                    /* device [rows, ch] or NULL */
 } fpcc_epilogue;
 
 /* replaces the 12 requant entry points of binding.cu:118-129 */

@@ -472,6 +472,71 @@ def test_fused_second_stage_equals_prelu_then_requant(ops, k, n):
         assert got.dtype == torch.int8 and (got.cpu().numpy() == want).all()
 
 
+@pytest.mark.parametrize('k,n', [(64, 64), (256, 256)])
+def test_dual_output_int32_and_fused_int8(ops, k, n):
+    """fpcc_epilogue::aux_out: the int32 (Q8.23) rows AND the int8 rows of one consumer's [PReLU +] requant leave the same
+    kernel.  Both must equal the stand-alone steps of the reference (bias_requant_to_int32 [+ residual + prelu], then
+    prelu + requant_to_int8), for the linear (plain, PReLU, occupancy row bias), for the ResBlock conv2 form (residual +
+    post PReLU, rows grouped), with first stages that saturate int32 (exact redo) and parameters outside the lean path."""
+    rng = np.random.default_rng(k * 77 + n)
+    m = 900
+    a = rng.integers(-128, 128, (m, k)).astype(np.int8)
+    w = rng.integers(-127, 128, (n, k)).astype(np.int8)
+    acc = K.gemm_int8(a, w, None)
+    zp1 = np.zeros(1, np.int64)
+    for shift1, mul_hi, bias_hi, slope1 in ((9, 1 << 20, 1 << 16, None), (12, 1 << 22, 1 << 20, int(0.25 * (1 << 25))), (3, 1 << 27, 1 << 28, None),
+                                            (5, (1 << 32) - 1, 1000, None)):
+        mul1 = rng.integers(mul_hi >> 2, mul_hi, n, endpoint=True).astype(np.uint32)
+        bias = rng.integers(-bias_hi, bias_hi, n, endpoint=True).astype(np.int32)
+        sl1 = None if slope1 is None else np.array([slope1], np.int32)
+        y = K.requant(acc, mul1, zp1, shift1, np.int32, bias=bias, slope=sl1)
+        for shift2, mul2v, zp2v, slope2v in ((48, (1 << 30) + 12345, 0, None), (44, (1 << 30) - 3, (5 << 44) + 99, int(0.1 * (1 << 25))),
+                                            (40, 12345, -(3 << 39), None), (62, (1 << 30) + 1, -(1 << 59), 0)):
+            mul2, zp2 = np.array([mul2v], np.uint32), np.array([zp2v], np.int64)
+            sl2 = None if slope2v is None else np.array([slope2v], np.int32)
+            want8 = K.requant(y if sl2 is None else K.prelu(y, sl2), np.full(n, mul2v, np.uint32), zp2, shift2, np.int8)
+            aux = torch.full((m, n), 77, dtype=torch.int8, device='cuda')
+            ep = ops.make_epilogue(dev(mul1), dev(zp1), shift1, ops.OUT_I32, bias=dev(bias), slope=None if sl1 is None else dev(sl1),
+                                   post_requant=(dev(mul2), dev(zp2), shift2, None if sl2 is None else dev(sl2)), aux_out=aux)
+            got = ops.linear(dev(a), dev(w), ep)
+            assert got.dtype == torch.int32 and (got.cpu().numpy() == y).all(), ('i32', shift1, shift2)
+            assert (aux.cpu().numpy() == want8).all(), ('i8', shift1, shift2, mul2v, zp2v, slope2v)
+    # occupancy row bias + dual output (LinearIn8W8.forward_with_bits as dec[1])
+    table = rng.integers(-(1 << 20), 1 << 20, (256, n)).astype(np.int32)
+    idx = rng.integers(0, 256, m).astype(np.uint8)
+    mul1 = rng.integers(1 << 16, 1 << 19, n).astype(np.uint32)
+    bias = rng.integers(-100000, 100000, n).astype(np.int32)
+    sl1 = np.array([int(0.3 * (1 << 25))], np.int32)
+    accb = (acc.astype(np.int64) + table[idx].astype(np.int64)).astype(np.int32)
+    y = K.requant(accb, mul1, zp1, 8, np.int32, bias=bias, slope=sl1)
+    mul2, zp2 = np.array([(1 << 30) + 5], np.uint32), np.array([3 << 44], np.int64)
+    want8 = K.requant(y, np.full(n, mul2[0], np.uint32), zp2, 47, np.int8)
+    aux = torch.empty((m, n), dtype=torch.int8, device='cuda')
+    ep = ops.make_epilogue(dev(mul1), dev(zp1), 8, ops.OUT_I32, bias=dev(bias), slope=dev(sl1), row_bias=(dev(table), dev(idx), 1 << 20),
+                           post_requant=(dev(mul2), dev(zp2), 47, None), aux_out=aux)
+    got = ops.linear(dev(a), dev(w), ep)
+    assert (got.cpu().numpy() == y).all() and (aux.cpu().numpy() == want8).all()
+    # ResBlock conv2 form: conv + residual + post PReLU -> int32 block output, plus the next Requant's int8 rows
+    if k % 16 == 0 and ops.gemm_engine(k, n, 27) == 'tc':
+        C = _cloud(9, n=2000, bits=6)
+        nn_ = C.shape[0]
+        f = rng.integers(-128, 128, (nn_, k)).astype(np.int8)
+        w3 = rng.integers(-127, 128, (27, n, k)).astype(np.int8)
+        res = rng.integers(-(1 << 28), 1 << 28, (nn_, n)).astype(np.int32)
+        post = np.array([int(0.2 * (1 << 25))], np.int32)
+        acc3, _ = K.sparse_conv_in8w8out32(f, w3, C, C, (3, 3, 3), (1, 1, 1), None, None, True)
+        y = K.prelu((K.requant(acc3, mul1, zp1, 12, np.int32, bias=bias).astype(np.int64) + res.astype(np.int64)).astype(np.int32), post)
+        want8 = K.requant(y, np.full(n, mul2[0], np.uint32), zp2, 47, np.int8)
+        keys, vals = ops.hash_build(dev(C))
+        tb = ops.kmap_lookup(keys, vals, dev(C), (3, 3, 3), (1, 1, 1))
+        tp, perm = ops.group_rows(tb)
+        aux = torch.empty((nn_, n), dtype=torch.int8, device='cuda')
+        ep = ops.make_epilogue(dev(mul1), dev(zp1), 12, ops.OUT_I32, bias=dev(bias), residual=dev(res), post_slope=dev(post),
+                               post_requant=(dev(mul2), dev(zp2), 47, None), aux_out=aux)
+        got = ops.spconv(dev(f), dev(w3), tp, ep, row_perm=perm)
+        assert (got.cpu().numpy() == y).all() and (aux.cpu().numpy() == want8).all()
+
+
 def test_selected_linear_equals_masked_dense(ops):
     """Linear(C->8C) + child mask (model.py:64-66) == occupied-children-only evaluation."""
     rng = np.random.default_rng(4)
