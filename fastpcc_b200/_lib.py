@@ -16,7 +16,7 @@ class Epilogue(C.Structure):
     _fields_ = [('bias', _vp), ('slope', _vp), ('requant_mul', _vp), ('zero_point', _vp),
                 ('shift', C.c_int32), ('out_type', C.c_int32), ('mul_is_scalar', C.c_int32),
                 ('residual', _vp), ('post_slope', _vp), ('row_bias', _vp), ('row_idx', _vp), ('row_bias_bound', C.c_int32),
-                ('post_requant_mul', _vp), ('post_zero_point', _vp), ('post_shift', C.c_int32), ('post_requant_slope', _vp), ('aux_out', _vp)]
+                ('post_requant_mul', _vp), ('post_zero_point', _vp), ('post_shift', C.c_int32), ('post_requant_slope', _vp), ('aux_out', _vp), ('out_ld', C.c_int64)]
 
 
 _EP = C.POINTER(Epilogue)
@@ -38,6 +38,7 @@ SIGNATURES = {
     'fpcc_upsample': (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'fpcc_occ_to_bits': (_i, [_vp, _i, _vp, _vp]),
     'fpcc_gather_patches': (_i, [_vp, _i, _vp, _i64, _i, _i, _vp, _i, _vp]),
+    'fpcc_occ_bits_q8': (_i, [_vp, _i64, _i, _i, _vp, _i64, _vp]),
     'fpcc_slot_table': (_i, [_vp, _vp, _i, _vp, _i64, _vp]),
     'fpcc_morton_encode': (_i, [_vp, _i64, _i, _i, _vp, _vp]),
     'fpcc_gather_rows16': (_i, [_vp, _vp, _i64, _vp, _vp]),

@@ -48,6 +48,10 @@ int check_epilogue(const fpcc_epilogue *e, bool allow_residual) {
         FPCC_REQUIRE(e->post_requant_slope == nullptr, "epilogue: post_requant_slope without post_requant_mul");
         FPCC_REQUIRE(e->aux_out == nullptr, "epilogue: aux_out without post_requant_mul");
     }
+    if (e->out_ld != 0) {
+        FPCC_REQUIRE(allow_residual && e->out_ld > 0 && e->out_ld % 16 == 0, "epilogue: out_ld must be a positive multiple of 16 (fused kernels only)");
+        FPCC_REQUIRE(e->out_type == FPCC_OUT_I8 || (e->post_requant_mul && !e->aux_out), "epilogue: out_ld applies to int8 output rows");
+    }
     return FPCC_OK;
 }
 

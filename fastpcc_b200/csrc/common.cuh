@@ -88,6 +88,7 @@ struct EpiParams {  // device-side copy of fpcc_epilogue with scalars resolved t
     const int64_t *post_zp;
     int32_t post_shift;
     const int32_t *post_slope2;
+    int64_t out_ld;               // int8 outputs of the fused kernels: row pitch in elements (0 = dense rows of ch)
     int8_t *aux_out;              // dual output: int8 rows of the second stage beside the int32 rows (NULL = off)
 };
 static inline EpiParams to_params(const fpcc_epilogue *e) {
@@ -96,7 +97,7 @@ static inline EpiParams to_params(const fpcc_epilogue *e) {
     p.shift = e->shift; p.out_type = e->out_type; p.mul_is_scalar = e->mul_is_scalar;
     p.residual = e->residual; p.post_slope = e->post_slope;
     p.row_bias = e->row_bias; p.row_idx = e->row_idx; p.row_bias_bound = e->row_bias_bound;
-    p.post_mul = e->post_requant_mul; p.post_zp = e->post_zero_point; p.post_shift = e->post_shift; p.post_slope2 = e->post_requant_slope; p.aux_out = e->aux_out;
+    p.post_mul = e->post_requant_mul; p.post_zp = e->post_zero_point; p.post_shift = e->post_shift; p.post_slope2 = e->post_requant_slope; p.aux_out = e->aux_out; p.out_ld = e->out_ld;
     return p;
 }
 int check_epilogue(const fpcc_epilogue *e, bool allow_residual);

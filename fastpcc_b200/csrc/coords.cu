@@ -524,6 +524,34 @@ __global__ void __launch_bounds__(256) gather_rows16_kernel(const int4 *__restri
 }
 }  // namespace fpcc
 
+namespace fpcc {
+__global__ void __launch_bounds__(256) occ_bits_q8_kernel(const uint8_t *__restrict__ occ, int64_t n, uint32_t q0, uint32_t q1,
+                                                          uint8_t *__restrict__ out, int64_t out_ld) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t o = occ[i];
+        uint32_t w0 = 0, w1 = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // channel k = bit 7 - k (model.py:63: cur_bin, most significant child first)
+            w0 |= (((o >> (7 - k)) & 1u) ? q1 : q0) << (8 * k);
+            w1 |= (((o >> (3 - k)) & 1u) ? q1 : q0) << (8 * k);
+        }
+        *reinterpret_cast<uint4 *>(out + i * out_ld) = make_uint4(w0, w1, 0u, 0u);
+    }
+}
+}  // namespace fpcc
+
+extern "C" int fpcc_occ_bits_q8(const uint8_t *occ, int64_t n, int q0, int q1, int8_t *out, int64_t out_ld, void *stream) {
+    FPCC_REQUIRE(occ && out && n >= 0, "occ_bits_q8: bad arguments");
+    FPCC_REQUIRE(out_ld >= 16 && out_ld % 16 == 0 && ((uintptr_t)out & 15) == 0, "occ_bits_q8: 16-byte aligned rows expected");
+    FPCC_REQUIRE(q0 >= -128 && q0 <= 127 && q1 >= -128 && q1 <= 127, "occ_bits_q8: int8 levels expected");
+    if (n == 0) return FPCC_OK;
+    const int64_t blocks = (n + 255) / 256, cap = (int64_t)fpcc::sm_count() * 16;
+    fpcc::occ_bits_q8_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(occ, n, (uint32_t)(q0 & 0xff), (uint32_t)(q1 & 0xff),
+                                                                                                   (uint8_t *)out, out_ld);
+    FPCC_LAUNCH_CHECK();
+    return FPCC_OK;
+}
+
 extern "C" int fpcc_gather_rows16(const void *src, const int64_t *idx, int64_t n, void *dst, void *stream) {
     FPCC_REQUIRE(src && idx && dst && n >= 0, "gather_rows16: bad arguments");
     FPCC_REQUIRE((((uintptr_t)src | (uintptr_t)dst) & 15) == 0, "gather_rows16: rows must be 16-byte aligned");

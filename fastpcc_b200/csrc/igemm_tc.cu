@@ -1394,7 +1394,7 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
         const int shift = ep.shift;
         const int cols_grp = (((a.n_tile + P_EPI_WARPS / 4 - 1) / (P_EPI_WARPS / 4) + EC - 1) / EC) * EC;  // columns per group, multiple of EC
         const int c_begin = min(a.n_tile, group * cols_grp), c_end = min(a.n_tile, c_begin + cols_grp);
-        const bool out_al = ((uintptr_t)out & 15) == 0;
+        const bool out_al = ((uintptr_t)out & 15) == 0 && (ep.out_ld & 15) == 0;
         LeanU lu;
         {
             const int64_t c0v = zp + (shift > 0 ? (int64_t)1 << (shift - 1) : 0);
@@ -1513,9 +1513,11 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
             if (KIND == 0 && lean) {
                 LeanTile lt;
                 lt.tacc = tacc; lt.chan_addr = smem_u32(chan4_s); lt.c_begin = c_begin; lt.c_end = c_end; lt.ncols = a.N - n0; lt.n0 = n0; lt.ncols_total = a.N;
-                lt.have_acc = have_acc; lt.row_ok = row_ok; lt.has_post = has_post; lt.al32 = MODE == 0 && ((uintptr_t)out & 31) == 0;
+                lt.have_acc = have_acc; lt.row_ok = row_ok; lt.has_post = has_post; lt.al32 = MODE == 0 && ((uintptr_t)out & 31) == 0 && (ep.out_ld & 31) == 0;
                 const int64_t row0 = row_ok ? m * a.N + n0 : 0;
-                lt.orow = (char *)out + row0 * ((ep.out_type == FPCC_OUT_I8 || post2_on) ? 1 : 4);
+                // int8 rows may go to a column slice of a wider buffer (fpcc_epilogue::out_ld: row pitch in elements)
+                const int64_t ld8 = ep.out_ld > 0 ? ep.out_ld : a.N;
+                lt.orow = (ep.out_type == FPCC_OUT_I8 || post2_on) ? (char *)out + (row_ok ? m * ld8 + n0 : 0) : (char *)out + row0 * 4;
                 lt.rb_row = ep.row_bias ? ep.row_bias + (row_ok ? (int64_t)__ldg(&ep.row_idx[m]) * a.N + n0 : 0) : nullptr;
                 lt.res_row = ep.residual ? ep.residual + row0 : nullptr;
                 lt.aux_row = (OUTK == OK_I32 && ep.aux_out) ? ep.aux_out + row0 : nullptr;
@@ -1558,7 +1560,8 @@ __global__ void __launch_bounds__((EW + prod_warps<MODE>() + 2) * 32, 1) igemm_t
                 cx.residual = ep.residual ? ep.residual + m * a.N + nb : nullptr;
                 cx.has_post = has_post;
                 cx.nvalid = min(EC, a.N - nb);
-                void *optr = (char *)out + (m * a.N + nb) * ((ep.out_type == FPCC_OUT_I8 || post2_on) ? 1 : (ep.out_type == FPCC_OUT_I16 ? 2 : 4));
+                void *optr = (ep.out_type == FPCC_OUT_I8 || post2_on) ? (void *)((char *)out + m * (ep.out_ld > 0 ? (int64_t)ep.out_ld : (int64_t)a.N) + nb)
+                                                                      : (void *)((char *)out + (m * a.N + nb) * (ep.out_type == FPCC_OUT_I16 ? 2 : 4));
                 const bool vec = out_al && (a.N & 15) == 0;
                 const bool rb = ep.row_bias != nullptr;
                 Post2 p2;

@@ -259,6 +259,7 @@ extern "C" int fpcc_spconv_i8(const int8_t *in_feats, int n_in, int c_in, const 
     }
     FPCC_REQUIRE(!row_perm, "spconv_i8: a grouped (row_perm) table needs the tensor-core path (see fpcc_gemm_engine)");
     FPCC_REQUIRE(!e->post_requant_mul, "spconv_i8: the fused second stage needs the tensor-core path (see fpcc_gemm_engine)");
+    FPCC_REQUIRE(e->out_ld == 0, "spconv_i8: an output pitch needs the tensor-core path (see fpcc_gemm_engine)");
     return launch_conv_simt(in_feats, c_in, weight, kvol, c_out, nbr_table, ld, n_out, zp_comp, ep, out, (cudaStream_t)stream);
 }
 
@@ -285,5 +286,6 @@ extern "C" int fpcc_linear_i8(const int8_t *A, int m, int k, const int8_t *W, in
         if (rc != FPCC_ERR_UNSUPPORTED) return rc;
     }
     FPCC_REQUIRE(!e->post_requant_mul, "linear_i8: the fused second stage needs the tensor-core path (see fpcc_gemm_engine)");
+    FPCC_REQUIRE(e->out_ld == 0, "linear_i8: an output pitch needs the tensor-core path (see fpcc_gemm_engine)");
     return launch_pairs_simt(a, ep, out, max_tiles, (cudaStream_t)stream);
 }

@@ -504,7 +504,7 @@ class LinearIn8W8(_AffineIn8):
         return (not self.out_scaled_int and not getattr(self, 'padded_output', False) and self.out_ch % 16 == 0
                 and ops.gemm_engine(self.in_ch if self.in_ch % 16 == 0 else self.in_ch - 8, self.out_ch) == 'tc')
 
-    def forward(self, input: torch.Tensor, sel=None, n_out_rows=None, post_requant=None, aux_requant=None) -> torch.Tensor:
+    def forward(self, input: torch.Tensor, sel=None, n_out_rows=None, post_requant=None, aux_requant=None, out=None) -> torch.Tensor:
         """GEMM + bias + [PReLU] + requant in one kernel.  `sel` (from ops.slot_pairs) evaluates only the
         occupied (row, child) blocks of a C -> 8C linear: identical values, 4-8x less work.  `post_requant`
         (RequantFxpToScaledInt8.as_post_stage of the ONLY consumer of this layer's int32 output) makes the kernel
@@ -516,7 +516,8 @@ class LinearIn8W8(_AffineIn8):
             return ops.linear(input, self.weight, self.epilogue(True, post_requant=aux_requant, aux_out=aux)), aux
         if post_requant is not None:
             assert not self.out_scaled_int and not getattr(self, 'padded_output', False)
-            return ops.linear(input, self.weight, self.epilogue(True, post_requant=post_requant), sel=sel, n_out_rows=n_out_rows)
+            # `out`: an int8 column slice of a wider buffer the rows go to (the next Linear(cat(F, bits)), forward_cat_bits)
+            return ops.linear(input, self.weight, self.epilogue(True, post_requant=post_requant), sel=sel, n_out_rows=n_out_rows, out=out)
         if sel is None and getattr(self, 'padded_output', False) and self.out_ch % 16 != 0 and self.in_ch % 16 == 0 and self.in_ch >= 32:
             # opt-in (the consumer must accept a row pitch), e.g. the 255 logits feeding the CDF kernels: run the
             # kernel on 256 zero-padded channels so that its rows are 16-byte aligned
@@ -546,6 +547,27 @@ class LinearIn8W8(_AffineIn8):
 
         cache = _cached(self, '_pad_cache', key, make)
         return cache[1], cache[2]
+
+    def can_cat_bits(self) -> bool:
+        """Linear over cat(F, 8 occupancy bits) as ONE tensor-core GEMM with K = C + 16 (forward_cat_bits)"""
+        c = self.in_ch - 8
+        return c >= 32 and c % 16 == 0 and ops.gemm_engine(c + 16, self.out_ch) == 'tc'
+
+    def forward_cat_bits(self, buf: torch.Tensor) -> torch.Tensor:
+        """Linear over cat(input, bits) with the concatenation already in memory: `buf` is int8 [rows, C + 16] whose first C
+        columns hold the requantised features (written there by their producer: ops.requant(out=...) or a fused second stage
+        with an output pitch), columns C .. C+7 the requantised occupancy bits (ops.occ_bits_q8) and 8 zero columns.  The
+        occupancy row-bias form (forward_with_bits) keeps K = C but reads 1 KB of bias per output row in the epilogue -- as
+        much as an int32 residual; here the bit channels ride in a third, nearly empty K stage of the MMA instead."""
+        c = self.in_ch - 8
+        key = (self.weight._version, self.weight.data_ptr())
+
+        def make():
+            return (torch.nn.functional.pad(self.weight, (0, 8)).contiguous(),)   # [out_ch, C + 8 + 8]
+
+        _, w_cat = _cached(self, '_cat_cache', key, make)
+        assert buf.dtype == torch.int8 and buf.shape[1] == c + 16 and buf.is_contiguous()
+        return ops.linear(buf, w_cat, self.epilogue(True))
 
     def forward_with_bits(self, input: torch.Tensor, occ: torch.Tensor, q0: int, q1: int, aux_requant=None) -> torch.Tensor:
         """Linear over cat(input, bits) where `bits` are the 8 occupancy channels of `occ` (channel k = bit 7-k)

@@ -68,7 +68,7 @@ class _Trace:
 class SparseSequential(nn.Sequential):
     """model.py:524-534; `sel`/`n_out_rows` are forwarded to the LAST linear (occupied-children form)."""
 
-    def forward(self, input: SparseTensor, sel=None, n_out_rows=None, post_requant=None, skip=0) -> SparseTensor:
+    def forward(self, input: SparseTensor, sel=None, n_out_rows=None, post_requant=None, skip=0, out=None) -> SparseTensor:
         """`post_requant`: fused second stage of the LAST linear (see LinearIn8W8.forward); `skip`: leading modules
         whose work a producer's fused second stage has already done."""
         x = SparseTensor(input.F, input.C, input.stride, input.spatial_range)
@@ -79,7 +79,7 @@ class SparseSequential(nn.Sequential):
                 continue
             if isinstance(module, _DENSE):
                 if i == last and (sel is not None or post_requant is not None):
-                    x.F = module(x.F, sel=sel, n_out_rows=n_out_rows, post_requant=post_requant)
+                    x.F = module(x.F, sel=sel, n_out_rows=n_out_rows, post_requant=post_requant, out=out)
                 else:
                     x.F = module(x.F)
             else:
@@ -121,6 +121,13 @@ def linear_with_bits(requant: RequantFxpToScaledInt8, linear: LinearIn8W8, f: to
     channels requantise to two constants, so their share of the contraction is a bias row chosen by the
     occupancy byte (LinearIn8W8.forward_with_bits) and the GEMM keeps K = C."""
     q0, q1 = requant.bit_levels()
+    if CAT_BITS and aux_requant is None and linear.can_cat_bits():
+        # the concatenation in memory, without a copy: the requant writes the first C columns of the [rows, C + 16] buffer
+        c = linear.in_ch - 8
+        buf = torch.empty((f.shape[0], c + 16), dtype=torch.int8, device=f.device)
+        requant(f, prelu=prelu, out=buf[:, :c])
+        ops.occ_bits_q8(occ, q0, q1, buf[:, c:])
+        return linear.forward_cat_bits(buf)
     return linear.forward_with_bits(requant(f, prelu=prelu), occ, q0, q1, aux_requant=aux_requant)
 
 
@@ -136,6 +143,9 @@ import os as _os
 # 35.0 -> 22.8 ms per step, but the producing conv / linear epilogues +7.1 / +4.7 ms: the step does not move (433 vs 435 ms,
 # profiles/r02_dual_outputs.txt) and peak memory grows, so it is OFF by default; FPCC_DUAL_OUTPUTS=1 turns it on.
 DUAL_OUTPUTS = _os.environ.get('FPCC_DUAL_OUTPUTS', '0') == '1'
+# Linear(cat(F, occupancy bits)) as one GEMM over an in-memory concatenation (K = C + 16) instead of the occupancy row-bias
+# form (K = C + 1 KB of bias rows per output row read by the epilogue); identical bytes, FPCC_CAT_BITS=0 for the A/B
+CAT_BITS = _os.environ.get('FPCC_CAT_BITS', '1') != '0'
 
 
 def seed_kernel_map(src_caches, dst_caches, coarse_stride, coarse_occ: torch.Tensor, fine: Level):
@@ -295,16 +305,29 @@ class OneScaleMultiStepPredictor(nn.Module):
                 return None
             return nxt[1].as_post_stage(nxt[0]) if j + 1 != S - 1 else nxt[0].as_post_stage(None)
 
+        def cat_buffer(j):
+            """When step j's selection linear emits the int8 input of step j+1's Linear(cat(f, bits)) (fused second stage), it
+            writes the first C columns of that linear's [rows, C + 16] buffer directly (output pitch): no copy, no row bias."""
+            if not CAT_BITS or j + 1 >= S - 1:
+                return None
+            lin = self.pred[j + 1][2]
+            if not (isinstance(lin, LinearIn8W8) and lin.can_cat_bits()):
+                return None
+            return torch.empty((levels[j + 1].n, lin.in_ch - 8 + 16), dtype=torch.int8, device=cur.F.device)
+
         fused = None  # second stage already applied to x.F by the producing linear
+        catbuf = None  # [n_j, C + 16] buffer whose first C columns the producing linear has filled
         for j, block in enumerate(self.pred):
             post = consumer_stage(j)
+            nxt_buf = cat_buffer(j) if post is not None else None
+            out_view = nxt_buf[:, : nxt_buf.shape[1] - 16] if nxt_buf is not None else None
             if j == 0:
                 src, skip = (cur, 0) if cur_q is None else (_with(cur_q, cur), 1)
                 if S > 1:
-                    x = block(src, sel=levels[1].sel(), n_out_rows=levels[1].n, post_requant=post, skip=skip)
+                    x = block(src, sel=levels[1].sel(), n_out_rows=levels[1].n, post_requant=post, skip=skip, out=out_view)
                 else:
                     x = block(src, skip=skip)
-                fused = post
+                fused, catbuf = post, nxt_buf
                 continue
             lv = levels[j]
             f = x.F  # [n_j, C]: features of the occupied children (selection already applied)
@@ -314,14 +337,18 @@ class OneScaleMultiStepPredictor(nn.Module):
                 # PReLU -> Requant -> LinearPReLU(C+8 -> C) on cat(f, bits) -> Conv -> Linear(C -> 8C)[child mask]
                 if fused is not None:
                     q0, q1 = block[1].bit_levels()
-                    f = block[2].forward_with_bits(f, lv.occ, q0, q1)
+                    if catbuf is not None:  # f IS catbuf[:, :C], written there by the producing linear
+                        ops.occ_bits_q8(lv.occ, q0, q1, catbuf[:, catbuf.shape[1] - 16:])
+                        f = block[2].forward_cat_bits(catbuf)
+                    else:
+                        f = block[2].forward_with_bits(f, lv.occ, q0, q1)
                 else:
                     f = linear_with_bits(block[1], block[2], f, lv.occ, prelu=block[0])
                 x = block[3](_with(f, cur, C=lv.C, stride=st))
-                x.F = block[4](x.F, sel=levels[j + 1].sel(), n_out_rows=levels[j + 1].n, post_requant=post)
+                x.F = block[4](x.F, sel=levels[j + 1].sel(), n_out_rows=levels[j + 1].n, post_requant=post, out=out_view)
             else:
                 x = block(_with(f, cur, C=lv.C, stride=st), skip=1 if fused is not None else 0)
-            fused = post
+            fused, catbuf = post, nxt_buf
         return cur, x.F
 
 

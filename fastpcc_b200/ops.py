@@ -304,6 +304,16 @@ def morton_encode(xyz_rows, col0=1, msb_axis=0):
     return codes
 
 
+def occ_bits_q8(occ, q0, q1, out):
+    """the 8 occupancy-bit channels (already requantised to the int8 levels q0 / q1) + 8 zero bytes into the 16-column slice
+    `out` of a [rows, C + 16] int8 buffer (fpcc_occ_bits_q8)"""
+    _need(occ, torch.uint8, 'occ', 1)
+    if out.dtype != torch.int8 or out.dim() != 2 or out.shape != (occ.shape[0], 16) or out.stride(1) != 1:
+        raise RuntimeError('occ_bits_q8: out must be an int8 [rows, 16] column slice')
+    _call('fpcc_occ_bits_q8', _p(occ), occ.shape[0], int(q0), int(q1), out.data_ptr(), out.stride(0), _s(), work={'bytes': 17.0 * occ.shape[0]})
+    return out
+
+
 def gather_rows(rows, idx):
     """rows[idx] for an int32 [n, 4] coordinate tensor and an int64 permutation (the result of torch.argsort)."""
     _need(rows, torch.int32, 'rows', 2)
@@ -434,6 +444,11 @@ def linear(a, weight, ep, sel=None, n_out_rows=None, out=None):
     m, k = a.shape
     if weight.shape[1] != k:
         raise RuntimeError(f'linear: K mismatch {tuple(a.shape)} x {tuple(weight.shape)}')
+    if out is not None and not out.is_contiguous():
+        # int8 rows into a column slice of a wider buffer (fpcc_epilogue::out_ld)
+        if out.dtype != torch.int8 or _ep_out_dtype(ep) != torch.int8 or out.dim() != 2 or out.stride(1) != 1 or out.stride(0) % 16:
+            raise RuntimeError('linear: a strided output must be an int8 column slice with a pitch that is a multiple of 16')
+        ep.out_ld = out.stride(0)
     if sel is None:
         n = weight.shape[0]
         out = torch.empty((m, n), dtype=_ep_out_dtype(ep), device=a.device) if out is None else out

@@ -233,6 +233,10 @@ typedef struct {
      * predictor step, lossl_coord_int/model.py:147-172) leaves its producer once in each form and the stand-alone requant
      * pass over it disappears. */
     int8_t *aux_out;                    /* device [rows, ch] or NULL */
+    /* int8 outputs of the fused kernels (FPCC_OUT_I8, or int32 + fused second stage without aux_out): row pitch of `out` in
+     * elements, 0 = dense.  Lets a producer write the first C columns of the [rows, C + 16] buffer that the next
+     * Linear(cat(F, occupancy bits)) (lossl_coord_int/model.py:63-64) contracts over -- the concatenation costs no copy. */
+    int64_t out_ld;
 } fpcc_epilogue;
 
 /* replaces the 12 requant entry points of binding.cu:118-129 */
@@ -276,6 +280,10 @@ int fpcc_gather_patches(const int8_t *feats, int c, const int32_t *table, int64_
                         int8_t *patches, int kp, void *stream);
 
 /* k-major table for the selection above: table[g*ld + j] = child_parent[j]+1 if child_slot[j]==g else 0 */
+/* The 8 occupancy-bit channels of `cat(F, bin << 23)` after RequantFxpToScaledInt8 (lossl_coord_int/model.py:63-64): byte k
+ * (k = 0..7) of row r is q1 when bit 7-k of occ[r] is set, else q0 (the int8 images of the Q8.23 values 1.0 and 0); bytes 8..15
+ * are zero.  16 bytes per row at out + r * out_ld: the tail columns of the [rows, C + 16] buffer of fpcc_epilogue::out_ld. */
+int fpcc_occ_bits_q8(const uint8_t *occ, int64_t n, int q0, int q1, int8_t *out, int64_t out_ld, void *stream);
 int fpcc_slot_table(const int32_t *child_parent, const uint8_t *child_slot, int n_child, int32_t *table, int64_t ld,
                     void *stream);
 

@@ -537,6 +537,49 @@ def test_dual_output_int32_and_fused_int8(ops, k, n):
         assert (got.cpu().numpy() == y).all() and (aux.cpu().numpy() == want8).all()
 
 
+def test_linear_over_in_memory_concat_of_features_and_occupancy_bits(ops):
+    """Linear(cat(F, bits)) (lossl_coord_int/model.py:63-64) as ONE GEMM with K = C + 16: the requant writes the first C
+    columns of the buffer (fpcc_requant_ld), fpcc_occ_bits_q8 the 8 bit channels + 8 zero columns; a producer with a fused
+    second stage writes its int8 rows there through fpcc_epilogue::out_ld.  Equal to the GEMM over the explicit
+    concatenation and to the occupancy row-bias form."""
+    rng = np.random.default_rng(21)
+    m, c, n = 777, 64, 96
+    x32 = rng.integers(-(1 << 27), 1 << 27, (m, c)).astype(np.int32)
+    occ = rng.integers(1, 256, m).astype(np.uint8)
+    q0, q1 = -7, 93
+    mulr, zpr = np.array([(1 << 30) + 321], np.uint32), np.array([5 << 40], np.int64)
+    f8 = K.requant(x32, np.full(c, mulr[0], np.uint32), zpr, 47, np.int8)
+    bits = ((occ[:, None] >> np.arange(7, -1, -1)[None]) & 1).astype(bool)
+    a_cat = np.concatenate([f8, np.where(bits, q1, q0).astype(np.int8)], 1)
+    w = rng.integers(-127, 128, (n, c + 8)).astype(np.int8)
+    bias = rng.integers(-50000, 50000, n).astype(np.int32)
+    mul = rng.integers(1 << 20, 1 << 23, n).astype(np.uint32)
+    zp = np.array([-3], np.int64)
+    slope = np.array([int(0.2 * (1 << 25))], np.int32)
+    want = K.requant(K.gemm_int8(a_cat, w, None), mul, zp, 30, np.int8, bias=bias, slope=slope)
+    buf = torch.full((m, c + 16), 55, dtype=torch.int8, device='cuda')
+    ops.requant(dev(x32), ops.make_epilogue(dev(mulr), dev(zpr), 47, ops.OUT_I8), out=buf[:, :c])
+    ops.occ_bits_q8(dev(occ), q0, q1, buf[:, c:])
+    assert (buf.cpu().numpy()[:, :c + 8] == a_cat).all() and (buf.cpu().numpy()[:, c + 8:] == 0).all()
+    w_cat = np.concatenate([w, np.zeros((n, 8), np.int8)], 1)
+    ep = ops.make_epilogue(dev(mul), dev(zp), 30, ops.OUT_I8, bias=dev(bias), slope=dev(slope))
+    got = ops.linear(buf, dev(w_cat), ep).cpu().numpy()
+    assert (got == want).all()
+    # a producer with a fused second stage writes its int8 rows into the column slice (output pitch)
+    k2 = 64
+    a2 = rng.integers(-128, 128, (m, k2)).astype(np.int8)
+    w2 = rng.integers(-127, 128, (c, k2)).astype(np.int8)
+    mul1 = rng.integers(1 << 18, 1 << 21, c).astype(np.uint32)
+    y = K.requant(K.gemm_int8(a2, w2, None), mul1, np.zeros(1, np.int64), 10, np.int32)
+    want8 = K.requant(y, np.full(c, mulr[0], np.uint32), zpr, 47, np.int8)
+    buf2 = torch.full((m, c + 16), 55, dtype=torch.int8, device='cuda')
+    ep2 = ops.make_epilogue(dev(mul1), dev(np.zeros(1, np.int64)), 10, ops.OUT_I32, post_requant=(dev(mulr), dev(zpr), 47, None))
+    ret = ops.linear(dev(a2), dev(w2), ep2, out=buf2[:, :c])
+    assert ret.data_ptr() == buf2.data_ptr()
+    b2 = buf2.cpu().numpy()
+    assert (b2[:, :c] == want8).all() and (b2[:, c:] == 55).all()
+
+
 def test_selected_linear_equals_masked_dense(ops):
     """Linear(C->8C) + child mask (model.py:64-66) == occupied-children-only evaluation."""
     rng = np.random.default_rng(4)
