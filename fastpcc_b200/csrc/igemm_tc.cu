@@ -1057,7 +1057,10 @@ __device__ __forceinline__ void pairs_tile_lookup(const TcArgs &a, int tile_m, P
             t -= nt;
         }
     }
-    m->group = g; m->begin = begin; m->end = end;
+    // a tile past the last group (the grid covers an upper bound of the tile count) keeps begin = end = -1; its group index
+    // must still be a valid one: the epilogue restages that group's (bias, mul) before it learns that the tile is empty
+    // (reading one block past the end of the parameter arrays faulted when they ended a mapped region)
+    m->group = g < a.n_groups ? g : a.n_groups - 1; m->begin = begin; m->end = end;
 }
 
 // KIND: 0 = int8 x int8 -> int32 (kind::i8, integer requant epilogue), 1 = fp16, 2 = bf16 (kind::f16, fp32
